@@ -1,0 +1,80 @@
+"""ctypes binding of libtrackkern.so (the C ABI declared in include/trackkern.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C tracklab_b200/csrc``.
+A missing library is a hard error — there is no Python or CPU fallback for the product path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtrackkern.so")
+
+TK_ERRORS = {-1: "TK_ERR_ARG", -2: "TK_ERR_CUDA", -3: "TK_ERR_CAPACITY", -4: "TK_ERR_INFEASIBLE"}
+DEV_STATUS = {1: "track capacity overflow", 2: "detections-per-frame capacity overflow",
+              4: "assignment infeasible", 8: "output capacity overflow", 16: "non-PD innovation covariance"}
+
+
+class TrackKernError(RuntimeError):
+    pass
+
+
+class BytetrackParams(ctypes.Structure):
+    _fields_ = [("track_thresh", ctypes.c_double), ("match_thresh", ctypes.c_double),
+                ("min_confidence", ctypes.c_double), ("track_buffer", ctypes.c_int),
+                ("frame_rate", ctypes.c_int), ("first_id", ctypes.c_int)]
+
+
+_lib = None
+
+
+def _declare(lib):
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    P = ctypes.POINTER
+    sig = {
+        "tk_abi_version": ([], ci),
+        "tk_last_cuda_error": ([], ci),
+        "tk_bytetrack_create": ([P(BytetrackParams), ci, ci, ci, P(vp)], ci),
+        "tk_bytetrack_reset": ([vp, vp], ci),
+        "tk_bytetrack_run": ([vp, vp, vp, ci, vp, vp, vp, vp, vp], ci),
+        "tk_bytetrack_status": ([vp, P(ci), vp], ci),
+        "tk_bytetrack_destroy": ([vp], ci),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+    return sig
+
+
+def load():
+    """Load (once) and return the ctypes handle. Raises TrackKernError when the library is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TrackKernError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). tracklab_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    """Names include/trackkern.h declares (used by the not-gpu ABI test)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "trackkern.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"^\s*int\s+(tk_[a-z0-9_]+)\s*\(", txt, flags=re.M)))
+
+
+def check(code: int, what: str):
+    if code != 0:
+        lib = load()
+        raise TrackKernError(f"{what} failed: {TK_ERRORS.get(code, code)} (last CUDA error {lib.tk_last_cuda_error()})")
+
+
+def status_text(bits: int) -> str:
+    return ", ".join(v for k, v in DEV_STATUS.items() if bits & k) or "ok"

@@ -1,0 +1,63 @@
+// Shared helpers for libtrackkern (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define TK_OK 0
+#define TK_ERR_ARG -1
+#define TK_ERR_CUDA -2
+#define TK_ERR_CAPACITY -3
+#define TK_ERR_INFEASIBLE -4
+
+#define TK_CUDA_TRY(expr)                                   \
+    do {                                                    \
+        cudaError_t _e = (expr);                            \
+        if (_e != cudaSuccess) { tk_set_last_cuda_error((int)_e); return TK_ERR_CUDA; } \
+    } while (0)
+
+void tk_set_last_cuda_error(int e);
+
+// device-side error flags written into a per-sequence status word
+#define TK_DEV_OVERFLOW_TRACKS 1
+#define TK_DEV_OVERFLOW_DETS 2
+#define TK_DEV_LAP_INFEASIBLE 4
+#define TK_DEV_OVERFLOW_OUT 8
+#define TK_DEV_BAD_CHOLESKY 16
+
+namespace tk {
+
+constexpr int WARP = 32;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// IEEE double -> unsigned key with the same total order (for integer min reductions)
+__device__ __forceinline__ unsigned long long ordered_key(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// warp arg-min over (value, index): 2 REDUX + 1 ballot instead of 5 shuffle rounds on 64-bit pairs.
+// Ties are resolved towards the smallest index. Every lane must call it; result is warp-uniform.
+__device__ __forceinline__ void warp_argmin(double val, int idx, double& out_val, int& out_idx) {
+    const unsigned full = 0xffffffffu;
+    unsigned long long k = ordered_key(val);
+    unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    unsigned mhi = __reduce_min_sync(full, hi);
+    unsigned mlo = __reduce_min_sync(full, hi == mhi ? lo : 0xffffffffu);
+    bool win = (hi == mhi) && (lo == mlo);
+    unsigned midx = __reduce_min_sync(full, win ? (unsigned)idx : 0xffffffffu);
+    unsigned b = __ballot_sync(full, win && (unsigned)idx == midx);
+    int src = __ffs(b) - 1;
+    out_val = __shfl_sync(full, val, src);
+    out_idx = (int)midx;
+}
+
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+}  // namespace tk

@@ -1,0 +1,102 @@
+"""Whole-video device trackers: thin Python objects over the stateful C-ABI handles.
+
+PyTorch is used only for device memory and streams; all association arithmetic runs inside
+libtrackkern's kernels.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.TrackKernError(f"{name} must be a CUDA tensor (tracklab_b200 has no CPU path)")
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ByteTrackDevice:
+    """ByteTrack for ``n_seq`` independent videos (C ABI: tk_bytetrack_*).
+
+    Mirrors BYTETracker(**hyperparams) + the wrapper's ``min_confidence`` filter
+    (/root/reference/plugins/track/byte_track/byte_tracker.py:151-165,
+    /root/reference/tracklab/wrappers/track/byte_track_api.py:50-56).
+    """
+
+    def __init__(self, track_thresh=0.6, match_thresh=0.8, track_buffer=30, frame_rate=30,
+                 min_confidence=0.4, first_id=1, n_seq=1, cap_tracks=128, cap_dets=128, device="cuda:0"):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.TrackKernError("CUDA device required")
+        self.device = torch.device(device)
+        self.n_seq, self.cap_tracks, self.cap_dets = n_seq, cap_tracks, cap_dets
+        self.params = _lib.BytetrackParams(track_thresh, match_thresh, min_confidence, track_buffer, frame_rate, first_id)
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tk_bytetrack_create(ctypes.byref(self.params), n_seq, cap_tracks, cap_dets,
+                                                    ctypes.byref(self.handle)), "tk_bytetrack_create")
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tk_bytetrack_reset(self.handle, _stream_ptr()), "tk_bytetrack_reset")
+
+    def run(self, dets: torch.Tensor, offsets: torch.Tensor, out_rows: torch.Tensor | None = None,
+            out_start: torch.Tensor | None = None, out_count: torch.Tensor | None = None):
+        """dets float64[N,7] (device), offsets int32[n_seq, F+1] (device, absolute row indices).
+        Returns (out_rows float64[N,8], out_frame_count int32[n_seq,F], out_count int32[n_seq]) — all
+        device tensors, nothing is synchronised."""
+        _require_cuda(dets, "dets"); _require_cuda(offsets, "offsets")
+        assert dets.dtype == torch.float64 and dets.is_contiguous()
+        assert offsets.dtype == torch.int32 and offsets.is_contiguous() and offsets.shape[0] == self.n_seq
+        n_frames = offsets.shape[1] - 1
+        if out_rows is None:
+            out_rows = torch.empty((max(1, dets.shape[0]), 8), dtype=torch.float64, device=dets.device)
+        if out_start is None:
+            out_start = offsets[:, 0].contiguous()
+        if out_count is None:
+            out_count = torch.zeros(self.n_seq, dtype=torch.int32, device=dets.device)
+        out_fc = torch.empty((self.n_seq, n_frames), dtype=torch.int32, device=dets.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tk_bytetrack_run(self.handle, dets.data_ptr(), offsets.data_ptr(), n_frames,
+                                                 out_rows.data_ptr(), out_start.data_ptr(), out_fc.data_ptr(),
+                                                 out_count.data_ptr(), _stream_ptr()), "tk_bytetrack_run")
+        return out_rows, out_fc, out_count
+
+    def status(self) -> np.ndarray:
+        st = (ctypes.c_int * self.n_seq)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tk_bytetrack_status(self.handle, st, _stream_ptr()), "tk_bytetrack_status")
+        return np.asarray(list(st), dtype=np.int32)
+
+    def check_status(self):
+        st = self.status()
+        if (st != 0).any():
+            raise _lib.TrackKernError("device tracker error: " + "; ".join(
+                f"video {i}: {_lib.status_text(int(s))}" for i, s in enumerate(st) if s))
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.tk_bytetrack_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def rows_to_frames(out_rows: torch.Tensor, out_fc: torch.Tensor, out_start: torch.Tensor, seq: int = 0):
+    """Host helper: split the rows of video ``seq`` per frame -> (rows float64[R,8], frame int32[R])."""
+    fc = out_fc[seq].cpu().numpy()
+    start = int(out_start[seq].item())
+    total = int(fc.sum())
+    rows = out_rows[start:start + total].cpu().numpy()
+    return rows, np.repeat(np.arange(len(fc), dtype=np.int32), fc)
