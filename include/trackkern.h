@@ -19,6 +19,55 @@ int tk_abi_version(void);
 /* last CUDA runtime error code seen by the library (cudaError_t as int), 0 if none */
 int tk_last_cuda_error(void);
 
+
+/* element types for tensor arguments */
+#define TK_DTYPE_F32 0
+#define TK_DTYPE_BF16 1
+
+/* device-side status bits (per video / per call status words) */
+#define TK_STATUS_OVERFLOW_TRACKS 1
+#define TK_STATUS_OVERFLOW_DETS 2
+#define TK_STATUS_LAP_INFEASIBLE 4
+#define TK_STATUS_OVERFLOW_OUT 8
+#define TK_STATUS_BAD_CHOLESKY 16
+
+/* ---- Detector pre-processing: letterbox ---------------------------------------------------------
+ * Replaces rtmlib YOLOX.preprocess (ratio = min(S/h,S/w); cv2.resize INTER_LINEAR; 114-padded SxS canvas,
+ * top-left paste; HWC uint8 -> CHW float) that runs behind
+ *   /root/reference/tracklab/wrappers/bbox_detector/rtmlib_api.py:19-30
+ * src: device uint8 [n_frames, H, W, 3] (16-byte aligned, frame pitch `frame_stride_bytes`);
+ * dst: device [n_frames, 3, S, S] of out_dtype (out_nhwc=1: channels-last storage [n_frames, S, S, 3]); swap_rb=1 turns the engine's RGB frames
+ * (/root/reference/tracklab/utils/cv2.py:54-66) into the BGR order cv2.imread feeds the detector
+ * (rtmlib_api.py:28). *ratio_out (host, optional) receives the letterbox ratio.
+ */
+int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, int W, long long frame_stride_bytes,
+                    void* dst, int out_dtype, int out_nhwc, int S, int pad_value, int swap_rb, double* ratio_out,
+                    void* stream);
+
+/* ---- Detector post-processing: YOLOX decode + threshold + class-aware NMS --------------------------
+ * Replaces rtmlib YOLOX.postprocess / multiclass_nms behind rtmlib_api.py:30 (score_thr 0.7, nms_thr 0.45).
+ * pred: device [n_images, n_anchors, 5+n_classes] (reg xywh raw, obj, cls; logits=1 -> sigmoid applied here),
+ * outputs per image: up to max_out (<=1024) boxes float32 xyxy in original-image pixels, scores, classes,
+ * count; sorted by score descending. status_dev: device int, TK_STATUS_* bits are OR-ed in.
+ */
+int tk_yolox_nms(const void* pred, int pred_dtype, int n_images, int n_anchors, int n_classes, int input_size,
+                 int logits, float ratio, float score_thr, float nms_thr, int max_out, float* out_boxes,
+                 float* out_scores, int* out_cls, int* out_count, int* status_dev, void* stream);
+
+/* ---- Detector wrapper row packing --------------------------------------------------------------------
+ * Replaces RTMLibDetector.process' per-box Series construction (rtmlib_api.py:31-46: clip with
+ * ltrb_to_ltwh(bbox,(W,H)), bbox_conf = 1.0, running id) and the tracker wrappers' row builder
+ * (/root/reference/tracklab/wrappers/track/oc_sort_api.py:33-47): writes double[.,7] rows
+ * [l,t,r,b,conf,cls,det_id]. cursor_dev is a device int[2] = {next row, next frame}, read and advanced by the
+ * call (so consecutive batches of one video chain without host involvement, CUDA-graph friendly): rows are
+ * appended at dets_out[cursor[0]..], frame offsets written to offsets_out[cursor[1] .. cursor[1]+n_images].
+ * fixed_conf < 0 keeps the detector score. keep_class < 0 keeps every class.
+ */
+int tk_pack_detections(const float* boxes, const float* scores, const int* cls, const int* counts, int n_images,
+                       int max_per_image, int keep_class, int img_w, int img_h, double fixed_conf, double category_id,
+                       int* cursor_dev, double* dets_out, int* offsets_out, int dets_cap, int frames_cap,
+                       int* status_dev, void* stream);
+
 /* ---- ByteTrack: whole-video association -------------------------------------------------------
  * Replaces BYTETracker.update called once per frame by the wrapper:
  *   /root/reference/plugins/track/byte_track/byte_tracker.py:167-320  (update)

@@ -1,0 +1,186 @@
+// Frame pre-processing kernels: letterbox (detector input) — HBM-bound byte work.
+//
+// tk_letterbox_u8 replaces rtmlib 0.0.13 YOLOX.preprocess + the HWC->CHW float conversion that runs
+// behind /root/reference/tracklab/wrappers/bbox_detector/rtmlib_api.py:19-30 (un-vendored; restated in
+// oracle/preprocess_np.py): ratio = min(S/h, S/w), cv2.resize(INTER_LINEAR) to (int(w*ratio), int(h*ratio)),
+// paste top-left into a 114-filled SxS canvas, no mean/std. The resize is OpenCV's 8-bit path: 11-bit
+// fixed-point taps, horizontal pass in int32, vertical pass ((b*(S>>4))>>16 summed, +2 >> 2) — restated
+// here integer-exactly so the detector sees the same bytes as the CPU path.
+//
+// B200 shape: one CTA per output row. The one or two source rows an output row needs are contiguous
+// byte spans in HBM, so one elected thread moves them into shared memory with 1-D bulk async copies
+// (cp.async.bulk, the TMA engine, completion on an mbarrier) — fully coalesced, no register staging —
+// and every thread then blends its pixels out of shared memory and writes the three channel planes
+// with coalesced stores. Rows whose vertical weight is zero (exact integer ratios such as 1080p -> 360)
+// are not fetched at all.
+#include <cuda_bf16.h>
+#include "tk_common.cuh"
+#include "trackkern.h"
+
+namespace {
+
+constexpr int LB_THREADS = 256;
+
+struct Tap { int s0, s1, w0, w1; };
+
+// OpenCV resize.cpp (INTER_LINEAR, 8U): fx = (float)((d+0.5)*scale-0.5), floor, clamp, 11-bit weights
+__device__ __forceinline__ Tap linear_tap(int d, int src_n, double scale) {
+    float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+    int s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    if (s < 0) { f = 0.0f; s = 0; }
+    if (s >= src_n - 1) { f = 0.0f; s = src_n - 1; }
+    Tap t;
+    t.s0 = s;
+    t.s1 = min(s + 1, src_n - 1);
+    t.w1 = __float2int_rn(__fmul_rn(f, 2048.0f));
+    t.w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.0f, f), 2048.0f));
+    return t;
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned phase) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(phase));
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <typename OutT> __device__ __forceinline__ OutT cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// src u8 [B, H, W, 3] (row pitch = W*3, frame pitch = frame_stride bytes), dst OutT [B, 3, S, S]
+template <typename OutT>
+__global__ void __launch_bounds__(LB_THREADS)
+letterbox_kernel(const unsigned char* __restrict__ src, size_t frame_stride, int H, int W, OutT* __restrict__ dst,
+                 int S, int rw, int rh, double scale_x, double scale_y, int area2x, int pad, int swap_rb, int nhwc,
+                 const unsigned char* __restrict__ src_end) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int y = blockIdx.x, b = blockIdx.y;
+    // planar [B,3,S,S] or interleaved channels-last [B,S,S,3] (what cuDNN's NHWC tensor-core kernels want)
+    const size_t xs = nhwc ? 3 : 1;
+    OutT* out0 = nhwc ? dst + (((size_t)b * S + y) * S) * 3 : dst + ((size_t)b * 3 + 0) * S * S + (size_t)y * S;
+    OutT* out1 = nhwc ? out0 + 1 : out0 + (size_t)S * S;
+    OutT* out2 = nhwc ? out0 + 2 : out1 + (size_t)S * S;
+    const OutT padv = cvt_out<OutT>((float)pad);
+    if (y >= rh) {  // pure padding row
+        for (int x = threadIdx.x; x < S; x += LB_THREADS) { out0[x * xs] = padv; out1[x * xs] = padv; out2[x * xs] = padv; }
+        return;
+    }
+    Tap ty;
+    if (area2x) { ty.s0 = 2 * y; ty.s1 = 2 * y + 1; ty.w0 = 1; ty.w1 = 1; }
+    else ty = linear_tap(y, H, scale_y);
+    const bool need1 = area2x || ty.w1 != 0;
+    const size_t row_bytes = (size_t)W * 3;
+    const unsigned char* base = src + (size_t)b * frame_stride;
+    const unsigned char* g0 = base + (size_t)ty.s0 * row_bytes;
+    const unsigned char* g1 = base + (size_t)ty.s1 * row_bytes;
+    // 16-byte aligned spans for the bulk copies
+    const size_t a0 = (size_t)g0 & 15, a1 = (size_t)g1 & 15;
+    const unsigned n0 = (unsigned)((a0 + row_bytes + 15) & ~(size_t)15);
+    const unsigned n1 = (unsigned)((a1 + row_bytes + 15) & ~(size_t)15);
+    const size_t pitch = (row_bytes + 31 + 15) & ~(size_t)15;
+    unsigned char* s0 = smem;
+    unsigned char* s1 = smem + pitch;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // the 16-byte rounding may reach past the end of the frame buffer on the very last rows: plain loads there
+    const bool tail = (g0 - a0 + n0 > src_end) || (need1 && (g1 - a1 + n1 > src_end));
+    if (tail) {
+        for (size_t i = threadIdx.x; i < row_bytes; i += LB_THREADS) {
+            s0[a0 + i] = g0[i];
+            if (need1) s1[a1 + i] = g1[i];
+        }
+        __syncthreads();
+    } else {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, n0 + (need1 ? n1 : 0u));
+            bulk_g2s(s0, g0 - a0, n0, &bar);
+            if (need1) bulk_g2s(s1, g1 - a1, n1, &bar);
+        }
+        mbar_wait(&bar, 0);
+    }
+    const unsigned char* r0 = s0 + a0;
+    const unsigned char* r1 = need1 ? s1 + a1 : r0;
+    const int c0 = swap_rb ? 2 : 0, c2 = swap_rb ? 0 : 2;
+    for (int x = threadIdx.x; x < S; x += LB_THREADS) {
+        if (x >= rw) { out0[x * xs] = padv; out1[x * xs] = padv; out2[x * xs] = padv; continue; }
+        int v[3];
+        if (area2x) {
+            const unsigned char* p0 = r0 + 6 * x;
+            const unsigned char* p1 = r1 + 6 * x;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = (p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2;
+        } else {
+            const Tap tx = linear_tap(x, W, scale_x);
+            const unsigned char* p00 = r0 + 3 * tx.s0;
+            const unsigned char* p01 = r0 + 3 * tx.s1;
+            const unsigned char* p10 = r1 + 3 * tx.s0;
+            const unsigned char* p11 = r1 + 3 * tx.s1;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int h0 = p00[c] * tx.w0 + p01[c] * tx.w1;
+                const int h1 = p10[c] * tx.w0 + p11[c] * tx.w1;
+                int o = (((ty.w0 * (h0 >> 4)) >> 16) + ((ty.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                v[c] = min(max(o, 0), 255);
+            }
+        }
+        out0[x * xs] = cvt_out<OutT>((float)v[c0]);
+        out1[x * xs] = cvt_out<OutT>((float)v[1]);
+        out2[x * xs] = cvt_out<OutT>((float)v[c2]);
+    }
+}
+
+}  // namespace
+
+extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, int W, long long frame_stride_bytes,
+                               void* dst, int out_dtype, int out_nhwc, int S, int pad_value, int swap_rb,
+                               double* ratio_out, void* stream) {
+    if (!src || !dst || n_frames <= 0 || H <= 0 || W <= 0 || S <= 0) return TK_ERR_ARG;
+    if (out_dtype != TK_DTYPE_F32 && out_dtype != TK_DTYPE_BF16) return TK_ERR_ARG;
+    // rtmlib: ratio = min(S/h, S/w) in Python floats; resized size = int(dim * ratio)
+    const double ratio = fmin((double)S / (double)H, (double)S / (double)W);
+    const int rw = (int)((double)W * ratio), rh = (int)((double)H * ratio);
+    if (rw <= 0 || rh <= 0 || rw > S || rh > S) return TK_ERR_ARG;
+    if (ratio_out) *ratio_out = ratio;
+    const double scale_x = 1.0 / ((double)rw / (double)W), scale_y = 1.0 / ((double)rh / (double)H);
+    const int area2x = (W == 2 * rw && H == 2 * rh) ? 1 : 0;
+    const size_t pitch = ((size_t)W * 3 + 31 + 15) & ~(size_t)15;
+    const size_t smem = 2 * pitch + 16;
+    if (smem > 200 * 1024) return TK_ERR_CAPACITY;
+    if (((size_t)src & 15) != 0) return TK_ERR_ARG;  // bulk copies round spans down to 16 B
+    const unsigned char* src_end = src + (size_t)(n_frames - 1) * (size_t)frame_stride_bytes + (size_t)H * W * 3;
+    dim3 grid(S, n_frames);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == TK_DTYPE_F32) {
+        TK_CUDA_TRY(cudaFuncSetAttribute(letterbox_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        letterbox_kernel<float><<<grid, LB_THREADS, smem, st>>>(src, (size_t)frame_stride_bytes, H, W, (float*)dst, S, rw, rh,
+                                                               scale_x, scale_y, area2x, pad_value, swap_rb, out_nhwc, src_end);
+    } else {
+        TK_CUDA_TRY(cudaFuncSetAttribute(letterbox_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        letterbox_kernel<__nv_bfloat16><<<grid, LB_THREADS, smem, st>>>(src, (size_t)frame_stride_bytes, H, W,
+                                                                       (__nv_bfloat16*)dst, S, rw, rh, scale_x, scale_y,
+                                                                       area2x, pad_value, swap_rb, out_nhwc, src_end);
+    }
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
