@@ -49,7 +49,7 @@ def _synthetic_pred(rng, B, nc, n_obj):
             for d in (1, 2):
                 if a + d < A:
                     pred[b, a + d] = pred[b, a]
-                    pred[b, a + d, 4] *= 0.97
+                    pred[b, a + d, 4] *= (0.97 if d == 1 else 0.95)  # distinct scores: tie order is a NumPy sort detail
     return pred
 
 
