@@ -86,7 +86,9 @@ typedef struct {
 /* n_seq independent videos tracked side by side (one CTA each); cap_tracks = max live tracks per video
  * (tracked + lost), cap_dets = max detections per frame; both <= 256. */
 int tk_bytetrack_create(const tk_bytetrack_params* p, int n_seq, int cap_tracks, int cap_dets, void** handle);
-int tk_bytetrack_reset(void* handle, void* stream);
+/* keep_id_counter != 0 continues the id numbering across videos like the reference's process-global
+ * BaseTrack._count (basetrack.py:13,35-37); 0 restarts at first_id. */
+int tk_bytetrack_reset(void* handle, int keep_id_counter, void* stream);
 /* Run `n_frames` consecutive frames of every video, continuing from the current tracker state.
  *   dets      device double[N,7] = [l,t,r,b,conf,cls,det_id] rows (oc_sort_api.py:33-47 layout)
  *   offsets   device int[n_seq*(n_frames+1)]: video s, frame f owns rows offsets[s*(n_frames+1)+f .. +f+1)
@@ -100,6 +102,36 @@ int tk_bytetrack_run(void* handle, const double* dets, const int* offsets, int n
 /* Copies the per-video device status words (0 = ok, TK_DEV_* bits otherwise) to host; synchronises `stream`. */
 int tk_bytetrack_status(void* handle, int* status_host, void* stream);
 int tk_bytetrack_destroy(void* handle);
+
+/* ---- OC-SORT: whole-video association ------------------------------------------------------------
+ * Replaces OCSort.update called once per frame by the wrapper:
+ *   /root/reference/plugins/track/oc_sort/ocsort.py:203-334            (update)
+ *   /root/reference/tracklab/wrappers/track/oc_sort_api.py:50-76       (per-frame filter + row layout)
+ * Hyper-parameters: /root/reference/tracklab/configs/modules/track/oc_sort.yaml:4-14.
+ * Same calling convention as tk_bytetrack_*; output rows are [x1,y1,x2,y2,id+1,cls,conf,det_id].
+ */
+#define TK_ASSO_IOU 0
+#define TK_ASSO_GIOU 1
+#define TK_ASSO_DIOU 2
+#define TK_ASSO_CIOU 3
+typedef struct {
+    double det_thresh;     /* oc_sort.yaml: det_thresh (0) */
+    double iou_threshold;  /* iou_threshold (0.2213...) */
+    double inertia;        /* inertia (0.3941...) — weight of the velocity-direction term */
+    double min_confidence; /* wrapper filter (0.4), oc_sort_api.py:54 */
+    int max_age;           /* 50 */
+    int min_hits;          /* 1 */
+    int delta_t;           /* 1 (<= 8) */
+    int asso_func;         /* TK_ASSO_* used by the BYTE / OCR rounds (ocsort.py:266,287); round 1 is plain IoU */
+    int use_byte;          /* false */
+} tk_ocsort_params;
+
+int tk_ocsort_create(const tk_ocsort_params* p, int n_seq, int cap_tracks, int cap_dets, void** handle);
+int tk_ocsort_reset(void* handle, int keep_id_counter, void* stream);
+int tk_ocsort_run(void* handle, const double* dets, const int* offsets, int n_frames, double* out_rows,
+                  const int* out_start, int* out_frame_count, int* out_count, void* stream);
+int tk_ocsort_status(void* handle, int* status_host, void* stream);
+int tk_ocsort_destroy(void* handle);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,42 @@
+"""GPU parity: OC-SORT whole-video kernel (C ABI) vs the committed reference goldens and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import assert_rows_match, load_golden
+from tracklab_b200.synth import make_video
+
+pytestmark = pytest.mark.gpu
+
+GOLDENS = ["ocsort_c1_iou_s1000", "ocsort_giou_s1001", "ocsort_byte_dt3_s1002"]
+
+
+def _run_device(video, hyper, min_conf, cap=128):
+    from tracklab_b200.device_trackers import OCSortDevice, rows_to_frames
+    trk = OCSortDevice(**hyper, min_confidence=min_conf, cap_tracks=cap, cap_dets=cap)
+    dets = torch.from_numpy(video.dets).cuda()
+    offs = torch.from_numpy(video.offsets.astype(np.int32))[None].cuda()
+    rows, fc, cnt = trk.run(dets, offs)
+    trk.check_status()
+    return rows_to_frames(rows, fc, offs[:, 0].contiguous())
+
+
+@pytest.mark.parametrize("name", GOLDENS)
+@pytest.mark.parametrize("cap", [64, 128])
+def test_ocsort_matches_reference_golden(name, cap):
+    g = load_golden(name)
+    video = make_video(**g["gen"])
+    rows, frames = _run_device(video, g["hyper"], g["min_conf"], cap)
+    err = assert_rows_match(rows, frames, g["rows"], g["frames"], box_tol=1e-6)
+    print(name, "max box err", err)
+
+
+@pytest.mark.parametrize("asso", ["iou", "giou", "diou", "ciou"])
+def test_ocsort_matches_oracle_fresh_seed(asso):
+    from oracle.ocsort_np import OCSortOracle
+    video = make_video(seed=21, n_frames=150, n_ids=50, conf_range=(0.2, 1.0))
+    hyper = dict(det_thresh=0.5, max_age=20, min_hits=2, iou_threshold=0.25, delta_t=2, asso_func=asso, inertia=0.3,
+                 use_byte=True)
+    ref_rows, ref_frames = OCSortOracle(**hyper, min_confidence=0.4).run_video(video.dets, video.offsets)
+    rows, frames = _run_device(video, hyper, 0.4)
+    assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1e-6)

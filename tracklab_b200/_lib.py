@@ -26,6 +26,14 @@ class BytetrackParams(ctypes.Structure):
                 ("frame_rate", ctypes.c_int), ("first_id", ctypes.c_int)]
 
 
+class OcsortParams(ctypes.Structure):
+    _fields_ = [("det_thresh", ctypes.c_double), ("iou_threshold", ctypes.c_double), ("inertia", ctypes.c_double),
+                ("min_confidence", ctypes.c_double), ("max_age", ctypes.c_int), ("min_hits", ctypes.c_int),
+                ("delta_t", ctypes.c_int), ("asso_func", ctypes.c_int), ("use_byte", ctypes.c_int)]
+
+
+ASSO_CODES = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3}
+
 _lib = None
 
 
@@ -39,10 +47,15 @@ def _declare(lib):
         "tk_yolox_nms": ([vp, ci, ci, ci, ci, ci, ci, ctypes.c_float, ctypes.c_float, ctypes.c_float, ci, vp, vp, vp, vp, vp, vp], ci),
         "tk_pack_detections": ([vp, vp, vp, vp, ci, ci, ci, ci, ci, cd, cd, vp, vp, vp, ci, ci, vp, vp], ci),
         "tk_bytetrack_create": ([P(BytetrackParams), ci, ci, ci, P(vp)], ci),
-        "tk_bytetrack_reset": ([vp, vp], ci),
+        "tk_bytetrack_reset": ([vp, ci, vp], ci),
         "tk_bytetrack_run": ([vp, vp, vp, ci, vp, vp, vp, vp, vp], ci),
         "tk_bytetrack_status": ([vp, P(ci), vp], ci),
         "tk_bytetrack_destroy": ([vp], ci),
+        "tk_ocsort_create": ([P(OcsortParams), ci, ci, ci, P(vp)], ci),
+        "tk_ocsort_reset": ([vp, ci, vp], ci),
+        "tk_ocsort_run": ([vp, vp, vp, ci, vp, vp, vp, vp, vp], ci),
+        "tk_ocsort_status": ([vp, P(ci), vp], ci),
+        "tk_ocsort_destroy": ([vp], ci),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)

@@ -617,10 +617,11 @@ struct BtHandle {
     int cost_in_smem;
 };
 
-__global__ void bytetrack_reset_kernel(char* base, size_t stride, int cap, int first_id) {
+__global__ void bytetrack_reset_kernel(char* base, size_t stride, int cap, int first_id, int keep_ids) {
     BtDev S = bt_carve(base + (size_t)blockIdx.x * stride, cap);
     if (threadIdx.x == 0) {
-        S.hdr[0] = 0; S.hdr[1] = first_id - 1; S.hdr[2] = 0; S.hdr[3] = 0; S.hdr[4] = 0; S.hdr[5] = cap;
+        // BaseTrack._count is process-global in the reference (basetrack.py:13): keep_ids continues the numbering
+        S.hdr[0] = 0; if (!keep_ids) S.hdr[1] = first_id - 1; S.hdr[2] = 0; S.hdr[3] = 0; S.hdr[4] = 0; S.hdr[5] = cap;
     }
     for (int i = threadIdx.x; i < cap; i += blockDim.x) {
         S.free_list[i] = cap - 1 - i;  // pop order = slot 0, 1, 2, ...
@@ -679,13 +680,14 @@ int tk_bytetrack_create(const tk_bytetrack_params* p, int n_seq, int cap_tracks,
         return TK_ERR_CUDA;
     }
     *handle = h;
-    return tk_bytetrack_reset(h, nullptr);
+    return tk_bytetrack_reset(h, 0, nullptr);
 }
 
-int tk_bytetrack_reset(void* handle, void* stream) {
+int tk_bytetrack_reset(void* handle, int keep_id_counter, void* stream) {
     if (!handle) return TK_ERR_ARG;
     BtHandle* h = (BtHandle*)handle;
-    bytetrack_reset_kernel<<<h->n_seq, 128, 0, (cudaStream_t)stream>>>(h->state, h->state_stride, h->cap, h->first_id);
+    bytetrack_reset_kernel<<<h->n_seq, 128, 0, (cudaStream_t)stream>>>(h->state, h->state_stride, h->cap, h->first_id,
+                                                                      keep_id_counter);
     TK_CUDA_TRY(cudaGetLastError());
     return TK_OK;
 }

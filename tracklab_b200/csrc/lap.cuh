@@ -25,7 +25,7 @@ constexpr int LAP_MAX_COLS = 32 * LAP_K;
 //   C[i*ld + j]  cost of row i (0<=i<nr) and column j (0<=j<nc), nr <= nc <= LAP_MAX_COLS
 //   u[nr], col4row[nr], row4col[nc], path[nc]  scratch visible to the warp (shared memory)
 // On return col4row[i] is the column of row i. Returns false when no finite assignment exists.
-__device__ __noinline__ bool lap_warp(const double* __restrict__ C, int ld, int nr, int nc,
+static __device__ __noinline__ bool lap_warp(const double* __restrict__ C, int ld, int nr, int nc,
                                       double* u, int* col4row, int* row4col, int* path) {
     const int lane = lane_id();
     const int kmax = (nc + 31) >> 5;

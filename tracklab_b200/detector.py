@@ -41,6 +41,9 @@ class YoloxDetectorDevice:
         self.use_graph = use_graph
         self.pred = None
         self.nms_out = None
+        self.time_kernels = False
+        self.kernel_events = []
+        self.variant = variant
         torch.backends.cudnn.benchmark = True
 
     # ---- synthetic-weight calibration ------------------------------------------------------------
@@ -105,7 +108,13 @@ class YoloxDetectorDevice:
                                                              self.max_per_image, status=self.status)
             kernels.pack_detections(boxes, scores, cls, count, W, H, self.cursor, self.dets, self.offsets, self.status)
             return
+        if self.time_kernels:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _, self.ratio = kernels.letterbox(frames, self.size, self.dtype, swap_rb=True, out=self.x)
+        if self.time_kernels:
+            e1.record()
+            self.kernel_events.append(("letterbox_kernel", e0, e1, B))
         if not self.use_graph:
             self._forward_post(W, H)
             return

@@ -22,35 +22,32 @@ def _stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-class ByteTrackDevice:
-    """ByteTrack for ``n_seq`` independent videos (C ABI: tk_bytetrack_*).
+class _VideoTrackerDevice:
+    """Shared driver of the stateful tk_<name>_{create,reset,run,status,destroy} entry points."""
 
-    Mirrors BYTETracker(**hyperparams) + the wrapper's ``min_confidence`` filter
-    (/root/reference/plugins/track/byte_track/byte_tracker.py:151-165,
-    /root/reference/tracklab/wrappers/track/byte_track_api.py:50-56).
-    """
+    _prefix = None
 
-    def __init__(self, track_thresh=0.6, match_thresh=0.8, track_buffer=30, frame_rate=30,
-                 min_confidence=0.4, first_id=1, n_seq=1, cap_tracks=128, cap_dets=128, device="cuda:0"):
+    def _create(self, params, n_seq, cap_tracks, cap_dets, device):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
-            raise _lib.TrackKernError("CUDA device required")
+            raise _lib.TrackKernError("CUDA device required (tracklab_b200 has no CPU path)")
         self.device = torch.device(device)
         self.n_seq, self.cap_tracks, self.cap_dets = n_seq, cap_tracks, cap_dets
-        self.params = _lib.BytetrackParams(track_thresh, match_thresh, min_confidence, track_buffer, frame_rate, first_id)
+        self.params = params
         self.handle = ctypes.c_void_p()
+        self._fn = {k: getattr(self.lib, f"tk_{self._prefix}_{k}") for k in ("create", "reset", "run", "status", "destroy")}
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tk_bytetrack_create(ctypes.byref(self.params), n_seq, cap_tracks, cap_dets,
-                                                    ctypes.byref(self.handle)), "tk_bytetrack_create")
+            _lib.check(self._fn["create"](ctypes.byref(params), n_seq, cap_tracks, cap_dets, ctypes.byref(self.handle)),
+                       f"tk_{self._prefix}_create")
 
-    def reset(self):
+    def reset(self, keep_id_counter: bool = False):
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tk_bytetrack_reset(self.handle, _stream_ptr()), "tk_bytetrack_reset")
+            _lib.check(self._fn["reset"](self.handle, int(keep_id_counter), _stream_ptr()), f"tk_{self._prefix}_reset")
 
     def run(self, dets: torch.Tensor, offsets: torch.Tensor, out_rows: torch.Tensor | None = None,
             out_start: torch.Tensor | None = None, out_count: torch.Tensor | None = None):
         """dets float64[N,7] (device), offsets int32[n_seq, F+1] (device, absolute row indices).
-        Returns (out_rows float64[N,8], out_frame_count int32[n_seq,F], out_count int32[n_seq]) — all
+        Returns (out_rows float64[.,8], out_frame_count int32[n_seq,F], out_count int32[n_seq]) — all
         device tensors, nothing is synchronised."""
         _require_cuda(dets, "dets"); _require_cuda(offsets, "offsets")
         assert dets.dtype == torch.float64 and dets.is_contiguous()
@@ -64,15 +61,15 @@ class ByteTrackDevice:
             out_count = torch.zeros(self.n_seq, dtype=torch.int32, device=dets.device)
         out_fc = torch.empty((self.n_seq, n_frames), dtype=torch.int32, device=dets.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tk_bytetrack_run(self.handle, dets.data_ptr(), offsets.data_ptr(), n_frames,
-                                                 out_rows.data_ptr(), out_start.data_ptr(), out_fc.data_ptr(),
-                                                 out_count.data_ptr(), _stream_ptr()), "tk_bytetrack_run")
+            _lib.check(self._fn["run"](self.handle, dets.data_ptr(), offsets.data_ptr(), n_frames, out_rows.data_ptr(),
+                                       out_start.data_ptr(), out_fc.data_ptr(), out_count.data_ptr(), _stream_ptr()),
+                       f"tk_{self._prefix}_run")
         return out_rows, out_fc, out_count
 
     def status(self) -> np.ndarray:
         st = (ctypes.c_int * self.n_seq)()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tk_bytetrack_status(self.handle, st, _stream_ptr()), "tk_bytetrack_status")
+            _lib.check(self._fn["status"](self.handle, st, _stream_ptr()), f"tk_{self._prefix}_status")
         return np.asarray(list(st), dtype=np.int32)
 
     def check_status(self):
@@ -83,7 +80,7 @@ class ByteTrackDevice:
 
     def close(self):
         if getattr(self, "handle", None) and self.handle.value:
-            self.lib.tk_bytetrack_destroy(self.handle)
+            self._fn["destroy"](self.handle)
             self.handle = ctypes.c_void_p()
 
     def __del__(self):
@@ -91,6 +88,38 @@ class ByteTrackDevice:
             self.close()
         except Exception:
             pass
+
+
+class ByteTrackDevice(_VideoTrackerDevice):
+    """ByteTrack for ``n_seq`` independent videos (C ABI: tk_bytetrack_*).
+
+    Mirrors BYTETracker(**hyperparams) + the wrapper's ``min_confidence`` filter
+    (/root/reference/plugins/track/byte_track/byte_tracker.py:151-165,
+    /root/reference/tracklab/wrappers/track/byte_track_api.py:50-56)."""
+
+    _prefix = "bytetrack"
+
+    def __init__(self, track_thresh=0.6, match_thresh=0.8, track_buffer=30, frame_rate=30,
+                 min_confidence=0.4, first_id=1, n_seq=1, cap_tracks=128, cap_dets=128, device="cuda:0"):
+        self._create(_lib.BytetrackParams(track_thresh, match_thresh, min_confidence, track_buffer, frame_rate, first_id),
+                     n_seq, cap_tracks, cap_dets, device)
+
+
+class OCSortDevice(_VideoTrackerDevice):
+    """OC-SORT for ``n_seq`` independent videos (C ABI: tk_ocsort_*).
+
+    Mirrors OCSort(**hyperparams) (/root/reference/plugins/track/oc_sort/ocsort.py:184-201) + the wrapper filter
+    (/root/reference/tracklab/wrappers/track/oc_sort_api.py:50-56)."""
+
+    _prefix = "ocsort"
+
+    def __init__(self, det_thresh=0.0, max_age=50, min_hits=1, iou_threshold=0.22136877277096445, delta_t=1,
+                 asso_func="giou", inertia=0.3941737016672115, use_byte=False, min_confidence=0.4,
+                 n_seq=1, cap_tracks=128, cap_dets=128, device="cuda:0"):
+        if asso_func not in _lib.ASSO_CODES:
+            raise _lib.TrackKernError(f"asso_func {asso_func!r} not supported on device (iou/giou/diou/ciou)")
+        self._create(_lib.OcsortParams(det_thresh, iou_threshold, inertia, min_confidence, max_age, min_hits, delta_t,
+                                       _lib.ASSO_CODES[asso_func], int(bool(use_byte))), n_seq, cap_tracks, cap_dets, device)
 
 
 def rows_to_frames(out_rows: torch.Tensor, out_fc: torch.Tensor, out_start: torch.Tensor, seq: int = 0):

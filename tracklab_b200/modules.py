@@ -1,0 +1,170 @@
+"""B200-native drop-in modules for the reference engine (``tracklab.pipeline`` API).
+
+``ByteTrack`` and ``OCSORT`` keep the reference wrappers' class names, column contracts, constructor signature
+``(cfg, device, **kwargs)``, ``reset()`` and the result layout
+(/root/reference/tracklab/wrappers/track/byte_track_api.py:14-76, oc_sort_api.py:14-76), but:
+
+  * the per-frame Python tracker is replaced by ONE whole-video kernel launch (libtrackkern, tk_*_run),
+    triggered when the engine hands the video's detections to the module's datapipe
+    (/root/reference/tracklab/engine/offline.py:24) — explicitly allowed by the module API
+    ("datapipe (optional) ... dataloader (optional)", imagelevel_module.py:18-23);
+  * the module's dataloader yields whole-video batches (image ids only): no worker processes, no per-sample
+    image decode (datapipe.py:27-48 decodes the frame for every tracker sample although trackers ignore it),
+    and ``process`` returns the rows of the batch's images from the precomputed device result, so the engine's
+    DataFrame merge (engine.py:180-181) runs once per batch instead of once per frame.
+
+There is no CPU fallback: constructing these modules without CUDA raises.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _lib
+from .device_trackers import ByteTrackDevice, OCSortDevice
+from .pipeline import ImageLevelModule
+
+
+def _cfg_get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+class _VideoBatches:
+    """Iterable the engine treats as the module's DataLoader: yields ``(image_ids, batch)``."""
+
+    def __init__(self, pipe):
+        self.pipe = pipe
+
+    def __iter__(self):
+        ids = self.pipe.image_ids
+        n = self.pipe.frames_per_batch or len(ids)
+        for i in range(0, len(ids), max(1, n)):
+            chunk = ids[i:i + n]
+            yield chunk, {"image_ids": chunk}
+
+    def __len__(self):
+        n = self.pipe.frames_per_batch or max(1, len(self.pipe.image_ids))
+        return (len(self.pipe.image_ids) + n - 1) // max(1, n)
+
+
+class _TrackerDatapipe:
+    """Stands in for EngineDatapipe (datastruct/datapipe.py:5-48): ``update`` receives the video's detections."""
+
+    def __init__(self, module, frames_per_batch):
+        self.module = module
+        self.frames_per_batch = frames_per_batch
+        self.image_ids = []
+
+    def update(self, image_filepaths, img_metadatas, detections):
+        self.image_ids = list(img_metadatas.index)
+        self.module._track_video(img_metadatas, detections)
+
+    def __len__(self):
+        return len(self.image_ids)
+
+
+class _DeviceTrackerModule(ImageLevelModule):
+    input_columns = ["bbox_ltwh", "bbox_conf", "category_id"]
+    output_columns = ["track_id", "track_bbox_ltwh", "track_bbox_conf"]
+    collate_fn = None
+    _device_cls = None
+    _continue_ids = False
+
+    def __init__(self, cfg, device, **kwargs):
+        super().__init__(batch_size=1)
+        if not torch.cuda.is_available():
+            raise _lib.TrackKernError(f"{type(self).__name__} needs a CUDA device: tracklab_b200 has no CPU path")
+        self.cfg = cfg
+        self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
+        self.cap_tracks = int(_cfg_get(cfg, "cap_tracks", 256))
+        self.cap_dets = int(_cfg_get(cfg, "cap_dets", 256))
+        self.frames_per_batch = _cfg_get(cfg, "frames_per_batch", None)
+        hyper = dict(_cfg_get(cfg, "hyperparams", {}) or {})
+        self.tracker = self._device_cls(**hyper, min_confidence=float(_cfg_get(cfg, "min_confidence", 0.4)),
+                                        cap_tracks=self.cap_tracks, cap_dets=self.cap_dets, device=self.device)
+        self._pipe = _TrackerDatapipe(self, self.frames_per_batch)
+        self._result = None
+        self._first_reset = True
+
+    # -- module API --------------------------------------------------------------------------------
+    def reset(self):
+        """New video: drop the tracker state (the reference re-creates the tracker, byte_track_api.py:28-30)."""
+        self.tracker.reset(keep_id_counter=self._continue_ids and not self._first_reset)
+        self._first_reset = False
+        self._result = None
+
+    @property
+    def datapipe(self):
+        return self._pipe
+
+    def dataloader(self, engine=None):
+        return _VideoBatches(self._pipe)
+
+    def preprocess(self, image, detections, metadata):   # never called: the datapipe is overridden
+        return {"input": []}
+
+    def _track_video(self, img_metadatas: pd.DataFrame, detections: pd.DataFrame):
+        """Rows ``[l,t,r,b,conf,cls,det_id]`` of the whole video -> device -> one kernel launch -> cached frame."""
+        image_ids = np.asarray(img_metadatas.index)
+        if detections is None or len(detections) == 0:
+            self._result = pd.DataFrame(columns=["image_id"] + self.output_columns)
+            return
+        pos = {int(i): k for k, i in enumerate(image_ids)}
+        img = detections["image_id"].to_numpy()
+        keep = np.fromiter((int(i) in pos for i in img), dtype=bool, count=len(img))
+        det = detections[keep]
+        frame = np.fromiter((pos[int(i)] for i in det["image_id"].to_numpy()), dtype=np.int64, count=len(det))
+        order = np.argsort(frame, kind="stable")          # rows grouped by frame, detection order kept inside a frame
+        ltwh = np.stack(det["bbox_ltwh"].to_numpy()).astype(np.float64).reshape(-1, 4)[order]
+        rows = np.empty((len(det), 7), dtype=np.float64)
+        rows[:, 0] = ltwh[:, 0]
+        rows[:, 1] = ltwh[:, 1]
+        rows[:, 2] = ltwh[:, 0] + ltwh[:, 2]                # ltwh_to_ltrb (utils/coordinates.py:257-267)
+        rows[:, 3] = ltwh[:, 1] + ltwh[:, 3]
+        rows[:, 4] = det["bbox_conf"].to_numpy(dtype=np.float64)[order]
+        rows[:, 5] = det["category_id"].to_numpy(dtype=np.float64)[order]
+        rows[:, 6] = np.asarray(det.index, dtype=np.float64)[order]
+        counts = np.bincount(frame, minlength=len(image_ids))
+        offsets = np.zeros(len(image_ids) + 1, dtype=np.int32)
+        np.cumsum(counts, out=offsets[1:])
+        if counts.max() > self.cap_dets:
+            raise _lib.TrackKernError(f"{counts.max()} detections in one frame exceed cap_dets={self.cap_dets}")
+        d_dev = torch.from_numpy(rows).to(self.device)
+        o_dev = torch.from_numpy(offsets)[None].to(self.device)
+        out_rows, out_fc, out_cnt = self.tracker.run(d_dev, o_dev)
+        self.tracker.check_status()                          # one synchronisation per video
+        n = int(out_cnt[0].item())
+        res = out_rows[:n].cpu().numpy()
+        fc = out_fc[0].cpu().numpy()
+        frame_of_row = np.repeat(np.arange(len(fc)), fc)
+        ltrb = res[:, :4]
+        self._result = pd.DataFrame({
+            "track_bbox_ltwh": list(np.column_stack([ltrb[:, 0], ltrb[:, 1], ltrb[:, 2] - ltrb[:, 0], ltrb[:, 3] - ltrb[:, 1]])),
+            "track_bbox_conf": res[:, 6],
+            "track_id": res[:, 4],
+            "image_id": image_ids[frame_of_row],
+        }, index=pd.Index(res[:, 7].astype(int), name="idxs"))
+
+    def process(self, batch, detections: pd.DataFrame, metadatas: pd.DataFrame):
+        if len(detections) == 0 or self._result is None or len(self._result) == 0:
+            return []
+        sel = self._result[self._result["image_id"].isin(list(metadatas.index))]
+        if len(sel) == 0:
+            return []
+        assert set(sel.index).issubset(detections.index), \
+            "Mismatch of indexes during the tracking. The results should match the detections."
+        return sel[["track_bbox_ltwh", "track_bbox_conf", "track_id"]]
+
+
+class ByteTrack(_DeviceTrackerModule):
+    """Drop-in for tracklab.wrappers.track.byte_track_api.ByteTrack (same name => same ``module.name``)."""
+    _device_cls = ByteTrackDevice
+    _continue_ids = True   # BaseTrack._count is process-global in the reference (byte_track/basetrack.py:13)
+
+
+class OCSORT(_DeviceTrackerModule):
+    """Drop-in for tracklab.wrappers.track.oc_sort_api.OCSORT."""
+    _device_cls = OCSortDevice
