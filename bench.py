@@ -40,7 +40,7 @@ MIN_CONF = 0.4
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=500)
@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             return
@@ -105,6 +105,29 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------
+def pick_cpu_threads(model, frames, video, cores):
+    """The CPU arm gets the thread count that serves it best: batch-1 convolutions on small feature maps do not
+    scale to every hardware thread of a 100+ core host (oversubscription makes them slower, not faster)."""
+    import torch
+
+    from oracle.pipeline_np import detect_frame
+    best, best_t = None, None
+    cands = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores})
+    for c in cands:
+        torch.set_num_threads(c)
+        detect_frame(model, frames[0])
+        t0 = time.perf_counter()
+        for k in range(2):
+            detect_frame(model, frames[k % len(frames)])
+        dt = (time.perf_counter() - t0) / 2
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+        if dt > 4 * best_t:
+            break
+    torch.set_num_threads(best)
+    return best
+
+
 def run_reference(args):
     """CPU arm: bounded sample of the same workload per step, all host threads torch/BLAS will use."""
     import numpy as np
@@ -118,12 +141,12 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     video = make_video(seed=2000, n_frames=args.frames, n_ids=44)
     n = min(args.ref_frames, args.frames)
     frames = make_frames(video, 0, n, device="cpu").numpy()
     model = build_yolox(args.variant).float().eval()
     offs = video.offsets
+    used = pick_cpu_threads(model, frames, video, cores)
 
     def one_step():
         t0 = time.perf_counter()
@@ -135,12 +158,13 @@ def run_reference(args):
     times = [one_step()[0] for _ in range(args.steps)]
     total = sum(times)
     fps = args.steps * n / total
-    sample = f"first {n} frames of the {args.frames}-frame video per step (detector batch 1, fp32, {cores} threads)"
+    sample = (f"first {n} frames of the {args.frames}-frame video per step (detector batch 1, fp32, {used} of {cores} "
+              "host threads: best of 4/8/16/32/64/all)")
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 detector / f64 association", "data": "synthetic",
             "config": workload_config(args),
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -218,10 +242,12 @@ def run_ours(args):
         return ms, res, last
 
     # ---- HBM-resident run (value) ----
-    timed(frames, args.warmup, False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    timed(frames, args.warmup, False)
+    if rank == 0:
+        sampler.rows.clear()       # keep only samples taken during the timed steps
     pipe.launches = 0
     pipe.kernel_events, det.kernel_events = [], []
     ms, res, _ = timed(frames, args.steps, False, time_kernels=True)
@@ -315,10 +341,10 @@ def cpu_baseline(args, video):
     from tracklab_b200.nets.yolox import build_yolox
     from tracklab_b200.synth import make_frames
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     n = min(args.ref_frames, args.frames)
     frames = make_frames(video, 0, n, device="cpu").numpy()
     model = build_yolox(args.variant).float().eval()
+    used = pick_cpu_threads(model, frames, video, cores)
     detect_track_video(model, frames[:2], video.dets, video.offsets, HYPER, MIN_CONF)
     t0 = time.perf_counter()
     reps = 0
@@ -326,8 +352,9 @@ def cpu_baseline(args, video):
         detect_track_video(model, frames, video.dets, video.offsets, HYPER, MIN_CONF)
         reps += 1
     dt = time.perf_counter() - t0
-    return {"value": reps * n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{reps} x first {n} frames of the same video, detector batch 1 fp32 on {cores} host threads"}
+    return {"value": reps * n / dt, "unit": UNIT, "cores": used, "kind": "port",
+            "sample": f"{reps} x first {n} frames of the same video, detector batch 1 fp32, {used} of {cores} host threads "
+                      "(best of 4/8/16/32/64/all)"}
 
 
 if __name__ == "__main__":

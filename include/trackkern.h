@@ -36,12 +36,14 @@ int tk_last_cuda_error(void);
  * top-left paste; HWC uint8 -> CHW float) that runs behind
  *   /root/reference/tracklab/wrappers/bbox_detector/rtmlib_api.py:19-30
  * src: device uint8 [n_frames, H, W, 3] (16-byte aligned, frame pitch `frame_stride_bytes`);
- * dst: device [n_frames, 3, S, S] of out_dtype (out_nhwc=1: channels-last storage [n_frames, S, S, 3]); swap_rb=1 turns the engine's RGB frames
+ * dst: device tensor of out_dtype; out_layout 0 = planar [n,3,S,S], 1 = channels-last [n,S,S,3],
+ * 2 = YOLOX Focus space-to-depth pre-applied, channels-last [n,S/2,S/2,16] (12 used, 4 zero pad channels the
+ * caller must have zeroed once); swap_rb=1 turns the engine's RGB frames
  * (/root/reference/tracklab/utils/cv2.py:54-66) into the BGR order cv2.imread feeds the detector
  * (rtmlib_api.py:28). *ratio_out (host, optional) receives the letterbox ratio.
  */
 int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, int W, long long frame_stride_bytes,
-                    void* dst, int out_dtype, int out_nhwc, int S, int pad_value, int swap_rb, double* ratio_out,
+                    void* dst, int out_dtype, int out_layout, int S, int pad_value, int swap_rb, double* ratio_out,
                     void* stream);
 
 /* ---- Detector post-processing: YOLOX decode + threshold + class-aware NMS --------------------------
@@ -67,6 +69,17 @@ int tk_pack_detections(const float* boxes, const float* scores, const int* cls, 
                        int max_per_image, int keep_class, int img_w, int img_h, double fixed_conf, double category_id,
                        int* cursor_dev, double* dets_out, int* offsets_out, int dets_cap, int frames_cap,
                        int* status_dev, void* stream);
+
+/* ---- Backbone epilogues (channels-last bf16; the convolutions themselves stay in cuDNN) ----------------
+ * Replace the separate bias / activation / concat / max-pool / up-sampling passes the reference's runtimes
+ * execute between convolutions (rtmlib_api.py:19-30 -> onnxruntime; strong_sort/deep/models/resnet.py:342-361).
+ * act: 0 none, 1 SiLU, 2 ReLU, 3 ReLU applied after the residual add. Pitches/offsets in elements, multiples of 8.
+ */
+int tk_bias_act_nhwc(const void* src, const float* bias, void* dst, const void* residual, long long n_pixels, int channels,
+                     int dst_pitch, int dst_offset, int res_pitch, int res_offset, int act, void* stream);
+int tk_spp_nhwc(const void* x, void* dst, int n_images, int H, int W, int channels, int dst_pitch, int dst_offset, void* stream);
+int tk_upsample2x_nhwc(const void* src, int src_pitch, int src_offset, void* dst, int n_images, int h, int w, int channels,
+                       int dst_pitch, int dst_offset, void* stream);
 
 /* ---- ByteTrack: whole-video association -------------------------------------------------------
  * Replaces BYTETracker.update called once per frame by the wrapper:

@@ -1,0 +1,23 @@
+"""Run one whole-video tracker launch (for ncu captures): python tools/run_tracker_only.py [bytetrack|ocsort] [frames]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from tracklab_b200.synth import make_video
+from tracklab_b200.device_trackers import ByteTrackDevice, OCSortDevice
+
+kind = sys.argv[1] if len(sys.argv) > 1 else "bytetrack"
+F = int(sys.argv[2]) if len(sys.argv) > 2 else 100
+cap = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+video = make_video(seed=2000, n_frames=F, n_ids=44)
+dets = torch.from_numpy(video.dets).cuda()
+offs = torch.from_numpy(video.offsets.astype(np.int32))[None].cuda()
+trk = (ByteTrackDevice if kind == "bytetrack" else OCSortDevice)(cap_tracks=cap, cap_dets=cap)
+for _ in range(3):
+    trk.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rows, fc, cnt = trk.run(dets, offs)
+    e1.record()
+    torch.cuda.synchronize()
+    print(kind, F, "frames:", e0.elapsed_time(e1) * 1e3 / F, "us/frame", int(cnt.item()), "rows")
+trk.check_status()

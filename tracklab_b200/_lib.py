@@ -46,6 +46,9 @@ def _declare(lib):
         "tk_letterbox_u8": ([vp, ci, ci, ci, ctypes.c_longlong, vp, ci, ci, ci, ci, ci, P(cd), vp], ci),
         "tk_yolox_nms": ([vp, ci, ci, ci, ci, ci, ci, ctypes.c_float, ctypes.c_float, ctypes.c_float, ci, vp, vp, vp, vp, vp, vp], ci),
         "tk_pack_detections": ([vp, vp, vp, vp, ci, ci, ci, ci, ci, cd, cd, vp, vp, vp, ci, ci, vp, vp], ci),
+        "tk_bias_act_nhwc": ([vp, vp, vp, vp, ctypes.c_longlong, ci, ci, ci, ci, ci, ci, vp], ci),
+        "tk_spp_nhwc": ([vp, vp, ci, ci, ci, ci, ci, ci, vp], ci),
+        "tk_upsample2x_nhwc": ([vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_bytetrack_create": ([P(BytetrackParams), ci, ci, ci, P(vp)], ci),
         "tk_bytetrack_reset": ([vp, ci, vp], ci),
         "tk_bytetrack_run": ([vp, vp, vp, ci, vp, vp, vp, vp, vp], ci),

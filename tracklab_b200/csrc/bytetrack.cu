@@ -146,7 +146,7 @@ constexpr double W_POS = 1.0 / 20;
 constexpr double W_VEL = 1.0 / 160;
 
 // KalmanFilter.update (kalman_filter.py:194-226) incl. project (:126-153) for one track
-__device__ void bt_kf_update(BtDev& S, int slot, const float* detbox) {
+__device__ __noinline__ void bt_kf_update(BtDev& S, int slot, const float* detbox) {
     double m[8], P[64], z[4], r[4];
     double* gm = S.mean + (size_t)slot * 8;
     double* gP = S.cov + (size_t)slot * 64;
@@ -169,7 +169,7 @@ __device__ void bt_kf_update(BtDev& S, int slot, const float* detbox) {
 
 // KalmanFilter.multi_predict for one track (kalman_filter.py:155-192); q in float32 when the whole
 // pool still carries float32 means (NumPy promotion of np.asarray([...float32 means...])).
-__device__ void bt_kf_predict(BtDev& S, int slot, bool pool_f32) {
+__device__ __noinline__ void bt_kf_predict(BtDev& S, int slot, bool pool_f32) {
     double m[8], P[64], q[8];
     double* gm = S.mean + (size_t)slot * 8;
     double* gP = S.cov + (size_t)slot * 64;
@@ -216,32 +216,30 @@ __device__ void bt_kf_initiate(BtDev& S, int slot, const float* detbox) {
 
 struct BtShared {
     // sizes
+    int lap_ok;
     int nd, nh, nl, npool, nconf, nunc, nrest, nleft;
     int n_udet1, n_utrk1, n_births, n_lostnow, all_f32;
     int n_tracked, n_lost;
 };
 
-// Solve one association. rows_are_a == (na <= nb). cost (already limit-reduced) is stored with the smaller
-// side as rows. On return match_a[i] = j or -1, match_b[j] = i or -1.
-__device__ void solve_assignment(const double* C, int ld, int na, int nb, int* match_a, int* match_b,
-                                 double* u, int* col4row, int* row4col, int* path, int* status) {
+// Solve one association. cost (already limit-reduced) is stored with the smaller side as rows and leading
+// dimension lap_pitch(cols). On return match_a[i] = j or -1, match_b[j] = i or -1.
+__device__ void solve_assignment(const double* C, int na, int nb, int* match_a, int* match_b,
+                                 double* u, int* col4row, int* row4col, int* path, int* ok_flag, int* status) {
     for (int i = threadIdx.x; i < na; i += blockDim.x) match_a[i] = -1;
     for (int j = threadIdx.x; j < nb; j += blockDim.x) match_b[j] = -1;
     __syncthreads();
     if (na == 0 || nb == 0) return;
     const bool a_rows = na <= nb;
     const int nr = a_rows ? na : nb, nc = a_rows ? nb : na;
-    if (warp_id() == 0) {
-        const bool ok = lap_warp(C, ld, nr, nc, u, col4row, row4col, path);
-        if (!ok && lane_id() == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE);
-        if (ok) {
-            for (int r = lane_id(); r < nr; r += 32) {
-                const int c = col4row[r];
-                if (c >= 0 && C[(size_t)r * ld + c] < 0.0) {  // pairs at/above the limit carry cost 0
-                    if (a_rows) { match_a[r] = c; match_b[c] = r; }
-                    else { match_a[c] = r; match_b[r] = c; }
-                }
-            }
+    const int ld = lap_pitch(nc);
+    const bool ok = lap_solve_cta(C, ld, nr, nc, true, u, col4row, row4col, path, ok_flag);
+    if (!ok) { if (threadIdx.x == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); return; }
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        const int c = col4row[r];
+        if (c >= 0 && C[(size_t)r * ld + c] < 0.0) {  // pairs at/above the limit carry cost 0
+            if (a_rows) { match_a[r] = c; match_b[c] = r; }
+            else { match_a[c] = r; match_b[r] = c; }
         }
     }
     __syncthreads();
@@ -360,7 +358,7 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
         // ---- D. first association: fused IoU/score cost, limit match_thresh ----------------------
         {
             const bool a_rows = npool <= nh;
-            const int ld = a_rows ? nh : npool;
+            const int ld = lap_pitch(a_rows ? nh : npool);
             for (int e = tid; e < npool * nh; e += BT_THREADS) {
                 const int it = e / nh, jd = e % nh;
                 const int di = d_high[jd];
@@ -371,7 +369,7 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
                 if (a_rows) cost[(size_t)it * ld + jd] = red; else cost[(size_t)jd * ld + it] = red;
             }
             __syncthreads();
-            solve_assignment(cost, ld, npool, nh, match_a, match_b, lap_u, col4row, row4col, path, status);
+            solve_assignment(cost, npool, nh, match_a, match_b, lap_u, col4row, row4col, path, &sh->lap_ok, status);
         }
         // matched pool tracks: update / re_activate (byte_tracker.py:229-237)
         for (int k = tid; k < npool; k += BT_THREADS) {
@@ -402,7 +400,7 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
         __syncthreads();
         {
             const bool a_rows = nrest <= nl;
-            const int ld = a_rows ? nl : nrest;
+            const int ld = lap_pitch(a_rows ? nl : nrest);
             for (int e = tid; e < nrest * nl; e += BT_THREADS) {
                 const int it = e / nl, jd = e % nl;
                 const float dist = iou_dist_p1(t_tlbr + 4 * it, d_tlbr + 4 * d_low[jd]);
@@ -410,7 +408,7 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
                 if (a_rows) cost[(size_t)it * ld + jd] = red; else cost[(size_t)jd * ld + it] = red;
             }
             __syncthreads();
-            solve_assignment(cost, ld, nrest, nl, match_a, match_b, lap_u, col4row, row4col, path, status);
+            solve_assignment(cost, nrest, nl, match_a, match_b, lap_u, col4row, row4col, path, &sh->lap_ok, status);
         }
         for (int k = tid; k < nrest; k += BT_THREADS) {
             const int s = rest[k];
@@ -439,7 +437,7 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
         __syncthreads();
         {
             const bool a_rows = nunc <= nleft;
-            const int ld = a_rows ? nleft : nunc;
+            const int ld = lap_pitch(a_rows ? nleft : nunc);
             for (int e = tid; e < nunc * nleft; e += BT_THREADS) {
                 const int it = e / nleft, jd = e % nleft;
                 const int di = d_left[jd];
@@ -450,7 +448,7 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
                 if (a_rows) cost[(size_t)it * ld + jd] = red; else cost[(size_t)jd * ld + it] = red;
             }
             __syncthreads();
-            solve_assignment(cost, ld, nunc, nleft, match_a, match_b, lap_u, col4row, row4col, path, status);
+            solve_assignment(cost, nunc, nleft, match_a, match_b, lap_u, col4row, row4col, path, &sh->lap_ok, status);
         }
         for (int k = tid; k < nunc; k += BT_THREADS) {
             const int s = unconf[k];
@@ -664,10 +662,10 @@ int tk_bytetrack_create(const tk_bytetrack_params* p, int n_seq, int cap_tracks,
     h->state_stride = (bt_state_bytes(cap_tracks) + 255) & ~(size_t)255;
     h->state = nullptr; h->cost = nullptr;
     const size_t fixed = bt_smem_fixed(cap_tracks, cap_dets);
-    const size_t cost_bytes = (size_t)cap_tracks * cap_dets * sizeof(double);
+    const size_t cost_bytes = (size_t)(cap_tracks + 1) * (cap_dets + 1) * sizeof(double);
     h->cost_in_smem = (fixed + cost_bytes <= 200 * 1024) ? 1 : 0;
     h->smem_bytes = fixed + (h->cost_in_smem ? cost_bytes : 0);
-    h->cost_stride = (size_t)cap_tracks * cap_dets;
+    h->cost_stride = (size_t)(cap_tracks + 1) * (cap_dets + 1);
     cudaError_t e = cudaMalloc((void**)&h->state, h->state_stride * n_seq);
     if (e == cudaSuccess && !h->cost_in_smem) e = cudaMalloc((void**)&h->cost, h->cost_stride * sizeof(double) * n_seq);
     if (e == cudaSuccess)

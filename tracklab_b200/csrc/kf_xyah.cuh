@@ -32,8 +32,11 @@ __device__ __forceinline__ void kf8_predict(double* __restrict__ m, double* __re
     for (int i = 0; i < 8; ++i) P[i * 9] = P[i * 9] + q[i];
 }
 
-// lower Cholesky of the 4x4 S = P[:4,:4] + diag(r); returns false when S is not positive definite
-__device__ __forceinline__ bool kf8_chol4(const double* __restrict__ P, const double* r, double* L /*16*/, double* S /*16*/) {
+// lower Cholesky of the 4x4 S = P[:4,:4] + diag(r); returns false when S is not positive definite.
+// invd[i] = 1 / L[i][i]: the factorisation and the triangular solves multiply by these four reciprocals
+// instead of issuing ~80 fp64 divisions per update (each a ~35-instruction subroutine on sm_100a).
+__device__ __forceinline__ bool kf8_chol4(const double* __restrict__ P, const double* r, double* L /*16*/, double* S /*16*/,
+                                          double* invd /*4*/) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -47,21 +50,22 @@ __device__ __forceinline__ bool kf8_chol4(const double* __restrict__ P, const do
         ok = ok && (d > 0.0);
         const double ljj = sqrt(d);
         L[j * 4 + j] = ljj;
+        invd[j] = 1.0 / ljj;
 #pragma unroll
         for (int i = j + 1; i < 4; ++i) {
             double s = S[i * 4 + j];
 #pragma unroll
             for (int k = 0; k < j; ++k) s -= L[i * 4 + k] * L[j * 4 + k];
-            L[i * 4 + j] = s / ljj;
+            L[i * 4 + j] = s * invd[j];
         }
     }
     return ok;
 }
 
 // Measurement update with z[4] and measurement-noise variances r[4] (diagonal).
-__device__ __forceinline__ bool kf8_update(double* __restrict__ m, double* __restrict__ P, const double* z, const double* r) {
-    double L[16], S[16];
-    const bool ok = kf8_chol4(P, r, L, S);
+static __device__ __noinline__ bool kf8_update(double* __restrict__ m, double* __restrict__ P, const double* z, const double* r) {
+    double L[16], S[16], invd[4];
+    const bool ok = kf8_chol4(P, r, L, S, invd);
     // gain K[8][4]: solve S X = (P H^T)^T column by column, K = X^T
     double K[32];
 #pragma unroll
@@ -72,14 +76,14 @@ __device__ __forceinline__ bool kf8_update(double* __restrict__ m, double* __res
             double s = P[c * 8 + i];
 #pragma unroll
             for (int k = 0; k < i; ++k) s -= L[i * 4 + k] * y[k];
-            y[i] = s / L[i * 4 + i];
+            y[i] = s * invd[i];
         }
 #pragma unroll
         for (int i = 3; i >= 0; --i) {
             double s = y[i];
 #pragma unroll
             for (int k = i + 1; k < 4; ++k) s -= L[k * 4 + i] * y[k];
-            y[i] = s / L[i * 4 + i];
+            y[i] = s * invd[i];
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) K[c * 4 + i] = y[i];
@@ -118,14 +122,14 @@ __device__ __forceinline__ bool kf8_update(double* __restrict__ m, double* __res
 }
 
 // squared Mahalanobis distance of z[4] to (H m, H P H^T + diag(r)) given the Cholesky factor L of S
-__device__ __forceinline__ double kf8_maha(const double* m, const double* L, const double* z) {
+__device__ __forceinline__ double kf8_maha(const double* m, const double* L, const double* invd, const double* z) {
     double y[4], acc = 0.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         double s = z[i] - m[i];
 #pragma unroll
         for (int k = 0; k < i; ++k) s -= L[i * 4 + k] * y[k];
-        y[i] = s / L[i * 4 + i];
+        y[i] = s * invd[i];
         acc += y[i] * y[i];
     }
     return acc;

@@ -1,0 +1,167 @@
+// Channels-last (NHWC) bf16 epilogue kernels around the cuDNN convolutions of the detector / ReID backbones.
+//
+// The reference runs these networks in third-party runtimes (onnxruntime / torch) where every convolution is
+// followed by separate bias, activation, concat, pooling and up-sampling passes over HBM
+// (/root/reference/tracklab/wrappers/bbox_detector/rtmlib_api.py:19-30 -> rtmlib/onnxruntime;
+//  /root/reference/plugins/track/strong_sort/deep/models/resnet.py:342-361). On B200 the convolutions themselves
+// stay in cuDNN (tensor cores, per BASELINE.json north_star); everything between them is HBM-bound byte work and
+// is collapsed here into single passes that also write straight into channel slices of the concat buffers,
+// so torch.cat / separate SiLU / separate bias / max-pool / upsample kernels disappear:
+//   tk_bias_act_nhwc   dst[..., off:off+C] = act(src + bias) (+ residual)      16-byte vector loads/stores
+//   tk_spp_nhwc        dst = [x, pool5(x), pool9(x), pool13(x)] (SPP bottleneck) one read, four slices written
+//   tk_upsample2x_nhwc dst[..., off:off+C] = nearest-2x(src)
+#include <cuda_bf16.h>
+#include "tk_common.cuh"
+#include "trackkern.h"
+
+namespace {
+
+struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// src [n_pix, C] contiguous; dst / res rows of pitch dst_pitch / res_pitch elements, channel offsets given.
+__global__ void __launch_bounds__(256)
+bias_act_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst,
+                const __nv_bfloat16* __restrict__ res, long long n_vec, int c_vec, int dst_pitch, int dst_off,
+                int res_pitch, int res_off, int act) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / c_vec;
+        const int cv = (int)(i - pix * c_vec);
+        const bf16x8 x = *reinterpret_cast<const bf16x8*>(src + i * 8);
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + cv * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + cv * 8 + 4);
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(x.v[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        if (act == 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+        } else if (act == 2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+        }
+        if (res) {
+            const bf16x8 r = *reinterpret_cast<const bf16x8*>(res + pix * res_pitch + res_off + cv * 8);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(r.v[k]); f[2 * k] += t.x; f[2 * k + 1] += t.y; }
+            if (act == 3) {   // residual first, then ReLU (ResNet bottleneck tail)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+            }
+        }
+        bf16x8 o;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+        *reinterpret_cast<bf16x8*>(dst + pix * dst_pitch + dst_off + cv * 8) = o;
+    }
+}
+
+// SPP: x [B, H, W, C] -> dst [B, H, W, 4C] = [x | max5 | max9 | max13] (stride 1, -inf padding).
+// max9 = max5(max5), max13 = max5(max9) exactly. One CTA per (image, 8-channel group), tile in shared memory.
+__global__ void __launch_bounds__(256)
+spp_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dst, int H, int W, int C, int dst_pitch, int dst_off) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    bf16x8* a = reinterpret_cast<bf16x8*>(smem);   // [H*W]
+    bf16x8* b = a + H * W;
+    const int img = blockIdx.y, cg = blockIdx.x;
+    const int n = H * W;
+    const __nv_bfloat16* xi = x + (size_t)img * n * C + cg * 8;
+    __nv_bfloat16* di = dst + (size_t)img * n * dst_pitch + dst_off + cg * 8;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) {
+        const bf16x8 v = *reinterpret_cast<const bf16x8*>(xi + (size_t)p * C);
+        a[p] = v;
+        *reinterpret_cast<bf16x8*>(di + (size_t)p * dst_pitch) = v;
+    }
+    __syncthreads();
+    bf16x8* in = a;
+    bf16x8* out = b;
+    for (int stage = 1; stage <= 3; ++stage) {
+        for (int p = threadIdx.x; p < n; p += blockDim.x) {
+            const int y = p / W, xx = p % W;
+            bf16x8 m = in[p];
+            for (int dy = -2; dy <= 2; ++dy) {
+                const int yy = y + dy;
+                if (yy < 0 || yy >= H) continue;
+                for (int dx = -2; dx <= 2; ++dx) {
+                    const int xc = xx + dx;
+                    if (xc < 0 || xc >= W) continue;
+                    const bf16x8 t = in[yy * W + xc];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) m.v[k] = __hmax2(m.v[k], t.v[k]);
+                }
+            }
+            out[p] = m;
+            *reinterpret_cast<bf16x8*>(di + (size_t)p * dst_pitch + (size_t)stage * C) = m;
+        }
+        __syncthreads();
+        bf16x8* t = in; in = out; out = t;
+    }
+}
+
+// nearest 2x: src [B, h, w, C] -> dst [B, 2h, 2w, dst_pitch] at channel offset
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __nv_bfloat16* __restrict__ src, int src_pitch, int src_off, __nv_bfloat16* __restrict__ dst,
+                  long long n_vec, int h, int w, int c_vec, int dst_pitch, int dst_off) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % c_vec);
+        long long p = i / c_vec;            // output pixel index over [B, 2h, 2w]
+        const int ox = (int)(p % (2 * w)); p /= (2 * w);
+        const int oy = (int)(p % (2 * h));
+        const long long bimg = p / (2 * h);
+        const long long sp = (bimg * h + (oy >> 1)) * w + (ox >> 1);
+        const bf16x8 v = *reinterpret_cast<const bf16x8*>(src + sp * src_pitch + src_off + cv * 8);
+        const long long dp = (bimg * 2 * h + oy) * (2 * w) + ox;
+        *reinterpret_cast<bf16x8*>(dst + dp * dst_pitch + dst_off + cv * 8) = v;
+    }
+}
+
+inline int grid_for(long long n_vec) {
+    long long blocks = (n_vec + 255) / 256;
+    const long long cap = 148LL * 16;   // 16 resident CTAs of 256 threads per SM, grid-stride beyond that
+    return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int tk_bias_act_nhwc(const void* src, const float* bias, void* dst, const void* residual, long long n_pixels, int channels,
+                     int dst_pitch, int dst_offset, int res_pitch, int res_offset, int act, void* stream) {
+    if (!src || !bias || !dst || n_pixels <= 0 || channels <= 0) return TK_ERR_ARG;
+    if ((channels & 7) || (dst_pitch & 7) || (dst_offset & 7) || (residual && ((res_pitch & 7) || (res_offset & 7)))) return TK_ERR_ARG;
+    if (((size_t)src & 15) || ((size_t)dst & 15) || ((size_t)bias & 15) || (residual && ((size_t)residual & 15))) return TK_ERR_ARG;
+    const long long n_vec = n_pixels * (channels / 8);
+    bias_act_kernel<<<grid_for(n_vec), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, bias, (__nv_bfloat16*)dst, (const __nv_bfloat16*)residual, n_vec, channels / 8, dst_pitch,
+        dst_offset, res_pitch, res_offset, act);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_spp_nhwc(const void* x, void* dst, int n_images, int H, int W, int channels, int dst_pitch, int dst_offset, void* stream) {
+    if (!x || !dst || n_images <= 0 || H <= 0 || W <= 0 || (channels & 7) || (dst_pitch & 7) || (dst_offset & 7)) return TK_ERR_ARG;
+    const size_t smem = 2 * (size_t)H * W * 16;
+    if (smem > 200 * 1024) return TK_ERR_CAPACITY;
+    TK_CUDA_TRY(cudaFuncSetAttribute(spp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(channels / 8, n_images);
+    spp_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)dst, H, W, channels, dst_pitch,
+                                                          dst_offset);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_upsample2x_nhwc(const void* src, int src_pitch, int src_offset, void* dst, int n_images, int h, int w, int channels,
+                       int dst_pitch, int dst_offset, void* stream) {
+    if (!src || !dst || n_images <= 0 || h <= 0 || w <= 0) return TK_ERR_ARG;
+    if ((channels & 7) || (dst_pitch & 7) || (dst_offset & 7) || (src_pitch & 7) || (src_offset & 7)) return TK_ERR_ARG;
+    const long long n_vec = (long long)n_images * 4 * h * w * (channels / 8);
+    upsample2x_kernel<<<grid_for(n_vec), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_pitch, src_offset,
+                                                                       (__nv_bfloat16*)dst, n_vec, h, w, channels / 8,
+                                                                       dst_pitch, dst_offset);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+}  // extern "C"

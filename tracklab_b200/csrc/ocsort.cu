@@ -281,25 +281,24 @@ __device__ void oc_track_miss(OcDev& S, int s) {
 }
 
 struct OcShared {
+    int lap_ok;
     int nd, nlo, nt, shortcut, n_ud, n_ut, n_pairs, sorted_ud, n_births, n_out;
     int rowmax, colmax, maxflag;
 };
 
-// Solve min-cost full assignment of the smaller side (no limit). pairs as match_d[d] = t / -1.
-__device__ void oc_solve(const double* C, int ld, int nd, int nt, int* match_d, double* u, int* col4row, int* row4col,
-                         int* path, int* status) {
+// Solve the min-cost full assignment of the smaller side (no limit). match_d[d] = t or -1.
+// C is stored with the smaller side as rows and leading dimension lap_pitch(cols).
+__device__ void oc_solve(const double* C, int nd, int nt, int* match_d, double* u, int* col4row, int* row4col,
+                         int* path, int* ok_flag, int* status) {
     for (int i = threadIdx.x; i < nd; i += blockDim.x) match_d[i] = -1;
     __syncthreads();
     const bool d_rows = nd <= nt;
     const int nr = d_rows ? nd : nt, nc = d_rows ? nt : nd;
-    if (warp_id() == 0) {
-        const bool ok = lap_warp(C, ld, nr, nc, u, col4row, row4col, path);
-        if (!ok && lane_id() == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE);
-        if (ok)
-            for (int r = lane_id(); r < nr; r += 32) {
-                const int c = col4row[r];
-                if (d_rows) match_d[r] = c; else match_d[c] = r;
-            }
+    const bool ok = lap_solve_cta(C, lap_pitch(nc), nr, nc, false, u, col4row, row4col, path, ok_flag);
+    if (!ok) { if (threadIdx.x == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); return; }
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        const int c = col4row[r];
+        if (d_rows) match_d[r] = c; else match_d[c] = r;
     }
     __syncthreads();
 }
@@ -333,7 +332,7 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
     unsigned char* flag_d = (unsigned char*)take(capd);
     unsigned char* flag_t = (unsigned char*)take(cap);
     OcShared* sh = (OcShared*)take(sizeof(OcShared));
-    double* iou_m = cost_in_smem ? (double*)take(sizeof(double) * (size_t)cap * capd) : cost_scratch + (size_t)seq * cost_stride * 2;
+    double* iou_m = cost_in_smem ? (double*)take(sizeof(double) * (size_t)(cap + 1) * (capd + 1)) : cost_scratch + (size_t)seq * cost_stride * 2;
     double* cost = cost_in_smem ? (double*)take(0) : iou_m + cost_stride;
 
     int* status = &S.hdr[4];
@@ -419,7 +418,7 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
         for (int i = tid; i < nt; i += OC_THREADS) colcnt[i] = 0;
         __syncthreads();
         const bool d_rows = nd <= nt;
-        const int ld = d_rows ? nt : nd;
+        const int ld = lap_pitch(d_rows ? nt : nd);
         if (nt > 0) {
             for (int e = tid; e < nd * nt; e += OC_THREADS) {
                 const int d = e / nt, t = e % nt;
@@ -456,7 +455,7 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
                         if (iou_m[e] > prm.iou_threshold) match_d[e / nt] = e % nt;
                     __syncthreads();
                 } else {
-                    oc_solve(cost, ld, nd, nt, match_d, lap_u, col4row, row4col, path, status);
+                    oc_solve(cost, nd, nt, match_d, lap_u, col4row, row4col, path, &sh->lap_ok, status);
                 }
             }
         }
@@ -487,7 +486,7 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
             if (tid == 0) sh->maxflag = 0;
             __syncthreads();
             const bool dr = nlo <= nut;
-            const int l2 = dr ? nut : nlo;
+            const int l2 = lap_pitch(dr ? nut : nlo);
             for (int e = tid; e < nlo * nut; e += OC_THREADS) {
                 const int d = e / nut, t = e % nut;
                 const double v = asso_value(prm.asso, D + (size_t)d_lo[d] * 7, trk_box + 4 * un_t[t]);
@@ -497,7 +496,7 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
             }
             __syncthreads();
             if (sh->maxflag) {
-                oc_solve(cost, l2, nlo, nut, match_d, lap_u, col4row, row4col, path, status);
+                oc_solve(cost, nlo, nut, match_d, lap_u, col4row, row4col, path, &sh->lap_ok, status);
                 for (int t = tid; t < nut; t += OC_THREADS) flag_t[t] = 0;
                 __syncthreads();
                 for (int d = tid; d < nlo; d += OC_THREADS) {
@@ -525,7 +524,7 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
             if (tid == 0) sh->maxflag = 0;
             __syncthreads();
             const bool dr = nud <= nut;
-            const int l2 = dr ? nut : nud;
+            const int l2 = lap_pitch(dr ? nut : nud);
             for (int e = tid; e < nud * nut; e += OC_THREADS) {
                 const int d = e / nut, t = e % nut;
                 const double v = asso_value(prm.asso, D + (size_t)d_hi[un_d[d]] * 7, S.last_obs + (size_t)S.list[un_t[t]] * 5);
@@ -535,7 +534,7 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
             }
             __syncthreads();
             if (sh->maxflag) {
-                oc_solve(cost, l2, nud, nut, match_d, lap_u, col4row, row4col, path, status);
+                oc_solve(cost, nud, nut, match_d, lap_u, col4row, row4col, path, &sh->lap_ok, status);
                 for (int t = tid; t < nut; t += OC_THREADS) flag_t[t] = 0;
                 for (int d = tid; d < nud; d += OC_THREADS) flag_d[d] = 0;
                 __syncthreads();
@@ -682,10 +681,10 @@ int tk_ocsort_create(const tk_ocsort_params* p, int n_seq, int cap_tracks, int c
     h->state_stride = (oc_state_bytes(cap_tracks) + 255) & ~(size_t)255;
     h->state = nullptr; h->cost = nullptr;
     const size_t fixed = oc_smem_fixed(cap_tracks, cap_dets);
-    const size_t mat = (size_t)cap_tracks * cap_dets * sizeof(double);
+    const size_t mat = (size_t)(cap_tracks + 1) * (cap_dets + 1) * sizeof(double);
     h->cost_in_smem = (fixed + 2 * mat <= 200 * 1024) ? 1 : 0;
     h->smem_bytes = fixed + (h->cost_in_smem ? 2 * mat : 0);
-    h->cost_stride = (size_t)cap_tracks * cap_dets;
+    h->cost_stride = (size_t)(cap_tracks + 1) * (cap_dets + 1);
     cudaError_t e = cudaMalloc((void**)&h->state, h->state_stride * n_seq);
     if (e == cudaSuccess && !h->cost_in_smem) e = cudaMalloc((void**)&h->cost, 2 * h->cost_stride * sizeof(double) * n_seq);
     if (e == cudaSuccess)

@@ -73,14 +73,26 @@ letterbox_kernel(const unsigned char* __restrict__ src, size_t frame_stride, int
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     const int y = blockIdx.x, b = blockIdx.y;
-    // planar [B,3,S,S] or interleaved channels-last [B,S,S,3] (what cuDNN's NHWC tensor-core kernels want)
-    const size_t xs = nhwc ? 3 : 1;
-    OutT* out0 = nhwc ? dst + (((size_t)b * S + y) * S) * 3 : dst + ((size_t)b * 3 + 0) * S * S + (size_t)y * S;
-    OutT* out1 = nhwc ? out0 + 1 : out0 + (size_t)S * S;
-    OutT* out2 = nhwc ? out0 + 2 : out1 + (size_t)S * S;
+    // layouts: 0 planar [B,3,S,S]; 1 channels-last [B,S,S,3]; 2 "focus16" = YOLOX Focus space-to-depth already applied,
+    // channels-last [B,S/2,S/2,16]: channel = patch*3 + c with patch order (tl, bl, tr, br) as in Focus.forward, 12..15 stay zero
+    // (the stem convolution's input channels are zero-padded to 16 so cuDNN needs no NHWC padding pass).
+    size_t xs = 1;
+    OutT *out0, *out1, *out2;
+    if (nhwc == 2) {
+        const int S2 = S >> 1;
+        out0 = dst + (((size_t)b * S2 + (y >> 1)) * S2) * 16 + (y & 1) * 3;
+        out1 = out0 + 1; out2 = out0 + 2;
+    } else if (nhwc == 1) {
+        xs = 3;
+        out0 = dst + (((size_t)b * S + y) * S) * 3; out1 = out0 + 1; out2 = out0 + 2;
+    } else {
+        out0 = dst + ((size_t)b * 3 + 0) * S * S + (size_t)y * S; out1 = out0 + (size_t)S * S; out2 = out1 + (size_t)S * S;
+    }
+    // element offset of output column x inside the row pointers above
+    auto xo = [&](int x) -> size_t { return nhwc == 2 ? (size_t)(x >> 1) * 16 + (size_t)(x & 1) * 6 : (size_t)x * xs; };
     const OutT padv = cvt_out<OutT>((float)pad);
     if (y >= rh) {  // pure padding row
-        for (int x = threadIdx.x; x < S; x += LB_THREADS) { out0[x * xs] = padv; out1[x * xs] = padv; out2[x * xs] = padv; }
+        for (int x = threadIdx.x; x < S; x += LB_THREADS) { const size_t o = xo(x); out0[o] = padv; out1[o] = padv; out2[o] = padv; }
         return;
     }
     Tap ty;
@@ -123,7 +135,8 @@ letterbox_kernel(const unsigned char* __restrict__ src, size_t frame_stride, int
     const unsigned char* r1 = need1 ? s1 + a1 : r0;
     const int c0 = swap_rb ? 2 : 0, c2 = swap_rb ? 0 : 2;
     for (int x = threadIdx.x; x < S; x += LB_THREADS) {
-        if (x >= rw) { out0[x * xs] = padv; out1[x * xs] = padv; out2[x * xs] = padv; continue; }
+        const size_t o = xo(x);
+        if (x >= rw) { out0[o] = padv; out1[o] = padv; out2[o] = padv; continue; }
         int v[3];
         if (area2x) {
             const unsigned char* p0 = r0 + 6 * x;
@@ -144,16 +157,16 @@ letterbox_kernel(const unsigned char* __restrict__ src, size_t frame_stride, int
                 v[c] = min(max(o, 0), 255);
             }
         }
-        out0[x * xs] = cvt_out<OutT>((float)v[c0]);
-        out1[x * xs] = cvt_out<OutT>((float)v[1]);
-        out2[x * xs] = cvt_out<OutT>((float)v[c2]);
+        out0[o] = cvt_out<OutT>((float)v[c0]);
+        out1[o] = cvt_out<OutT>((float)v[1]);
+        out2[o] = cvt_out<OutT>((float)v[c2]);
     }
 }
 
 }  // namespace
 
 extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, int W, long long frame_stride_bytes,
-                               void* dst, int out_dtype, int out_nhwc, int S, int pad_value, int swap_rb,
+                               void* dst, int out_dtype, int out_layout, int S, int pad_value, int swap_rb,
                                double* ratio_out, void* stream) {
     if (!src || !dst || n_frames <= 0 || H <= 0 || W <= 0 || S <= 0) return TK_ERR_ARG;
     if (out_dtype != TK_DTYPE_F32 && out_dtype != TK_DTYPE_BF16) return TK_ERR_ARG;
@@ -161,6 +174,7 @@ extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, in
     const double ratio = fmin((double)S / (double)H, (double)S / (double)W);
     const int rw = (int)((double)W * ratio), rh = (int)((double)H * ratio);
     if (rw <= 0 || rh <= 0 || rw > S || rh > S) return TK_ERR_ARG;
+    if (out_layout < 0 || out_layout > 2 || (out_layout == 2 && (S & 1))) return TK_ERR_ARG;
     if (ratio_out) *ratio_out = ratio;
     const double scale_x = 1.0 / ((double)rw / (double)W), scale_y = 1.0 / ((double)rh / (double)H);
     const int area2x = (W == 2 * rw && H == 2 * rh) ? 1 : 0;
@@ -174,12 +188,12 @@ extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, in
     if (out_dtype == TK_DTYPE_F32) {
         TK_CUDA_TRY(cudaFuncSetAttribute(letterbox_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         letterbox_kernel<float><<<grid, LB_THREADS, smem, st>>>(src, (size_t)frame_stride_bytes, H, W, (float*)dst, S, rw, rh,
-                                                               scale_x, scale_y, area2x, pad_value, swap_rb, out_nhwc, src_end);
+                                                               scale_x, scale_y, area2x, pad_value, swap_rb, out_layout, src_end);
     } else {
         TK_CUDA_TRY(cudaFuncSetAttribute(letterbox_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         letterbox_kernel<__nv_bfloat16><<<grid, LB_THREADS, smem, st>>>(src, (size_t)frame_stride_bytes, H, W,
                                                                        (__nv_bfloat16*)dst, S, rw, rh, scale_x, scale_y,
-                                                                       area2x, pad_value, swap_rb, out_nhwc, src_end);
+                                                                       area2x, pad_value, swap_rb, out_layout, src_end);
     }
     TK_CUDA_TRY(cudaGetLastError());
     return TK_OK;

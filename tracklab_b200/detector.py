@@ -18,7 +18,7 @@ from .nets.yolox import build_yolox
 class YoloxDetectorDevice:
     def __init__(self, variant="s", device="cuda:0", batch=32, input_size=640, dtype=torch.bfloat16,
                  score_thr=0.7, nms_thr=0.45, max_per_image=256, num_classes=1, seed=1234,
-                 frames_cap=4096, dets_cap=1 << 18, use_graph=True, model=None):
+                 frames_cap=4096, dets_cap=1 << 18, use_graph=True, model=None, fused=True):
         if not torch.cuda.is_available():
             raise _lib.TrackKernError("YoloxDetectorDevice needs a CUDA device (no CPU path)")
         _lib.load()
@@ -29,8 +29,18 @@ class YoloxDetectorDevice:
         self.model = self.model.to(self.device).to(dtype).to(memory_format=torch.channels_last).eval()
         for p in self.model.parameters():
             p.requires_grad_(False)
-        self.x = torch.empty((batch, 3, input_size, input_size), dtype=dtype, device=self.device,
-                             memory_format=torch.channels_last)
+        self.fused = None
+        self.use_fused = bool(fused) and dtype == torch.bfloat16
+        if self.use_fused:
+            from .nets.yolox_fused import YoloxFused
+            self._fused_cls = YoloxFused
+            self.fused = YoloxFused(self.model, self.device)
+            # Focus-unfolded input written by the letterbox kernel; channels 12..15 are zero padding
+            self.x = torch.zeros((batch, 16, input_size // 2, input_size // 2), dtype=dtype,
+                                 device=self.device).contiguous(memory_format=torch.channels_last)
+        else:
+            self.x = torch.empty((batch, 3, input_size, input_size), dtype=dtype, device=self.device,
+                                 memory_format=torch.channels_last)
         self.status = torch.zeros((1,), dtype=torch.int32, device=self.device)
         self.cursor = torch.zeros((2,), dtype=torch.int32, device=self.device)      # {next row, next frame}
         self.dets = torch.zeros((dets_cap, 7), dtype=torch.float64, device=self.device)
@@ -54,7 +64,7 @@ class YoloxDetectorDevice:
         ``spread`` and pick one bias so that about ``target_per_image`` anchors pass the threshold — this
         gives decode+NMS a realistic candidate load with synthetic weights."""
         x, _ = kernels.letterbox(frames[: self.batch], self.size, self.dtype, swap_rb=True, channels_last=True)
-        raw = self.model(x).float()
+        raw = self.model(x).float()   # calibration statistics come from the plain module (same weights)
         A = raw.shape[1]
         n8, n16 = (self.size // 8) ** 2, (self.size // 16) ** 2
         bounds = [(0, n8), (n8, n8 + n16), (n8 + n16, A)]
@@ -81,11 +91,16 @@ class YoloxDetectorDevice:
             self.model.obj_preds[lvl].bias.data += shift
             self.model.cls_preds[lvl].bias.data += shift
         self.graph = None
+        if self.use_fused:
+            self.fused = self._fused_cls(self.model, self.device)
         return shift
 
     # ---- one batch ---------------------------------------------------------------------------------
+    def _net(self, x):
+        return self.fused(x) if self.use_fused else self.model(x)
+
     def _forward_post(self, W, H):
-        self.pred = self.model(self.x)
+        self.pred = self._net(self.x)
         self.nms_out = kernels.yolox_nms(self.pred, self.ratio, self.size, logits=True, score_thr=self.score_thr,
                                          nms_thr=self.nms_thr, max_out=self.max_per_image, status=self.status)
         boxes, scores, cls, count, _ = self.nms_out
@@ -102,8 +117,13 @@ class YoloxDetectorDevice:
         B, H, W, _ = frames.shape
         assert B <= self.batch
         if B < self.batch:   # ragged tail: run eagerly on a view (rare: once per video)
-            x, ratio = kernels.letterbox(frames, self.size, self.dtype, swap_rb=True, channels_last=True)
-            pred = self.model(x)
+            if self.use_fused:
+                x = torch.zeros((B, 16, self.size // 2, self.size // 2), dtype=self.dtype,
+                                device=self.device).contiguous(memory_format=torch.channels_last)
+                _, ratio = kernels.letterbox(frames, self.size, self.dtype, swap_rb=True, out=x, focus16=True)
+            else:
+                x, ratio = kernels.letterbox(frames, self.size, self.dtype, swap_rb=True, channels_last=True)
+            pred = self._net(x)
             boxes, scores, cls, count, _ = kernels.yolox_nms(pred, ratio, self.size, True, self.score_thr, self.nms_thr,
                                                              self.max_per_image, status=self.status)
             kernels.pack_detections(boxes, scores, cls, count, W, H, self.cursor, self.dets, self.offsets, self.status)
@@ -111,7 +131,7 @@ class YoloxDetectorDevice:
         if self.time_kernels:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _, self.ratio = kernels.letterbox(frames, self.size, self.dtype, swap_rb=True, out=self.x)
+        _, self.ratio = kernels.letterbox(frames, self.size, self.dtype, swap_rb=True, out=self.x, focus16=self.use_fused)
         if self.time_kernels:
             e1.record()
             self.kernel_events.append(("letterbox_kernel", e0, e1, B))

@@ -28,8 +28,9 @@ def _cuda(t: torch.Tensor, name: str):
 
 
 def letterbox(frames: torch.Tensor, size: int = 640, out_dtype=torch.bfloat16, pad: int = 114, swap_rb: bool = True,
-              out: torch.Tensor | None = None, channels_last: bool = False):
-    """uint8 [B,H,W,3] -> [B,3,size,size]; returns (tensor, ratio). C ABI: tk_letterbox_u8."""
+              out: torch.Tensor | None = None, channels_last: bool = False, focus16: bool = False):
+    """uint8 [B,H,W,3] -> [B,3,size,size] (or, focus16, the Focus-unfolded [B,16,size/2,size/2] channels-last tensor);
+    returns (tensor, ratio). C ABI: tk_letterbox_u8."""
     lib = _lib.load()
     _cuda(frames, "frames")
     assert frames.dtype == torch.uint8 and frames.dim() == 4 and frames.shape[3] == 3
@@ -37,8 +38,12 @@ def letterbox(frames: torch.Tensor, size: int = 640, out_dtype=torch.bfloat16, p
     if out is None:
         out = torch.empty((B, 3, size, size), dtype=out_dtype, device=frames.device,
                           memory_format=torch.channels_last if channels_last else torch.contiguous_format)
-    nhwc = out.is_contiguous(memory_format=torch.channels_last) and not out.is_contiguous()
-    assert nhwc or out.is_contiguous()
+    if focus16:
+        assert out.shape == (B, 16, size // 2, size // 2) and out.is_contiguous(memory_format=torch.channels_last)
+        nhwc = 2
+    else:
+        nhwc = int(out.is_contiguous(memory_format=torch.channels_last) and not out.is_contiguous())
+        assert nhwc or out.is_contiguous()
     ratio = ctypes.c_double()
     with torch.cuda.device(frames.device):
         _lib.check(lib.tk_letterbox_u8(frames.data_ptr(), B, H, W, frames.stride(0), out.data_ptr(), _dtype_code(out.dtype),
@@ -81,3 +86,38 @@ def pack_detections(boxes, scores, cls, count, width: int, height: int, cursor: 
                                           dets_out.shape[0], offsets_out.shape[0] - 1, status.data_ptr(), _stream()),
                    "tk_pack_detections")
     return dets_out, offsets_out
+
+
+def bias_act(src: torch.Tensor, bias: torch.Tensor, dst: torch.Tensor, dst_offset: int = 0, act: int = 1,
+             residual: torch.Tensor | None = None, res_offset: int = 0):
+    """dst[:, off:off+C] = act(src + bias) (+ residual). All tensors bf16 channels-last [B,C,H,W]; dst/residual may be wider
+    (concat buffers). C ABI: tk_bias_act_nhwc."""
+    lib = _lib.load()
+    B, C, H, W = src.shape
+    assert src.dtype == torch.bfloat16 and src.is_contiguous(memory_format=torch.channels_last) and bias.dtype == torch.float32
+    assert dst.is_contiguous(memory_format=torch.channels_last) and dst.shape[0] == B and dst.shape[2:] == src.shape[2:]
+    rp, r = (residual.shape[1], residual.data_ptr()) if residual is not None else (0, None)
+    with torch.cuda.device(src.device):
+        _lib.check(lib.tk_bias_act_nhwc(src.data_ptr(), bias.data_ptr(), dst.data_ptr(), r, B * H * W, C, dst.shape[1], dst_offset,
+                                        rp, res_offset, act, _stream()), "tk_bias_act_nhwc")
+    return dst
+
+
+def spp_pool(x: torch.Tensor, dst: torch.Tensor, dst_offset: int = 0):
+    """dst[:, off:off+4C] = [x, maxpool5(x), maxpool9(x), maxpool13(x)] (C ABI: tk_spp_nhwc)."""
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tk_spp_nhwc(x.data_ptr(), dst.data_ptr(), B, H, W, C, dst.shape[1], dst_offset, _stream()), "tk_spp_nhwc")
+    return dst
+
+
+def upsample2x(src: torch.Tensor, dst: torch.Tensor, dst_offset: int = 0, src_offset: int = 0, channels: int | None = None):
+    """dst[:, off:off+C, 2h, 2w] = nearest-2x(src[:, soff:soff+C]) (C ABI: tk_upsample2x_nhwc)."""
+    lib = _lib.load()
+    B, Cs, h, w = src.shape
+    C = channels or Cs
+    with torch.cuda.device(src.device):
+        _lib.check(lib.tk_upsample2x_nhwc(src.data_ptr(), Cs, src_offset, dst.data_ptr(), B, h, w, C, dst.shape[1], dst_offset,
+                                          _stream()), "tk_upsample2x_nhwc")
+    return dst

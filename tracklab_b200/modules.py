@@ -66,15 +66,15 @@ class _TrackerDatapipe:
         return len(self.image_ids)
 
 
-class _DeviceTrackerModule(ImageLevelModule):
-    input_columns = ["bbox_ltwh", "bbox_conf", "category_id"]
-    output_columns = ["track_id", "track_bbox_ltwh", "track_bbox_conf"]
-    collate_fn = None
-    _device_cls = None
-    _continue_ids = False
+# ``Module.level`` is derived from the name of the FIRST base class (pipeline/module.py:34-37), so every concrete module
+# below inherits ImageLevelModule directly and takes its behaviour from the functions of this section.
+_IN_COLS = ["bbox_ltwh", "bbox_conf", "category_id"]
+_OUT_COLS = ["track_id", "track_bbox_ltwh", "track_bbox_conf"]
 
+
+class _Impl:
     def __init__(self, cfg, device, **kwargs):
-        super().__init__(batch_size=1)
+        ImageLevelModule.__init__(self, batch_size=1)
         if not torch.cuda.is_available():
             raise _lib.TrackKernError(f"{type(self).__name__} needs a CUDA device: tracklab_b200 has no CPU path")
         self.cfg = cfg
@@ -96,7 +96,6 @@ class _DeviceTrackerModule(ImageLevelModule):
         self._first_reset = False
         self._result = None
 
-    @property
     def datapipe(self):
         return self._pipe
 
@@ -159,12 +158,30 @@ class _DeviceTrackerModule(ImageLevelModule):
         return sel[["track_bbox_ltwh", "track_bbox_conf", "track_id"]]
 
 
-class ByteTrack(_DeviceTrackerModule):
+def _bind(cls):
+    """Copy the shared implementation into a class whose first base is ImageLevelModule."""
+    for name in ("__init__", "reset", "dataloader", "preprocess", "_track_video", "process"):
+        setattr(cls, name, _Impl.__dict__[name])
+    cls.datapipe = property(_Impl.__dict__["datapipe"])
+    cls.__abstractmethods__ = frozenset()
+    return cls
+
+
+@_bind
+class ByteTrack(ImageLevelModule):
     """Drop-in for tracklab.wrappers.track.byte_track_api.ByteTrack (same name => same ``module.name``)."""
+    input_columns = list(_IN_COLS)
+    output_columns = list(_OUT_COLS)
+    collate_fn = None
     _device_cls = ByteTrackDevice
     _continue_ids = True   # BaseTrack._count is process-global in the reference (byte_track/basetrack.py:13)
 
 
-class OCSORT(_DeviceTrackerModule):
+@_bind
+class OCSORT(ImageLevelModule):
     """Drop-in for tracklab.wrappers.track.oc_sort_api.OCSORT."""
+    input_columns = list(_IN_COLS)
+    output_columns = list(_OUT_COLS)
+    collate_fn = None
     _device_cls = OCSortDevice
+    _continue_ids = False
