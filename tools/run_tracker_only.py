@@ -21,3 +21,15 @@ for _ in range(3):
     torch.cuda.synchronize()
     print(kind, F, "frames:", e0.elapsed_time(e1) * 1e3 / F, "us/frame", int(cnt.item()), "rows")
 trk.check_status()
+
+# optional per-phase cycle breakdown (library built with -DTK_PHASE_PROF)
+import ctypes
+from tracklab_b200 import _lib
+lib = _lib.load()
+if hasattr(lib, "tk_debug_bytetrack_phases") and kind == "bytetrack":
+    buf = (ctypes.c_ulonglong * 64)()
+    lib.tk_debug_bytetrack_phases(buf, 1)
+    trk.reset(); trk.run(dets, offs); torch.cuda.synchronize()
+    lib.tk_debug_bytetrack_phases(buf, 0)
+    tot = sum(buf)
+    print("phase cycles/frame:", {k: int(v / F) for k, v in enumerate(buf) if v}, "total", int(tot / F))

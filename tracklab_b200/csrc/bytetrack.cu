@@ -20,7 +20,16 @@ namespace {
 
 using namespace tk;
 
-constexpr int BT_THREADS = 128;
+constexpr int BT_THREADS = 256;   // 32 octets: one Kalman update per 8 lanes (kf_xyah.cuh)
+
+// Optional per-phase cycle accounting (build with -DTK_PHASE_PROF): thread 0 accumulates clock64() deltas between
+// the barriers of the frame loop into g_bt_prof[]; read back with tk_debug_bytetrack_phases().
+#ifdef TK_PHASE_PROF
+__device__ unsigned long long g_bt_prof[64];
+#define PH(k) do { if (threadIdx.x == 0) { const long long _t = clock64(); g_bt_prof[k] += (unsigned long long)(_t - ph_t0); ph_t0 = _t; } } while (0)
+#else
+#define PH(k) do { } while (0)
+#endif
 enum : unsigned char { ST_NEW = 0, ST_TRACKED = 1, ST_LOST = 2, ST_REMOVED = 3 };
 
 struct BtDev {
@@ -145,57 +154,42 @@ __device__ __forceinline__ void det_xyah(const float* b, double* z) {
 constexpr double W_POS = 1.0 / 20;
 constexpr double W_VEL = 1.0 / 160;
 
-// KalmanFilter.update (kalman_filter.py:194-226) incl. project (:126-153) for one track
-__device__ __noinline__ void bt_kf_update(BtDev& S, int slot, const float* detbox) {
-    double m[8], P[64], z[4], r[4];
-    double* gm = S.mean + (size_t)slot * 8;
-    double* gP = S.cov + (size_t)slot * 64;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = gm[i];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) P[i] = gP[i];
-    det_xyah(detbox, z);
-    double sp;
-    if (S.mean_f32[slot]) sp = (double)__fmul_rn((float)W_POS, (float)m[3]);  // python float * np.float32
-    else sp = W_POS * m[3];
-    r[0] = sp * sp; r[1] = sp * sp; r[2] = 1e-1 * 1e-1; r[3] = sp * sp;
-    if (!kf8_update(m, P, z, r)) atomicOr(&S.hdr[4], TK_DEV_BAD_CHOLESKY);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) gm[i] = m[i];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) gP[i] = P[i];
-    S.mean_f32[slot] = 0;
+// KalmanFilter.update (kalman_filter.py:194-226, project :126-153) and multi_predict (:155-192); q is float32 when the
+// whole pool still carries float32 means (NumPy promotion of np.asarray([...float32 means...])).
+// Octet-cooperative (8 lanes per track, kf_xyah.cuh), register resident.
+__device__ __forceinline__ void bt_octet_update(BtDev& S, int slot, bool active, const float* detbox) {
+    double z[4] = {0, 0, 0, 0}, r[4] = {1, 1, 1, 1};
+    double* gm = S.mean + (size_t)(active ? slot : 0) * 8;
+    double* gP = S.cov + (size_t)(active ? slot : 0) * 64;
+    if (active) {
+        det_xyah(detbox, z);
+        const double h = gm[3];
+        const double sp = S.mean_f32[slot] ? (double)__fmul_rn((float)W_POS, (float)h) : W_POS * h;
+        r[0] = sp * sp; r[1] = sp * sp; r[2] = 1e-1 * 1e-1; r[3] = sp * sp;
+    }
+    if (!kf8_octet_update(gm, gP, active, z, r)) atomicOr(&S.hdr[4], TK_DEV_BAD_CHOLESKY);
 }
 
-// KalmanFilter.multi_predict for one track (kalman_filter.py:155-192); q in float32 when the whole
-// pool still carries float32 means (NumPy promotion of np.asarray([...float32 means...])).
-__device__ __noinline__ void bt_kf_predict(BtDev& S, int slot, bool pool_f32) {
-    double m[8], P[64], q[8];
-    double* gm = S.mean + (size_t)slot * 8;
-    double* gP = S.cov + (size_t)slot * 64;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = gm[i];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) P[i] = gP[i];
-    if (S.state[slot] != ST_TRACKED) m[7] = 0.0;
-    if (pool_f32) {
-        const float h = (float)m[3];
-        const float sp = __fmul_rn((float)W_POS, h), sv = __fmul_rn((float)W_VEL, h);
-        const float ca = (float)1e-2, cv = (float)1e-5;
-        const double qp = (double)__fmul_rn(sp, sp), qv = (double)__fmul_rn(sv, sv);
-        q[0] = qp; q[1] = qp; q[2] = (double)__fmul_rn(ca, ca); q[3] = qp;
-        q[4] = qv; q[5] = qv; q[6] = (double)__fmul_rn(cv, cv); q[7] = qv;
-    } else {
-        const double sp = W_POS * m[3], sv = W_VEL * m[3];
-        q[0] = sp * sp; q[1] = sp * sp; q[2] = 1e-2 * 1e-2; q[3] = sp * sp;
-        q[4] = sv * sv; q[5] = sv * sv; q[6] = 1e-5 * 1e-5; q[7] = sv * sv;
+__device__ __forceinline__ void bt_octet_predict(BtDev& S, int slot, bool active, bool pool_f32) {
+    const int j = threadIdx.x & 7;
+    double* gm = S.mean + (size_t)(active ? slot : 0) * 8;
+    double* gP = S.cov + (size_t)(active ? slot : 0) * 64;
+    double qj = 0.0;
+    bool zero_vh = false;
+    if (active) {
+        zero_vh = S.state[slot] != ST_TRACKED;
+        const double h = gm[3];
+        const bool pos = j < 4;
+        if (pool_f32) {
+            const float hf = (float)h;
+            const float sd = (j == 2) ? (float)1e-2 : (j == 6) ? (float)1e-5 : __fmul_rn(pos ? (float)W_POS : (float)W_VEL, hf);
+            qj = (double)__fmul_rn(sd, sd);
+        } else {
+            const double sd = (j == 2) ? 1e-2 : (j == 6) ? 1e-5 : (pos ? W_POS : W_VEL) * h;
+            qj = sd * sd;
+        }
     }
-    kf8_predict(m, P, q);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) gm[i] = m[i];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) gP[i] = P[i];
-    S.mean_f32[slot] = 0;
+    kf8_octet_predict(gm, gP, active, zero_vh, qj);
 }
 
 // KalmanFilter.initiate (kalman_filter.py:55-86): mean stays float32-valued, std are float32 products
@@ -212,6 +206,24 @@ __device__ void bt_kf_initiate(BtDev& S, int slot, const float* detbox) {
     for (int i = 0; i < 64; ++i) gP[i] = 0.0;
     for (int i = 0; i < 8; ++i) gP[i * 9] = d[i];
     S.mean_f32[slot] = 1;
+}
+
+// Ordered compaction done by ONE warp: pred(i) for i in [0,n), emit(i, base + rank) for the passing items in index
+// order; returns base + count. The serial list edits of the reference become a few ballots instead of a
+// dependent-load loop on one thread (~60 cycles per element on shared memory).
+template <class Pred, class Emit>
+__device__ __forceinline__ int warp_compact(int n, int base, Pred pred, Emit emit) {
+    const int lane = lane_id();
+    int cnt = base;
+    for (int c = 0; c < n; c += 32) {
+        const int i = c + lane;
+        const bool f = (i < n) && pred(i);
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (f) emit(i, cnt + __popc(b & ((1u << lane) - 1u)));
+        cnt += __popc(b);
+    }
+    __syncwarp();
+    return cnt;
 }
 
 struct BtShared {
@@ -288,6 +300,37 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
     unsigned char* dup_b = (unsigned char*)take(cap);
     unsigned char* in_tracked = (unsigned char*)take(cap);
     BtShared* sh = (BtShared*)take(sizeof(BtShared));
+    // Book-keeping of the tracker (lists, per-slot flags/ids/scores) lives in shared memory for the whole launch:
+    // the frame loop below is a chain of short serial list edits, and every global round trip in it is pure latency.
+    // Only the Kalman means/covariances (576 B per track) stay in global memory (L1/L2 resident).
+    const BtDev G = S;
+    {
+        int* m_hdr = (int*)take(8 * sizeof(int));
+        double* m_score = (double*)take(sizeof(double) * cap);
+        double* m_cls = (double*)take(sizeof(double) * cap);
+        double* m_det = (double*)take(sizeof(double) * cap);
+        int* m_tid = (int*)take(sizeof(int) * cap);
+        int* m_fid = (int*)take(sizeof(int) * cap);
+        int* m_sf = (int*)take(sizeof(int) * cap);
+        int* m_trk = (int*)take(sizeof(int) * cap);
+        int* m_lost = (int*)take(sizeof(int) * cap);
+        int* m_free = (int*)take(sizeof(int) * cap);
+        unsigned char* m_state = (unsigned char*)take(cap);
+        unsigned char* m_act = (unsigned char*)take(cap);
+        unsigned char* m_f32 = (unsigned char*)take(cap);
+        unsigned char* m_rem = (unsigned char*)take(cap);
+        if (tid < 8) m_hdr[tid] = G.hdr[tid];
+        for (int i = tid; i < cap; i += BT_THREADS) {
+            m_score[i] = G.score[i]; m_cls[i] = G.cls[i]; m_det[i] = G.det_id[i];
+            m_tid[i] = G.track_id[i]; m_fid[i] = G.frame_id[i]; m_sf[i] = G.start_frame[i];
+            m_trk[i] = G.tracked[i]; m_lost[i] = G.lost[i]; m_free[i] = G.free_list[i];
+            m_state[i] = G.state[i]; m_act[i] = G.activated[i]; m_f32[i] = G.mean_f32[i]; m_rem[i] = G.in_removed[i];
+        }
+        S.hdr = m_hdr; S.score = m_score; S.cls = m_cls; S.det_id = m_det; S.track_id = m_tid; S.frame_id = m_fid;
+        S.start_frame = m_sf; S.tracked = m_trk; S.lost = m_lost; S.free_list = m_free; S.state = m_state;
+        S.activated = m_act; S.mean_f32 = m_f32; S.in_removed = m_rem;
+        __syncthreads();
+    }
     double* cost = cost_in_smem ? (double*)take(0) : cost_scratch + (size_t)seq * cost_stride;
 
     int* status = &S.hdr[4];
@@ -295,6 +338,9 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
     int out_base = out_start[seq];
     int out_n = out_count[seq];
 
+#ifdef TK_PHASE_PROF
+    long long ph_t0 = clock64();
+#endif
     for (int f = 0; f < n_frames; ++f) {
         const int r0 = offsets[seq * F1 + f], r1 = offsets[seq * F1 + f + 1];
         const int nraw = r1 - r0;
@@ -316,44 +362,54 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
             d_score[i] = d[4]; d_cls[i] = d[5]; d_id[i] = d[6];
         }
         __syncthreads();
-        if (tid == 0) {
-            const int frame_id = ++S.hdr[0];
-            (void)frame_id;
-            int nh = 0, nl = 0;
-            for (int i = 0; i < nraw; ++i) {
-                const double c = d_score[i];
-                if (!(c > prm.min_conf)) continue;       // wrapper filter (byte_track_api.py:54)
-                if (c > prm.track_thresh) d_high[nh++] = i;
-                else if (c > 0.1 && c < prm.track_thresh) d_low[nl++] = i;
-            }
-            sh->nh = nh; sh->nl = nl;
+        PH(1);
+        if (warp_id() == 0) {
+            const int lane = lane_id();
+            if (lane == 0) S.hdr[0] += 1;
+            // wrapper filter (byte_track_api.py:54) + score split (byte_tracker.py:186-203)
+            const int nh_ = warp_compact(nraw, 0, [&](int i) { const double c = d_score[i]; return c > prm.min_conf && c > prm.track_thresh; },
+                                         [&](int i, int p) { d_high[p] = i; });
+            const int nl_ = warp_compact(nraw, 0, [&](int i) { const double c = d_score[i]; return c > prm.min_conf && !(c > prm.track_thresh) && c > 0.1 && c < prm.track_thresh; },
+                                         [&](int i, int p) { d_low[p] = i; });
             // ---- B. split tracked list, build the pool = confirmed + lost (byte_tracker.py:207-218)
             const int nt = S.hdr[2], nlost = S.hdr[3];
-            int nc = 0, nu = 0, allf = 1;
-            for (int k = 0; k < nt; ++k) {
-                const int s = S.tracked[k];
-                if (S.activated[s]) pool[nc++] = s; else unconf[nu++] = s;
+            int nc = warp_compact(nt, 0, [&](int k) { return S.activated[S.tracked[k]] != 0; }, [&](int k, int p) { pool[p] = S.tracked[k]; });
+            const int nu = warp_compact(nt, 0, [&](int k) { return S.activated[S.tracked[k]] == 0; }, [&](int k, int p) { unconf[p] = S.tracked[k]; });
+            for (int k = lane; k < nlost; k += 32) pool[nc + k] = S.lost[k];
+            nc += nlost;
+            __syncwarp();
+            int allf = 1;
+            for (int k = lane; k < nc; k += 32) allf &= S.mean_f32[pool[k]];
+            allf = __all_sync(0xffffffffu, allf);
+            if (lane == 0) {
+                sh->nh = nh_; sh->nl = nl_; sh->npool = nc; sh->nunc = nu; sh->all_f32 = allf;
+                sh->n_tracked = nt; sh->n_lost = nlost;
             }
-            for (int k = 0; k < nlost; ++k) pool[nc++] = S.lost[k];
-            for (int k = 0; k < nc; ++k) allf &= S.mean_f32[pool[k]];
-            sh->npool = nc; sh->nunc = nu; sh->all_f32 = allf;
-            sh->n_tracked = nt; sh->n_lost = nlost;
         }
         __syncthreads();
+        PH(2);
         const int frame_id = S.hdr[0];
         const int nh = sh->nh, nl = sh->nl, npool = sh->npool, nunc = sh->nunc;
 
         // ---- C. multi_predict over the pool ----------------------------------------------------
         {
             const bool pf32 = sh->all_f32 != 0;
-            for (int k = tid; k < npool; k += BT_THREADS) bt_kf_predict(S, pool[k], pf32);
+            for (int base = 0; base < npool; base += BT_THREADS / 8) {
+                const int k = base + (tid >> 3);
+                const bool act = k < npool;
+                bt_octet_predict(S, act ? pool[k] : 0, act, pf32);
+            }
+            __syncthreads();
+            for (int k = tid; k < npool; k += BT_THREADS) S.mean_f32[pool[k]] = 0;
         }
         __syncthreads();
+        PH(3);
         for (int k = tid; k < npool; k += BT_THREADS) {
             const int s = pool[k];
             track_tlbr32(S.mean + (size_t)s * 8, S.mean_f32[s] != 0, t_tlbr + 4 * k);
         }
         __syncthreads();
+        PH(4);
 
         // ---- D. first association: fused IoU/score cost, limit match_thresh ----------------------
         {
@@ -369,27 +425,32 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
                 if (a_rows) cost[(size_t)it * ld + jd] = red; else cost[(size_t)jd * ld + it] = red;
             }
             __syncthreads();
+            PH(5);
             solve_assignment(cost, npool, nh, match_a, match_b, lap_u, col4row, row4col, path, &sh->lap_ok, status);
         }
         // matched pool tracks: update / re_activate (byte_tracker.py:229-237)
-        for (int k = tid; k < npool; k += BT_THREADS) {
-            const int j = match_a[k];
-            if (j < 0) continue;
-            const int s = pool[k], di = d_high[j];
-            bt_kf_update(S, s, d_box + 4 * di);
-            if (S.state[s] != ST_TRACKED) S.cls[s] = d_cls[di];   // re_activate also copies cls
-            S.state[s] = ST_TRACKED; S.activated[s] = 1; S.frame_id[s] = frame_id;
-            S.score[s] = d_score[di]; S.det_id[s] = d_id[di];
+        for (int base = 0; base < npool; base += BT_THREADS / 8) {
+            const int k = base + (tid >> 3);
+            const int j = k < npool ? match_a[k] : -1;
+            const bool act = j >= 0;
+            const int s = act ? pool[k] : 0, di = act ? d_high[j] : 0;
+            bt_octet_update(S, s, act, d_box + 4 * di);
+            if (act && (tid & 7) == 0) {
+                if (S.state[s] != ST_TRACKED) S.cls[s] = d_cls[di];   // re_activate also copies cls
+                S.state[s] = ST_TRACKED; S.activated[s] = 1; S.frame_id[s] = frame_id; S.mean_f32[s] = 0;
+                S.score[s] = d_score[di]; S.det_id[s] = d_id[di];
+            }
         }
         __syncthreads();
-        if (tid == 0) {
-            int nr = 0, nleft = 0;
-            for (int k = 0; k < npool; ++k)
-                if (match_a[k] < 0 && S.state[pool[k]] == ST_TRACKED) rest[nr++] = pool[k];
-            for (int j = 0; j < nh; ++j) if (match_b[j] < 0) d_left[nleft++] = d_high[j];
-            sh->nrest = nr; sh->nleft = nleft;
+        PH(6);
+        if (warp_id() == 0) {
+            const int nr = warp_compact(npool, 0, [&](int k) { return match_a[k] < 0 && S.state[pool[k]] == ST_TRACKED; },
+                                        [&](int k, int p) { rest[p] = pool[k]; });
+            const int nleft_ = warp_compact(nh, 0, [&](int j) { return match_b[j] < 0; }, [&](int j, int p) { d_left[p] = d_high[j]; });
+            if (lane_id() == 0) { sh->nrest = nr; sh->nleft = nleft_; }
         }
         __syncthreads();
+        PH(7);
         const int nrest = sh->nrest, nleft = sh->nleft;
 
         // ---- E. second association: remaining Tracked tracks vs low-score boxes, limit 0.5 -------
@@ -398,6 +459,7 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
             track_tlbr32(S.mean + (size_t)s * 8, S.mean_f32[s] != 0, t_tlbr + 4 * k);
         }
         __syncthreads();
+        PH(8);
         {
             const bool a_rows = nrest <= nl;
             const int ld = lap_pitch(a_rows ? nl : nrest);
@@ -408,26 +470,29 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
                 if (a_rows) cost[(size_t)it * ld + jd] = red; else cost[(size_t)jd * ld + it] = red;
             }
             __syncthreads();
+            PH(9);
             solve_assignment(cost, nrest, nl, match_a, match_b, lap_u, col4row, row4col, path, &sh->lap_ok, status);
         }
-        for (int k = tid; k < nrest; k += BT_THREADS) {
-            const int s = rest[k];
-            const int j = match_a[k];
-            if (j >= 0) {
-                const int di = d_low[j];
-                bt_kf_update(S, s, d_box + 4 * di);
-                S.state[s] = ST_TRACKED; S.activated[s] = 1; S.frame_id[s] = frame_id;
+        for (int base = 0; base < nrest; base += BT_THREADS / 8) {
+            const int k = base + (tid >> 3);
+            const int j = k < nrest ? match_a[k] : -1;
+            const bool act = j >= 0;
+            const int s = act ? rest[k] : 0, di = act ? d_low[j] : 0;
+            bt_octet_update(S, s, act, d_box + 4 * di);
+            if (act && (tid & 7) == 0) {
+                S.state[s] = ST_TRACKED; S.activated[s] = 1; S.frame_id[s] = frame_id; S.mean_f32[s] = 0;
                 S.score[s] = d_score[di]; S.det_id[s] = d_id[di];
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            int n = 0;
-            for (int k = 0; k < nrest; ++k)
-                if (match_a[k] < 0) { S.state[rest[k]] = ST_LOST; lostnow[n++] = rest[k]; }
-            sh->n_lostnow = n;
+        PH(10);
+        if (warp_id() == 0) {
+            const int n = warp_compact(nrest, 0, [&](int k) { return match_a[k] < 0; },
+                                       [&](int k, int p) { S.state[rest[k]] = ST_LOST; lostnow[p] = rest[k]; });
+            if (lane_id() == 0) sh->n_lostnow = n;
         }
         __syncthreads();
+        PH(11);
 
         // ---- F. unconfirmed tracks vs leftover high boxes, limit 0.7 (byte_tracker.py:266-278) ---
         for (int k = tid; k < nunc; k += BT_THREADS) {
@@ -435,6 +500,7 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
             track_tlbr32(S.mean + (size_t)s * 8, S.mean_f32[s] != 0, t_tlbr + 4 * k);
         }
         __syncthreads();
+        PH(12);
         {
             const bool a_rows = nunc <= nleft;
             const int ld = lap_pitch(a_rows ? nleft : nunc);
@@ -448,89 +514,86 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
                 if (a_rows) cost[(size_t)it * ld + jd] = red; else cost[(size_t)jd * ld + it] = red;
             }
             __syncthreads();
+            PH(13);
             solve_assignment(cost, nunc, nleft, match_a, match_b, lap_u, col4row, row4col, path, &sh->lap_ok, status);
         }
-        for (int k = tid; k < nunc; k += BT_THREADS) {
-            const int s = unconf[k];
-            const int j = match_a[k];
-            if (j >= 0) {
-                const int di = d_left[j];
-                bt_kf_update(S, s, d_box + 4 * di);
-                S.state[s] = ST_TRACKED; S.activated[s] = 1; S.frame_id[s] = frame_id;
-                S.score[s] = d_score[di]; S.det_id[s] = d_id[di];
-            } else {
-                S.state[s] = ST_REMOVED;   // mark_removed; it leaves `tracked` below and is never looked at again
+        for (int base = 0; base < nunc; base += BT_THREADS / 8) {
+            const int k = base + (tid >> 3);
+            const int j = k < nunc ? match_a[k] : -1;
+            const bool act = j >= 0;
+            const int s = k < nunc ? unconf[k] : 0, di = act ? d_left[j] : 0;
+            bt_octet_update(S, s, act, d_box + 4 * di);
+            if (k < nunc && (tid & 7) == 0) {
+                if (act) {
+                    S.state[s] = ST_TRACKED; S.activated[s] = 1; S.frame_id[s] = frame_id; S.mean_f32[s] = 0;
+                    S.score[s] = d_score[di]; S.det_id[s] = d_id[di];
+                } else {
+                    S.state[s] = ST_REMOVED;   // mark_removed; it leaves `tracked` below and is never looked at again
+                }
             }
         }
         __syncthreads();
+        PH(14);
 
         // ---- G. births (byte_tracker.py:280-286) + ageing (:288-291) + list maintenance (:293-299)
-        if (tid == 0) {
-            int nb = 0;
-            int nfree = S.hdr[5];
-            for (int j = 0; j < nleft; ++j) {
-                if (match_b[j] >= 0) continue;
-                const int di = d_left[j];
-                if (d_score[di] < prm.det_thresh) continue;
-                if (nfree == 0) { atomicOr(status, TK_DEV_OVERFLOW_TRACKS); break; }
-                const int s = S.free_list[--nfree];
-                births[nb] = di; birth_slot[nb] = s; ++nb;
-                S.track_id[s] = ++S.hdr[1];
-                S.state[s] = ST_TRACKED; S.activated[s] = (frame_id == 1) ? 1 : 0;
-                S.frame_id[s] = frame_id; S.start_frame[s] = frame_id; S.in_removed[s] = 0;
-                S.score[s] = d_score[di]; S.cls[s] = d_cls[di]; S.det_id[s] = d_id[di];
-            }
-            S.hdr[5] = nfree;
-            sh->n_births = nb;
+        if (warp_id() == 0) {
+            const int nfree = S.hdr[5];
+            const int id0 = S.hdr[1];
+            const int nb = warp_compact(nleft, 0, [&](int j) { return match_b[j] < 0 && !(d_score[d_left[j]] < prm.det_thresh); },
+                                        [&](int j, int p) {
+                                            if (p >= nfree) { atomicOr(status, TK_DEV_OVERFLOW_TRACKS); return; }
+                                            const int di = d_left[j];
+                                            const int s = S.free_list[nfree - 1 - p];
+                                            births[p] = di; birth_slot[p] = s;
+                                            S.track_id[s] = id0 + 1 + p;
+                                            S.state[s] = ST_TRACKED; S.activated[s] = (frame_id == 1) ? 1 : 0;
+                                            S.frame_id[s] = frame_id; S.start_frame[s] = frame_id; S.in_removed[s] = 0;
+                                            S.score[s] = d_score[di]; S.cls[s] = d_cls[di]; S.det_id[s] = d_id[di];
+                                        });
+            const int nb_ok = nb < nfree ? nb : nfree;
+            if (lane_id() == 0) { S.hdr[5] = nfree - nb_ok; S.hdr[1] = id0 + nb_ok; sh->n_births = nb_ok; }
         }
         __syncthreads();
+        PH(15);
         for (int k = tid; k < sh->n_births; k += BT_THREADS) bt_kf_initiate(S, birth_slot[k], d_box + 4 * births[k]);
-        if (tid == 0) {
-            const int nt = sh->n_tracked, nlost = sh->n_lost;
+        if (warp_id() == 0) {
+            const int lane = lane_id();
+            const int nt = sh->n_tracked, nlost = sh->n_lost, nb = sh->n_births;
             // ageing of the OLD lost list; removed_now membership is applied to in_removed after the subtraction
-            for (int k = 0; k < nlost; ++k) {
+            for (int k = lane; k < nlost; k += 32) {
                 const int s = S.lost[k];
-                dup_b[k] = 0;
-                if (frame_id - S.frame_id[s] > prm.max_time_lost) { S.state[s] = ST_REMOVED; dup_b[k] = 1; }
+                const bool aged = frame_id - S.frame_id[s] > prm.max_time_lost;
+                if (aged) S.state[s] = ST_REMOVED;
+                dup_b[k] = aged ? 1 : 0;
             }
+            for (int k = lane; k < cap; k += 32) in_tracked[k] = 0;
+            __syncwarp();
             // tracked' = [old tracked still Tracked] + births + refinds(lost order)
-            int n = 0;
-            for (int k = 0; k < cap; ++k) in_tracked[k] = 0;
-            for (int k = 0; k < nt; ++k) {
-                const int s = S.tracked[k];
-                if (S.state[s] == ST_TRACKED) { newlist[n++] = s; in_tracked[s] = 1; }
-            }
-            for (int k = 0; k < sh->n_births; ++k) { newlist[n++] = birth_slot[k]; in_tracked[birth_slot[k]] = 1; }
-            for (int k = 0; k < nlost; ++k) {
-                const int s = S.lost[k];
-                if (S.state[s] == ST_TRACKED && !in_tracked[s]) { newlist[n++] = s; in_tracked[s] = 1; }
-            }
-            // lost' = (old lost - tracked') + lost_now, minus everything that was in `removed` BEFORE this frame
-            int m = 0;
+            int n = warp_compact(nt, 0, [&](int k) { return S.state[S.tracked[k]] == ST_TRACKED; },
+                                 [&](int k, int p) { const int s = S.tracked[k]; newlist[p] = s; in_tracked[s] = 1; });
+            for (int k = lane; k < nb; k += 32) { newlist[n + k] = birth_slot[k]; in_tracked[birth_slot[k]] = 1; }
+            n += nb;
+            __syncwarp();
+            n = warp_compact(nlost, n, [&](int k) { const int s = S.lost[k]; return S.state[s] == ST_TRACKED && !in_tracked[s]; },
+                             [&](int k, int p) { const int s = S.lost[k]; newlist[p] = s; in_tracked[s] = 1; });
+            // free-list pushes (slot numbers are anonymous, their order is irrelevant)
             int nfree = S.hdr[5];
-            for (int k = 0; k < nlost; ++k) {
-                const int s = S.lost[k];
-                if (in_tracked[s]) continue;
-                if (S.in_removed[s]) { S.free_list[nfree++] = s; continue; }   // dropped from every list
-                if (dup_b[k]) S.in_removed[s] = 1;                                // removed_now -> removed (after the subtraction)
-                rest[m++] = s;                                                    // reuse `rest` as the new lost list
-            }
-            for (int k = 0; k < sh->n_lostnow; ++k) {
-                const int s = lostnow[k];
-                if (S.in_removed[s]) { S.free_list[nfree++] = s; continue; }
-                rest[m++] = s;
-            }
-            // unconfirmed tracks that were removed leave `tracked`; free their slots
-            for (int k = 0; k < nt; ++k) {
-                const int s = S.tracked[k];
-                if (S.state[s] == ST_REMOVED && !S.activated[s]) S.free_list[nfree++] = s;
-            }
-            S.hdr[5] = nfree;
-            for (int k = 0; k < n; ++k) S.tracked[k] = newlist[k];
-            for (int k = 0; k < m; ++k) S.lost[k] = rest[k];
-            sh->n_tracked = n; sh->n_lost = m;
+            nfree = warp_compact(nlost, nfree, [&](int k) { const int s = S.lost[k]; return !in_tracked[s] && S.in_removed[s]; },
+                                 [&](int k, int p) { S.free_list[p] = S.lost[k]; });
+            nfree = warp_compact(sh->n_lostnow, nfree, [&](int k) { return S.in_removed[lostnow[k]] != 0; },
+                                 [&](int k, int p) { S.free_list[p] = lostnow[k]; });
+            nfree = warp_compact(nt, nfree, [&](int k) { const int s = S.tracked[k]; return S.state[s] == ST_REMOVED && !S.activated[s]; },
+                                 [&](int k, int p) { S.free_list[p] = S.tracked[k]; });
+            // lost' = (old lost - tracked') + lost_now, minus everything that was in `removed` BEFORE this frame
+            int m = warp_compact(nlost, 0, [&](int k) { const int s = S.lost[k]; return !in_tracked[s] && !S.in_removed[s]; },
+                                 [&](int k, int p) { const int s = S.lost[k]; if (dup_b[k]) S.in_removed[s] = 1; rest[p] = s; });
+            m = warp_compact(sh->n_lostnow, m, [&](int k) { return S.in_removed[lostnow[k]] == 0; }, [&](int k, int p) { rest[p] = lostnow[k]; });
+            for (int k = lane; k < n; k += 32) S.tracked[k] = newlist[k];
+            for (int k = lane; k < m; k += 32) S.lost[k] = rest[k];
+            if (lane == 0) { S.hdr[5] = nfree; sh->n_tracked = n; sh->n_lost = m; }
         }
         __syncthreads();
+        PH(16);
 
         // ---- H. remove_duplicate_stracks (byte_tracker.py:348-361) ------------------------------
         {
@@ -546,6 +609,7 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
                 dup_b[k] = 0;
             }
             __syncthreads();
+            PH(17);
             for (int e = tid; e < nt * nlost; e += BT_THREADS) {
                 const int p = e / nlost, q = e % nlost;
                 const float dist = iou_dist_p1(t_tlbr + 4 * p, t_tlbr2 + 4 * q);
@@ -557,25 +621,31 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
                 }
             }
             __syncthreads();
-            if (tid == 0) {
-                int n = 0, m = 0, nfree = S.hdr[5];
-                for (int k = 0; k < nt; ++k) {
-                    const int s = S.tracked[k];
-                    if (dup_a[k]) S.free_list[nfree++] = s; else S.tracked[n++] = s;
-                }
-                for (int k = 0; k < nlost; ++k) {
-                    const int s = S.lost[k];
-                    if (dup_b[k]) S.free_list[nfree++] = s; else S.lost[m++] = s;
-                }
-                S.hdr[5] = nfree; S.hdr[2] = n; S.hdr[3] = m;
+            PH(18);
+            if (warp_id() == 0) {
+                int nfree = S.hdr[5];
+                nfree = warp_compact(nt, nfree, [&](int k) { return dup_a[k] != 0; }, [&](int k, int p) { S.free_list[p] = S.tracked[k]; });
+                nfree = warp_compact(nlost, nfree, [&](int k) { return dup_b[k] != 0; }, [&](int k, int p) { S.free_list[p] = S.lost[k]; });
+                // in-place ordered compaction is safe: every lane reads its element before the ballot, writes land at <= its index
+                const int n = warp_compact(nt, 0, [&](int k) { return dup_a[k] == 0; },
+                                           [&](int k, int p) { const int s = S.tracked[k]; newlist[p] = s; });
+                for (int k = lane_id(); k < n; k += 32) S.tracked[k] = newlist[k];
+                const int m = warp_compact(nlost, 0, [&](int k) { return dup_b[k] == 0; },
+                                           [&](int k, int p) { const int s = S.lost[k]; rest[p] = s; });
+                for (int k = lane_id(); k < m; k += 32) S.lost[k] = rest[k];
+                __syncwarp();
                 // ---- I. output rows of activated tracks (byte_tracker.py:301-318)
-                int cnt = 0;
-                for (int k = 0; k < n; ++k) out_pos[k] = S.activated[S.tracked[k]] ? cnt++ : -1;
-                sh->n_tracked = n;
-                sh->nd = cnt;
-                out_frame_count[seq * n_frames + f] = cnt;
+                for (int k = lane_id(); k < n; k += 32) out_pos[k] = -1;
+                __syncwarp();
+                const int cnt = warp_compact(n, 0, [&](int k) { return S.activated[S.tracked[k]] != 0; }, [&](int k, int p) { out_pos[k] = p; });
+                if (lane_id() == 0) {
+                    S.hdr[5] = nfree; S.hdr[2] = n; S.hdr[3] = m;
+                    sh->n_tracked = n; sh->nd = cnt;
+                    out_frame_count[seq * n_frames + f] = cnt;
+                }
             }
             __syncthreads();
+            PH(19);
         }
         {
             const int n = sh->n_tracked;
@@ -600,8 +670,18 @@ bytetrack_video_kernel(BtParams prm, char* state_base, size_t state_stride, int 
             out_n += sh->nd;
         }
         __syncthreads();
+        PH(20);
     }
     if (tid == 0) out_count[seq] = out_n;
+    // write the book-keeping back for the next chunk of frames
+    __syncthreads();
+    if (tid < 8) G.hdr[tid] = S.hdr[tid];
+    for (int i = tid; i < cap; i += BT_THREADS) {
+        G.score[i] = S.score[i]; G.cls[i] = S.cls[i]; G.det_id[i] = S.det_id[i];
+        G.track_id[i] = S.track_id[i]; G.frame_id[i] = S.frame_id[i]; G.start_frame[i] = S.start_frame[i];
+        G.tracked[i] = S.tracked[i]; G.lost[i] = S.lost[i]; G.free_list[i] = S.free_list[i];
+        G.state[i] = S.state[i]; G.activated[i] = S.activated[i]; G.mean_f32[i] = S.mean_f32[i]; G.in_removed[i] = S.in_removed[i];
+    }
 }
 
 struct BtHandle {
@@ -642,6 +722,7 @@ size_t bt_smem_fixed(int cap, int capd) {
     s += 2 * al(sizeof(int) * cap);
     s += 3 * al((size_t)cap);
     s += al(sizeof(BtShared));
+    s += al(8 * sizeof(int)) + 3 * al(sizeof(double) * cap) + 6 * al(sizeof(int) * cap) + 4 * al((size_t)cap);   // book-keeping mirror
     return s;
 }
 
@@ -712,6 +793,15 @@ int tk_bytetrack_status(void* handle, int* status_host, void* stream) {
     TK_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return TK_OK;
 }
+
+#ifdef TK_PHASE_PROF
+int tk_debug_bytetrack_phases(unsigned long long* host_out64, int reset) {
+    cudaDeviceSynchronize();
+    if (host_out64) cudaMemcpyFromSymbol(host_out64, g_bt_prof, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_bt_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int tk_bytetrack_destroy(void* handle) {
     if (!handle) return TK_ERR_ARG;

@@ -135,4 +135,130 @@ __device__ __forceinline__ double kf8_maha(const double* m, const double* L, con
     return acc;
 }
 
+// ---- octet-cooperative variants: 8 consecutive lanes own one track, lane j holds row j of P and mean[j] ------------
+// One thread per track keeps 100+ doubles live (spills to local memory, ~13k cycles of dependent latency per update
+// on sm_100a); spreading a track over 8 lanes keeps everything in registers, makes the 512-byte covariance one
+// coalesced read per octet, and cuts the critical path to the 4x4 Cholesky (done redundantly by the 8 lanes).
+// The arithmetic (formulas and summation order) is identical to kf8_predict / kf8_update above.
+// All 32 lanes of the warp must call these; `active` is uniform within an octet.
+
+__device__ __forceinline__ double oct_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 8); }
+
+// q = process-noise variance of this lane's state index j (caller computes the model-specific value)
+__device__ __forceinline__ void kf8_octet_predict(double* __restrict__ gm, double* __restrict__ gP, bool active, bool zero_vh, double qj) {
+    const int j = threadIdx.x & 7;
+    double row[8], m = 0.0;
+    if (active) {
+        m = gm[j];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) row[c] = gP[j * 8 + c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) row[c] = 0.0;
+    }
+    if (zero_vh && j == 7) m = 0.0;
+    const double m_hi = oct_bcast(m, (j + 4) & 7);
+    if (j < 4) m = m + m_hi;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const double hi = oct_bcast(row[c], (j + 4) & 7);
+        if (j < 4) row[c] = row[c] + hi;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) row[c] = row[c] + row[c + 4];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c == j) row[c] = row[c] + qj;
+    if (active) {
+        gm[j] = m;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) gP[j * 8 + c] = row[c];
+    }
+}
+
+// z[4]: measurement, r[4]: measurement-noise variances (both uniform within the octet). Returns false if S is not PD.
+__device__ __forceinline__ bool kf8_octet_update(double* __restrict__ gm, double* __restrict__ gP, bool active,
+                                                 const double* z, const double* r) {
+    const int j = threadIdx.x & 7;
+    double row[8], m = 0.0;
+    if (active) {
+        m = gm[j];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) row[c] = gP[j * 8 + c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) row[c] = (c == j) ? 1.0 : 0.0;
+    }
+    double S[16], L[16], invd[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double v = oct_bcast(row[b], a);
+            S[a * 4 + b] = (a == b) ? v + r[a] : v;
+        }
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double d = S[c * 4 + c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) d -= L[c * 4 + k] * L[c * 4 + k];
+        ok = ok && (d > 0.0);
+        const double lcc = sqrt(d);
+        L[c * 4 + c] = lcc;
+        invd[c] = 1.0 / lcc;
+#pragma unroll
+        for (int i = c + 1; i < 4; ++i) {
+            double s = S[i * 4 + c];
+#pragma unroll
+            for (int k = 0; k < c; ++k) s -= L[i * 4 + k] * L[c * 4 + k];
+            L[i * 4 + c] = s * invd[c];
+        }
+    }
+    // gain row of this lane: K[j][:] = solve(S, P[j][:4])
+    double K[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double s = row[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) s -= L[i * 4 + k] * K[k];
+        K[i] = s * invd[i];
+    }
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+        double s = K[i];
+#pragma unroll
+        for (int k = i + 1; k < 4; ++k) s -= L[k * 4 + i] * K[k];
+        K[i] = s * invd[i];
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double mi = oct_bcast(m, i);
+        acc += (z[i] - mi) * K[i];
+    }
+    m = m + acc;
+    // T[:, j] = S K[j]^T, then P[j][b] -= sum_i K[j][i] T[i][b]
+    double t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s += S[i * 4 + k] * K[k];
+        t[i] = s;
+    }
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s += K[i] * oct_bcast(t[i], b);
+        row[b] = row[b] - s;
+    }
+    if (active) {
+        gm[j] = m;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) gP[j * 8 + c] = row[c];
+    }
+    return ok || !active;
+}
+
 }  // namespace tk

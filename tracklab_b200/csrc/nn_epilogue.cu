@@ -18,7 +18,14 @@ namespace {
 
 struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with the two MUFU approximations (ex2, rcp): 5 issue slots instead of ~20 for expf + IEEE division.
+// The pass is close to issue-bound at HBM speed (8 activations per 32 bytes moved), and the result is rounded to bf16.
+__device__ __forceinline__ float silu_f(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
 
 // src [n_pix, C] contiguous; dst / res rows of pitch dst_pitch / res_pitch elements, channel offsets given.
 __global__ void __launch_bounds__(256)

@@ -332,6 +332,23 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
     unsigned char* flag_d = (unsigned char*)take(capd);
     unsigned char* flag_t = (unsigned char*)take(cap);
     OcShared* sh = (OcShared*)take(sizeof(OcShared));
+    // per-slot scalars and the small observation records are mirrored in shared memory for the whole launch
+    // (the frame loop is a chain of short serial list edits; global round trips there are pure latency)
+    const OcDev G = S;
+#define OC_MIRROR(X) X(last_obs, double, 5) X(vel, double, 2) X(last_z, double, 4) X(conf, double, 1) X(cls, double, 1) \
+    X(det_id, double, 1) X(tsu, int, 1) X(uid, int, 1) X(hits, int, 1) X(streak, int, 1) X(age, int, 1) X(hist_len, int, 1) \
+    X(frozen_n, int, 1) X(last_z_idx, int, 1) X(list, int, 1) X(free_list, int, 1) X(has_vel, unsigned char, 1)           \
+    X(observed, unsigned char, 1) X(frozen, unsigned char, 1)
+    {
+        int* m_hdr = (int*)take(8 * sizeof(int));
+        if (tid < 8) m_hdr[tid] = G.hdr[tid];
+        S.hdr = m_hdr;
+#define X(name, type, n) { type* m = (type*)take(sizeof(type) * (size_t)cap * (n)); \
+        for (int i = tid; i < cap * (n); i += OC_THREADS) m[i] = G.name[i]; S.name = m; }
+        OC_MIRROR(X)
+#undef X
+        __syncthreads();
+    }
     double* iou_m = cost_in_smem ? (double*)take(sizeof(double) * (size_t)(cap + 1) * (capd + 1)) : cost_scratch + (size_t)seq * cost_stride * 2;
     double* cost = cost_in_smem ? (double*)take(0) : iou_m + cost_stride;
 
@@ -637,6 +654,11 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
         __syncthreads();
     }
     if (tid == 0) out_count[seq] = out_n;
+    __syncthreads();
+    if (tid < 8) G.hdr[tid] = S.hdr[tid];
+#define X(name, type, n) for (int i = tid; i < cap * (n); i += OC_THREADS) G.name[i] = S.name[i];
+    OC_MIRROR(X)
+#undef X
 }
 
 struct OcHandle {
@@ -662,6 +684,9 @@ size_t oc_smem_fixed(int cap, int capd) {
     s += 2 * al(sizeof(int) * capd) + 4 * al(sizeof(int) * side);
     s += al(sizeof(int) * capd) + al(sizeof(int) * cap) + al(sizeof(int) * capd) + al(sizeof(int) * cap);
     s += 2 * al(sizeof(int) * side) + al((size_t)capd) + al((size_t)cap) + al(sizeof(OcShared));
+    // book-keeping mirror: hdr + per-slot records (see OC_MIRROR in the kernel)
+    s += al(8 * sizeof(int)) + al(sizeof(double) * cap * 5) + al(sizeof(double) * cap * 2) + al(sizeof(double) * cap * 4)
+       + 3 * al(sizeof(double) * cap) + 10 * al(sizeof(int) * cap) + 3 * al((size_t)cap);
     return s;
 }
 
