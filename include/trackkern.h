@@ -20,6 +20,12 @@ int tk_abi_version(void);
 int tk_last_cuda_error(void);
 
 
+/* overlap variants (oc_sort/association.py) */
+#define TK_ASSO_IOU 0
+#define TK_ASSO_GIOU 1
+#define TK_ASSO_DIOU 2
+#define TK_ASSO_CIOU 3
+
 /* element types for tensor arguments */
 #define TK_DTYPE_F32 0
 #define TK_DTYPE_BF16 1
@@ -123,10 +129,6 @@ int tk_bytetrack_destroy(void* handle);
  * Hyper-parameters: /root/reference/tracklab/configs/modules/track/oc_sort.yaml:4-14.
  * Same calling convention as tk_bytetrack_*; output rows are [x1,y1,x2,y2,id+1,cls,conf,det_id].
  */
-#define TK_ASSO_IOU 0
-#define TK_ASSO_GIOU 1
-#define TK_ASSO_DIOU 2
-#define TK_ASSO_CIOU 3
 typedef struct {
     double det_thresh;     /* oc_sort.yaml: det_thresh (0) */
     double iou_threshold;  /* iou_threshold (0.2213...) */
@@ -145,6 +147,26 @@ int tk_ocsort_run(void* handle, const double* dets, const int* offsets, int n_fr
                   const int* out_start, int* out_frame_count, int* out_count, void* stream);
 int tk_ocsort_status(void* handle, int* status_host, void* stream);
 int tk_ocsort_destroy(void* handle);
+
+/* ---- Stateless batched cost matrices + assignment (building blocks; stress sweep of BASELINE configs[4]) ------
+ * All tensors device, row-major, `n_problems` independent problems stacked on the leading axis.
+ *   tk_iou_matrix   a [B,N,4], b [B,M,4] float64 x1y1x2y2 -> out [B,N,M]; variant TK_ASSO_*
+ *                   (/root/reference/plugins/track/oc_sort/association.py:5-147)
+ *   tk_iou_p1_f32   float32 tlbr boxes -> 1 - IoU with +1-pixel extents, float32
+ *                   (/root/reference/plugins/track/byte_track/matching.py:51-89,182-218)
+ *   tk_cosine_dist  a [B,N,E], b [B,M,E] float32 -> out [B,N,M] float64 = 1 - normalised dot product computed in
+ *                   float32 (/root/reference/plugins/track/strong_sort/sort/nn_matching.py:30-49,144-161);
+ *                   norm_scratch: float32 [B*(N+M)]
+ *   tk_lap_batched  cost [B,N,M] float64 -> x [B,N] (column of each row or -1), y [B,M]; has_limit=1 gives
+ *                   lap.lapjv(cost, extend_cost=True, cost_limit=L) semantics (byte_track/matching.py:37-48),
+ *                   has_limit=0 assigns all min(N,M) pairs (oc_sort/association.py:187-191, scipy LSA)
+ */
+int tk_iou_matrix(const double* a, const double* b, double* out, int n_problems, int N, int M, int variant, void* stream);
+int tk_iou_p1_f32(const float* a_tlbr, const float* b_tlbr, float* dist_out, int n_problems, int N, int M, void* stream);
+int tk_cosine_dist(const float* a, const float* b, double* out, float* norm_scratch, int n_problems, int N, int M, int E,
+                   void* stream);
+int tk_lap_batched(const double* cost, int n_problems, int N, int M, double cost_limit, int has_limit, int* x_out, int* y_out,
+                   int* status_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -30,7 +30,11 @@ def test_ocsort_matches_reference_golden(name, cap):
     print(name, "max box err", err)
 
 
-@pytest.mark.parametrize("asso", ["iou", "giou", "diou", "ciou"])
+# diou/ciou are not exercised through the whole tracker: against the [-1,-1,-1,-1] placeholder "last observation" of a
+# track born in the previous frame they give every track the SAME positive score (association.py:58-147 on a point box),
+# so the reference's OCR round (ocsort.py:284-306) is a pure solver tie there. Their arithmetic is pinned per element in
+# tests/test_pairwise_gpu.py instead.
+@pytest.mark.parametrize("asso", ["iou", "giou"])
 def test_ocsort_matches_oracle_fresh_seed(asso):
     from oracle.ocsort_np import OCSortOracle
     video = make_video(seed=21, n_frames=150, n_ids=50, conf_range=(0.2, 1.0))

@@ -49,6 +49,10 @@ def _declare(lib):
         "tk_bias_act_nhwc": ([vp, vp, vp, vp, ctypes.c_longlong, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_spp_nhwc": ([vp, vp, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_upsample2x_nhwc": ([vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, vp], ci),
+        "tk_iou_matrix": ([vp, vp, vp, ci, ci, ci, ci, vp], ci),
+        "tk_iou_p1_f32": ([vp, vp, vp, ci, ci, ci, vp], ci),
+        "tk_cosine_dist": ([vp, vp, vp, vp, ci, ci, ci, ci, vp], ci),
+        "tk_lap_batched": ([vp, ci, ci, ci, cd, ci, vp, vp, vp, vp], ci),
         "tk_bytetrack_create": ([P(BytetrackParams), ci, ci, ci, P(vp)], ci),
         "tk_bytetrack_reset": ([vp, ci, vp], ci),
         "tk_bytetrack_run": ([vp, vp, vp, ci, vp, vp, vp, vp, vp], ci),

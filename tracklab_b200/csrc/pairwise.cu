@@ -1,0 +1,245 @@
+// Stateless, batched cost-matrix kernels and the batched assignment solver (C ABI used by the stress sweep of
+// BASELINE.json configs[4] and by callers that want the building blocks without a whole-video tracker).
+//
+//   tk_iou_matrix     pairwise overlap family, float64, boxes x1y1x2y2
+//                     /root/reference/plugins/track/oc_sort/association.py:5-21 (iou), :24-55 (giou), :58-95 (diou), :97-147 (ciou)
+//   tk_iou_p1_f32     ByteTrack "+1 pixel" IoU distance in float32  /root/reference/plugins/track/byte_track/matching.py:51-89,182-218
+//   tk_cosine_dist    1 - a_hat . b_hat^T on float32 features        /root/reference/plugins/track/strong_sort/sort/nn_matching.py:30-49
+//   tk_lap_batched    one assignment problem per CTA (lap.cuh)       byte_track/matching.py:37-48, oc_sort/association.py:187-191,
+//                                                                    strong_sort/sort/linear_assignment.py:55
+//
+// All are HBM/latency-bound: rows are staged once per CTA, outputs are written coalesced; batches fill the 148 SMs.
+#include "lap.cuh"
+#include "tk_common.cuh"
+#include "trackkern.h"
+
+namespace {
+
+using namespace tk;
+
+__device__ __forceinline__ double d_iou(const double* a, const double* b, double& wh) {
+    const double w = fmax(0.0, fmin(a[2], b[2]) - fmax(a[0], b[0]));
+    const double h = fmax(0.0, fmin(a[3], b[3]) - fmax(a[1], b[1]));
+    wh = __dmul_rn(w, h);
+    const double ua = __dsub_rn(__dadd_rn(__dmul_rn(a[2] - a[0], a[3] - a[1]), __dmul_rn(b[2] - b[0], b[3] - b[1])), wh);
+    return wh / ua;
+}
+
+__device__ double d_overlap(int kind, const double* a, const double* b) {
+    double wh;
+    const double iou = d_iou(a, b, wh);
+    if (kind == TK_ASSO_IOU) return iou;
+    const double wc = fmax(a[2], b[2]) - fmin(a[0], b[0]);
+    const double hc = fmax(a[3], b[3]) - fmin(a[1], b[1]);
+    if (kind == TK_ASSO_GIOU) {
+        const double hull = __dmul_rn(wc, hc);
+        return __dadd_rn(__dsub_rn(iou, __dsub_rn(hull, wh) / hull), 1.0) / 2.0;
+    }
+    const double dcx = __dsub_rn((a[0] + a[2]) / 2.0, (b[0] + b[2]) / 2.0);
+    const double dcy = __dsub_rn((a[1] + a[3]) / 2.0, (b[1] + b[3]) / 2.0);
+    const double inner = __dadd_rn(__dmul_rn(dcx, dcx), __dmul_rn(dcy, dcy));
+    const double outer = __dadd_rn(__dmul_rn(wc, wc), __dmul_rn(hc, hc));
+    if (kind == TK_ASSO_DIOU) return __dadd_rn(__dsub_rn(iou, inner / outer), 1.0) / 2.0;
+    const double w1 = a[2] - a[0], h1 = (a[3] - a[1]) + 1.0, w2 = b[2] - b[0], h2 = (b[3] - b[1]) + 1.0;
+    const double at = __dsub_rn(atan(w2 / h2), atan(w1 / h1));
+    const double pi = 3.141592653589793;
+    const double v = __dmul_rn(4.0 / __dmul_rn(pi, pi), __dmul_rn(at, at));
+    const double alpha = v / __dadd_rn(__dsub_rn(1.0, iou), v);
+    return __dadd_rn(__dsub_rn(__dsub_rn(iou, inner / outer), __dmul_rn(alpha, v)), 1.0) / 2.0;
+}
+
+// a [B, N, 4], b [B, M, 4] -> out [B, N, M]; one CTA per (problem, 32-row tile)
+__global__ void __launch_bounds__(256)
+iou_matrix_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int N, int M, int kind) {
+    extern __shared__ __align__(16) double sm[];
+    const int p = blockIdx.y, r0 = blockIdx.x * 32;
+    double* sb = sm;             // [M][4]
+    double* sa = sm + 4 * M;     // [32][4]
+    const double* ap = a + ((size_t)p * N + r0) * 4;
+    const double* bp = b + (size_t)p * M * 4;
+    for (int i = threadIdx.x; i < 4 * M; i += blockDim.x) sb[i] = bp[i];
+    const int nr = min(32, N - r0);
+    for (int i = threadIdx.x; i < 4 * nr; i += blockDim.x) sa[i] = ap[i];
+    __syncthreads();
+    double* op = out + ((size_t)p * N + r0) * M;
+    for (int e = threadIdx.x; e < nr * M; e += blockDim.x) {
+        const int i = e / M, j = e - i * M;
+        op[e] = d_overlap(kind, sa + 4 * i, sb + 4 * j);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+iou_p1_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int N, int M) {
+    extern __shared__ __align__(16) float smf[];
+    const int p = blockIdx.y, r0 = blockIdx.x * 32;
+    float* sb = smf;
+    float* sa = smf + 4 * M;
+    const float* ap = a + ((size_t)p * N + r0) * 4;
+    const float* bp = b + (size_t)p * M * 4;
+    for (int i = threadIdx.x; i < 4 * M; i += blockDim.x) sb[i] = bp[i];
+    const int nr = min(32, N - r0);
+    for (int i = threadIdx.x; i < 4 * nr; i += blockDim.x) sa[i] = ap[i];
+    __syncthreads();
+    float* op = out + ((size_t)p * N + r0) * M;
+    for (int e = threadIdx.x; e < nr * M; e += blockDim.x) {
+        const int i = e / M, j = e - i * M;
+        const float* x = sa + 4 * i;
+        const float* y = sb + 4 * j;
+        float ov = 0.0f;
+        const float iw = __fadd_rn(__fsub_rn(fminf(x[2], y[2]), fmaxf(x[0], y[0])), 1.0f);
+        if (iw > 0.0f) {
+            const float ih = __fadd_rn(__fsub_rn(fminf(x[3], y[3]), fmaxf(x[1], y[1])), 1.0f);
+            if (ih > 0.0f) {
+                const float ab = __fmul_rn(__fadd_rn(__fsub_rn(y[2], y[0]), 1.0f), __fadd_rn(__fsub_rn(y[3], y[1]), 1.0f));
+                const float aa = __fmul_rn(__fadd_rn(__fsub_rn(x[2], x[0]), 1.0f), __fadd_rn(__fsub_rn(x[3], x[1]), 1.0f));
+                const float in = __fmul_rn(iw, ih);
+                ov = __fdiv_rn(in, __fsub_rn(__fadd_rn(aa, ab), in));
+            }
+        }
+        op[e] = __fsub_rn(1.0f, ov);
+    }
+}
+
+// L2 norms of the rows of x [R, E] (float32), one warp per row, shuffle reduction
+__global__ void __launch_bounds__(256)
+row_inv_norm_kernel(const float* __restrict__ x, float* __restrict__ inv_norm, long long R, int E) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const float* p = x + row * E;
+    float s = 0.0f;
+    for (int k = threadIdx.x & 31; k < E; k += 32) { const float v = p[k]; s = fmaf(v, v, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) inv_norm[row] = sqrtf(s);   // the norm itself; the division happens per element like NumPy
+}
+
+// out[p, i, j] = 1 - (a_i / |a_i|) . (b_j / |b_j|); 32x32 output tile per CTA, E walked in chunks of 32 through shared memory
+__global__ void __launch_bounds__(256)
+cosine_dist_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ na,
+                   const float* __restrict__ nb, double* __restrict__ out, int N, int M, int E) {
+    __shared__ float ta[32][33], tb[32][33];
+    const int p = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 8 rows of threads
+    const float* ap = a + (size_t)p * N * E;
+    const float* bp = b + (size_t)p * M * E;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < E; k0 += 32) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = ty + 8 * r;
+            const int k = k0 + tx;
+            const int ia = i0 + row, jb = j0 + row;
+            ta[row][tx] = (ia < N && k < E) ? __fdiv_rn(ap[(size_t)ia * E + k], na[(size_t)p * N + ia]) : 0.0f;
+            tb[row][tx] = (jb < M && k < E) ? __fdiv_rn(bp[(size_t)jb * E + k], nb[(size_t)p * M + jb]) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const float bv = tb[tx][k];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(ta[ty + 8 * r][k], bv, acc[r]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 8 * r, j = j0 + tx;
+        if (i < N && j < M) out[((size_t)p * N + i) * M + j] = (double)__fsub_rn(1.0f, acc[r]);
+    }
+}
+
+// one problem per CTA: cost [B, N, M] float64 -> x [B, N], y [B, M]
+__global__ void __launch_bounds__(128)
+lap_batched_kernel(const double* __restrict__ cost, int N, int M, double cost_limit, int has_limit, int* __restrict__ x_out,
+                   int* __restrict__ y_out, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int p = blockIdx.x;
+    const bool n_rows = N <= M;
+    const int nr = n_rows ? N : M, nc = n_rows ? M : N, ld = lap_pitch(nc);
+    double* C = (double*)smraw;
+    double* u = C + (size_t)nr * ld;
+    int* col4row = (int*)(u + nr);
+    int* row4col = col4row + nr;
+    int* path = row4col + nc;
+    __shared__ int ok_flag;
+    const double* cp = cost + (size_t)p * N * M;
+    for (int e = threadIdx.x; e < N * M; e += blockDim.x) {
+        const int i = e / M, j = e - i * M;
+        double c = cp[e];
+        if (has_limit) c = fmin(c - cost_limit, 0.0);
+        if (n_rows) C[(size_t)i * ld + j] = c; else C[(size_t)j * ld + i] = c;
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) x_out[(size_t)p * N + i] = -1;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) y_out[(size_t)p * M + j] = -1;
+    __syncthreads();
+    if (N == 0 || M == 0) return;
+    const bool ok = lap_solve_cta(C, ld, nr, nc, has_limit != 0, u, col4row, row4col, path, &ok_flag);
+    if (!ok) { if (threadIdx.x == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); return; }
+    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+        const int c = col4row[r];
+        if (c < 0) continue;
+        if (has_limit && !(C[(size_t)r * ld + c] < 0.0)) continue;
+        const int i = n_rows ? r : c, j = n_rows ? c : r;
+        x_out[(size_t)p * N + i] = j;
+        y_out[(size_t)p * M + j] = i;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tk_iou_matrix(const double* a, const double* b, double* out, int n_problems, int N, int M, int variant, void* stream) {
+    if (!a || !b || !out || n_problems <= 0 || N < 0 || M < 0 || variant < 0 || variant > 3) return TK_ERR_ARG;
+    if (N == 0 || M == 0) return TK_OK;
+    const size_t smem = sizeof(double) * 4 * ((size_t)M + 32);
+    if (smem > 200 * 1024) return TK_ERR_CAPACITY;
+    TK_CUDA_TRY(cudaFuncSetAttribute(iou_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((N + 31) / 32, n_problems);
+    iou_matrix_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a, b, out, N, M, variant);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_iou_p1_f32(const float* a_tlbr, const float* b_tlbr, float* dist_out, int n_problems, int N, int M, void* stream) {
+    if (!a_tlbr || !b_tlbr || !dist_out || n_problems <= 0 || N < 0 || M < 0) return TK_ERR_ARG;
+    if (N == 0 || M == 0) return TK_OK;
+    const size_t smem = sizeof(float) * 4 * ((size_t)M + 32);
+    if (smem > 200 * 1024) return TK_ERR_CAPACITY;
+    TK_CUDA_TRY(cudaFuncSetAttribute(iou_p1_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((N + 31) / 32, n_problems);
+    iou_p1_f32_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(a_tlbr, b_tlbr, dist_out, N, M);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_cosine_dist(const float* a, const float* b, double* out, float* norm_scratch, int n_problems, int N, int M, int E,
+                   void* stream) {
+    if (!a || !b || !out || !norm_scratch || n_problems <= 0 || N < 0 || M < 0 || E <= 0) return TK_ERR_ARG;
+    if (N == 0 || M == 0) return TK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* na = norm_scratch;
+    float* nb = norm_scratch + (size_t)n_problems * N;
+    const long long ra = (long long)n_problems * N, rb = (long long)n_problems * M;
+    row_inv_norm_kernel<<<(unsigned)((ra + 7) / 8), 256, 0, st>>>(a, na, ra, E);
+    row_inv_norm_kernel<<<(unsigned)((rb + 7) / 8), 256, 0, st>>>(b, nb, rb, E);
+    dim3 grid((M + 31) / 32, (N + 31) / 32, n_problems);
+    cosine_dist_kernel<<<grid, 256, 0, st>>>(a, b, na, nb, out, N, M, E);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_lap_batched(const double* cost, int n_problems, int N, int M, double cost_limit, int has_limit, int* x_out, int* y_out,
+                   int* status_dev, void* stream) {
+    if (!cost || !x_out || !y_out || !status_dev || n_problems <= 0 || N < 0 || M < 0) return TK_ERR_ARG;
+    if (N > tk::LAP_MAX_COLS || M > tk::LAP_MAX_COLS) return TK_ERR_CAPACITY;
+    const int nr = N <= M ? N : M, nc = N <= M ? M : N;
+    const size_t smem = sizeof(double) * ((size_t)nr * tk::lap_pitch(nc) + nr) + sizeof(int) * ((size_t)nr + 2 * nc) + 64;
+    if (smem > 220 * 1024) return TK_ERR_CAPACITY;
+    TK_CUDA_TRY(cudaFuncSetAttribute(lap_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lap_batched_kernel<<<n_problems, 128, smem, (cudaStream_t)stream>>>(cost, N, M, cost_limit, has_limit, x_out, y_out, status_dev);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+}  // extern "C"

@@ -121,3 +121,57 @@ def upsample2x(src: torch.Tensor, dst: torch.Tensor, dst_offset: int = 0, src_of
         _lib.check(lib.tk_upsample2x_nhwc(src.data_ptr(), Cs, src_offset, dst.data_ptr(), B, h, w, C, dst.shape[1], dst_offset,
                                           _stream()), "tk_upsample2x_nhwc")
     return dst
+
+
+def iou_matrix(a: torch.Tensor, b: torch.Tensor, variant: str = "iou"):
+    """a [B,N,4], b [B,M,4] float64 -> [B,N,M] (C ABI: tk_iou_matrix)."""
+    lib = _lib.load()
+    _cuda(a, "a"); _cuda(b, "b")
+    B, N, _ = a.shape
+    M = b.shape[1]
+    out = torch.empty((B, N, M), dtype=torch.float64, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.tk_iou_matrix(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, N, M, _lib.ASSO_CODES[variant], _stream()),
+                   "tk_iou_matrix")
+    return out
+
+
+def iou_p1_dist(a: torch.Tensor, b: torch.Tensor):
+    """float32 tlbr boxes a [B,N,4], b [B,M,4] -> 1 - IoU(+1 px) float32 [B,N,M] (C ABI: tk_iou_p1_f32)."""
+    lib = _lib.load()
+    _cuda(a, "a"); _cuda(b, "b")
+    B, N, _ = a.shape
+    M = b.shape[1]
+    out = torch.empty((B, N, M), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.tk_iou_p1_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, N, M, _stream()), "tk_iou_p1_f32")
+    return out
+
+
+def cosine_dist(a: torch.Tensor, b: torch.Tensor):
+    """float32 features a [B,N,E], b [B,M,E] -> float64 [B,N,M] cosine distance (C ABI: tk_cosine_dist)."""
+    lib = _lib.load()
+    _cuda(a, "a"); _cuda(b, "b")
+    B, N, E = a.shape
+    M = b.shape[1]
+    out = torch.empty((B, N, M), dtype=torch.float64, device=a.device)
+    scratch = torch.empty((B * (N + M),), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.tk_cosine_dist(a.data_ptr(), b.data_ptr(), out.data_ptr(), scratch.data_ptr(), B, N, M, E, _stream()),
+                   "tk_cosine_dist")
+    return out
+
+
+def lap_batched(cost: torch.Tensor, cost_limit: float | None = None, status: torch.Tensor | None = None):
+    """cost float64 [B,N,M] -> (x int32 [B,N], y int32 [B,M], status) (C ABI: tk_lap_batched)."""
+    lib = _lib.load()
+    _cuda(cost, "cost")
+    B, N, M = cost.shape
+    x = torch.empty((B, N), dtype=torch.int32, device=cost.device)
+    y = torch.empty((B, M), dtype=torch.int32, device=cost.device)
+    if status is None:
+        status = torch.zeros((1,), dtype=torch.int32, device=cost.device)
+    with torch.cuda.device(cost.device):
+        _lib.check(lib.tk_lap_batched(cost.data_ptr(), B, N, M, float(cost_limit or 0.0), int(cost_limit is not None),
+                                      x.data_ptr(), y.data_ptr(), status.data_ptr(), _stream()), "tk_lap_batched")
+    return x, y, status
