@@ -185,6 +185,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from tracklab_b200 import _lib
+    from tracklab_b200 import dist as tdist
     from tracklab_b200.detector import YoloxDetectorDevice
     from tracklab_b200.device_trackers import ByteTrackDevice
     from tracklab_b200.synth import make_frames, make_video
@@ -234,10 +235,7 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = tdist.max_over_ranks(ms, dev)      # job time = slowest rank (device-timed per rank)
         det.time_kernels = False
         return ms, res, last
 
@@ -292,12 +290,7 @@ def run_ours(args):
     # ---- per-video metrics: the single collective of the multi-GPU path ----
     metrics = torch.tensor([F, video.n_dets, n_rows, float(len(torch.unique(res[0][:n_rows, 4]))), ms / args.steps],
                            dtype=torch.float64, device=dev)
-    if world > 1:
-        allm = [torch.empty_like(metrics) for _ in range(world)]
-        dist.all_gather(allm, metrics)
-        allm = torch.stack(allm).cpu().numpy()
-    else:
-        allm = metrics[None].cpu().numpy()
+    allm = tdist.gather_video_metrics(metrics[None])[:, 0].cpu().numpy()   # the single collective: [world, 5]
 
     if rank == 0:
         peak, peak_src = measured_peaks()
