@@ -148,6 +148,42 @@ int tk_ocsort_run(void* handle, const double* dets, const int* offsets, int n_fr
 int tk_ocsort_status(void* handle, int* status_host, void* stream);
 int tk_ocsort_destroy(void* handle);
 
+/* ---- StrongSORT (DeepSORT lineage): whole-video association with externally supplied appearance features ------
+ * Replaces StrongSORT.update called once per frame by the wrapper, minus the in-tracker ReID forward (a separate
+ * stage here) and ECC (out of scope):
+ *   /root/reference/plugins/track/strong_sort/strong_sort.py:41-85                 (update)
+ *   /root/reference/plugins/track/strong_sort/sort/tracker.py:53-59,80-115,151-193 (predict / update / _match)
+ *   /root/reference/tracklab/wrappers/track/strong_sort_api.py:66-93              (per-frame filter + row layout)
+ * Hyper-parameters: /root/reference/tracklab/configs/modules/track/strong_sort.yaml:8-23.
+ * features: device float32 [N, feature_dim], row i belongs to dets row i (raw, un-normalised ReID outputs).
+ * Output rows [x1,y1,x2,y2,track_id,cls,conf,det_id] with int()-truncated, clipped boxes (strong_sort.py:110-121);
+ * a track is reported while time_since_update <= 1, so up to 2x the detections of a frame may come out:
+ * out_capacity_rows bounds the rows of one video (TK_STATUS_OVERFLOW_OUT otherwise).
+ * Each video is served by a cooperative group of `ctas_per_video` CTAs (default 8); n_seq*ctas_per_video <= 148.
+ */
+typedef struct {
+    double max_dist;        /* strong_sort.yaml: max_dist (0.1594...) — appearance matching threshold */
+    double max_iou_dist;    /* max_iou_dist (0.5431...) */
+    double mc_lambda;       /* 0.995: weight of appearance vs Mahalanobis distance */
+    double ema_alpha;       /* 0.8962...: EMA of the appearance feature */
+    double min_confidence;  /* wrapper filter (0.4) */
+    int max_age;            /* 40 */
+    int n_init;             /* 3 */
+    int nn_budget;          /* 100: gallery length per track */
+    int max_unmatched_preds;/* must be 0 (reference YAML) */
+    int feature_dim;        /* E */
+    int image_width;        /* for the output clipping (strong_sort.py:112-118) */
+    int image_height;
+    int ctas_per_video;     /* 0 = default */
+} tk_strongsort_params;
+
+int tk_strongsort_create(const tk_strongsort_params* p, int n_seq, int cap_tracks, int cap_dets, void** handle);
+int tk_strongsort_reset(void* handle, int keep_id_counter, void* stream);
+int tk_strongsort_run(void* handle, const double* dets, const float* features, const int* offsets, int n_frames, double* out_rows,
+                      const int* out_start, int* out_frame_count, int* out_count, int out_capacity_rows, void* stream);
+int tk_strongsort_status(void* handle, int* status_host, void* stream);
+int tk_strongsort_destroy(void* handle);
+
 /* ---- Stateless batched cost matrices + assignment (building blocks; stress sweep of BASELINE configs[4]) ------
  * All tensors device, row-major, `n_problems` independent problems stacked on the leading axis.
  *   tk_iou_matrix   a [B,N,4], b [B,M,4] float64 x1y1x2y2 -> out [B,N,M]; variant TK_ASSO_*

@@ -39,6 +39,12 @@ CASES = {
     "ocsort_byte_dt3_s1002": ("ocsort", dict(seed=1002, n_frames=160, n_ids=30, conf_range=(0.05, 1.0)),
                               dict(det_thresh=0.5, max_age=8, min_hits=3, iou_threshold=0.3,
                                    delta_t=3, asso_func="iou", inertia=0.2, use_byte=True)),
+    "strongsort_s4000": ("strongsort", dict(seed=4000, n_frames=160, n_ids=30, emb_dim=64),
+                         dict(max_dist=0.1594374041012136, max_iou_dist=0.5431835667667874, max_age=40, max_unmatched_preds=0,
+                              n_init=3, nn_budget=100, mc_lambda=0.995, ema_alpha=0.8962157769329083)),
+    "strongsort_budget8_s4001": ("strongsort", dict(seed=4001, n_frames=120, n_ids=44, emb_dim=128, conf_range=(0.3, 1.0)),
+                                 dict(max_dist=0.2, max_iou_dist=0.7, max_age=12, max_unmatched_preds=0, n_init=2, nn_budget=8,
+                                      mc_lambda=0.98, ema_alpha=0.9)),
 }
 MIN_CONF = 0.4
 
@@ -51,16 +57,38 @@ def run_reference(tracker, video, hyper):
     elif tracker == "ocsort":
         from oc_sort import ocsort
         model = ocsort.OCSort(**hyper)
+    elif tracker == "strongsort":
+        # StrongSORT.__init__ builds the in-tracker ReID network (strong_sort.py:33); the association is exercised with
+        # externally supplied features, so the object is assembled without it and _get_features is replaced.
+        from strong_sort.sort.nn_matching import NearestNeighborDistanceMetric
+        from strong_sort.sort.tracker import Tracker
+        from strong_sort.strong_sort import StrongSORT
+        model = object.__new__(StrongSORT)
+        model.max_dist = hyper["max_dist"]
+        metric = NearestNeighborDistanceMetric("cosine", hyper["max_dist"], hyper["nn_budget"])
+        model.tracker = Tracker(metric, max_iou_dist=hyper["max_iou_dist"], max_age=hyper["max_age"], n_init=hyper["n_init"],
+                                max_unmatched_preds=hyper["max_unmatched_preds"], mc_lambda=hyper["mc_lambda"],
+                                ema_alpha=hyper["ema_alpha"])
     else:
         raise KeyError(tracker)
     rows, frames = [], []
+    fake_img = np.zeros((video.height, video.width, 3), dtype=np.uint8)
     for f in range(video.n_frames):
         d = video.frame(f)
         if len(d) == 0:
             continue
-        d = d[d[:, 4] > MIN_CONF]
-        with torch.no_grad():
-            res = np.asarray(model.update(torch.from_numpy(d.copy()), None), dtype=np.float64)
+        keep = d[:, 4] > MIN_CONF
+        d = d[keep]
+        if tracker == "strongsort":
+            feats = video.embeddings[video.offsets[f]:video.offsets[f + 1]][keep]
+            model._get_features = lambda xywhs, img, _f=feats: torch.from_numpy(_f.copy())
+            with torch.no_grad():
+                res = model.update(torch.from_numpy(d.copy()), fake_img)
+            res = np.asarray(res)
+            res = res[:, [0, 1, 2, 3, 4, 5, 6, 8]].astype(np.float64) if res.size else np.zeros((0, 8))
+        else:
+            with torch.no_grad():
+                res = np.asarray(model.update(torch.from_numpy(d.copy()), None), dtype=np.float64)
         if res.size:
             rows.append(res.reshape(-1, 8))
             frames.append(np.full(res.reshape(-1, 8).shape[0], f, dtype=np.int32))

@@ -32,6 +32,14 @@ class OcsortParams(ctypes.Structure):
                 ("delta_t", ctypes.c_int), ("asso_func", ctypes.c_int), ("use_byte", ctypes.c_int)]
 
 
+class StrongsortParams(ctypes.Structure):
+    _fields_ = [("max_dist", ctypes.c_double), ("max_iou_dist", ctypes.c_double), ("mc_lambda", ctypes.c_double),
+                ("ema_alpha", ctypes.c_double), ("min_confidence", ctypes.c_double), ("max_age", ctypes.c_int),
+                ("n_init", ctypes.c_int), ("nn_budget", ctypes.c_int), ("max_unmatched_preds", ctypes.c_int),
+                ("feature_dim", ctypes.c_int), ("image_width", ctypes.c_int), ("image_height", ctypes.c_int),
+                ("ctas_per_video", ctypes.c_int)]
+
+
 ASSO_CODES = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3}
 
 _lib = None
@@ -63,6 +71,11 @@ def _declare(lib):
         "tk_ocsort_run": ([vp, vp, vp, ci, vp, vp, vp, vp, vp], ci),
         "tk_ocsort_status": ([vp, P(ci), vp], ci),
         "tk_ocsort_destroy": ([vp], ci),
+        "tk_strongsort_create": ([P(StrongsortParams), ci, ci, ci, P(vp)], ci),
+        "tk_strongsort_reset": ([vp, ci, vp], ci),
+        "tk_strongsort_run": ([vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp], ci),
+        "tk_strongsort_status": ([vp, P(ci), vp], ci),
+        "tk_strongsort_destroy": ([vp], ci),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)

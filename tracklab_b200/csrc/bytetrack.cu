@@ -208,24 +208,6 @@ __device__ void bt_kf_initiate(BtDev& S, int slot, const float* detbox) {
     S.mean_f32[slot] = 1;
 }
 
-// Ordered compaction done by ONE warp: pred(i) for i in [0,n), emit(i, base + rank) for the passing items in index
-// order; returns base + count. The serial list edits of the reference become a few ballots instead of a
-// dependent-load loop on one thread (~60 cycles per element on shared memory).
-template <class Pred, class Emit>
-__device__ __forceinline__ int warp_compact(int n, int base, Pred pred, Emit emit) {
-    const int lane = lane_id();
-    int cnt = base;
-    for (int c = 0; c < n; c += 32) {
-        const int i = c + lane;
-        const bool f = (i < n) && pred(i);
-        const unsigned b = __ballot_sync(0xffffffffu, f);
-        if (f) emit(i, cnt + __popc(b & ((1u << lane) - 1u)));
-        cnt += __popc(b);
-    }
-    __syncwarp();
-    return cnt;
-}
-
 struct BtShared {
     // sizes
     int lap_ok;

@@ -1,0 +1,628 @@
+// StrongSORT (DeepSORT lineage) association with externally supplied appearance features; whole video per launch.
+//
+// Device restatement of
+//   /root/reference/plugins/track/strong_sort/strong_sort.py:41-85,88-121            (update, box conversions, output rule)
+//   /root/reference/plugins/track/strong_sort/sort/tracker.py:53-59,80-115,151-193   (predict, update, _match, _initiate_track)
+//   /root/reference/plugins/track/strong_sort/sort/track.py:65-95,97-108,245-322     (Track life cycle, EMA feature)
+//   /root/reference/plugins/track/strong_sort/sort/kalman_filter.py:47-214            (x/y/a/h-scaled noise, confidence-scaled R)
+//   /root/reference/plugins/track/strong_sort/sort/nn_matching.py:30-49,73-91,127-161 (cosine metric, gallery with budget)
+//   /root/reference/plugins/track/strong_sort/sort/linear_assignment.py:11-72,131-174 (matching, Mahalanobis gating, fusion)
+//   /root/reference/plugins/track/strong_sort/sort/iou_matching.py:7-82               (IoU cost)
+// and of the wrapper filter /root/reference/tracklab/wrappers/track/strong_sort_api.py:66-93 (ecc off, max_unmatched_preds 0).
+//
+// Execution shape. The appearance term is min over a gallery of up to `budget` (100) EMA features per confirmed track:
+// T x budget x D x E multiply-adds per frame (164 MFLOP at 40 x 100 x 40 x 512) inside the per-frame dependency chain —
+// too much for one SM, so each video gets a GROUP of CTAs launched cooperatively: per frame the master CTA predicts
+// and lists, all CTAs of the group compute gallery-vs-detections cosine tiles (fp32 FMA out of shared memory), a
+// group barrier, then the master gates (Mahalanobis), fuses, solves both assignments (lap.cuh), updates filters
+// (octets), EMA features and galleries, and emits rows. Still one launch per chunk of frames, no host round trips.
+#include <cooperative_groups.h>
+#include "kf_xyah.cuh"
+#include "lap.cuh"
+#include "trackkern.h"
+
+namespace {
+
+using namespace tk;
+
+constexpr int SS_THREADS = 256;
+enum : unsigned char { SS_FREE = 0, SS_TENTATIVE = 1, SS_CONFIRMED = 2, SS_DELETED = 3 };
+constexpr double W_POS = 1.0 / 20, W_VEL = 1.0 / 160, INFTY_COST = 1e5, CHI2_4 = 9.4877;
+
+struct SsParams {
+    double max_dist, max_iou_dist, mc_lambda, min_conf;
+    float ema_alpha, ema_beta;   // float32(alpha), float32(1 - alpha): python float * float32 array (track.py:286)
+    int max_age, n_init, budget, width, height, E;
+};
+
+struct SsDev {
+    int* hdr;            // 0 next_id, 1 n_tracks, 2 -, 3 -, 4 status, 5 n_free, 6 nd (frame), 7 nconf (frame)
+    double *mean, *cov, *conf, *det_id;
+    int *hits, *age, *tsu, *track_id, *cls, *g_count, *g_head, *list, *free_list, *conf_list, *det_rows;
+    unsigned char *state, *fresh;
+    float *smooth, *gallery;   // [cap][E], [cap][budget][E] (gallery rows are stored re-normalised)
+    double* app;               // [cap][capd] appearance cost of the current frame (row = position in conf_list)
+    unsigned* bar;             // group barrier: count, generation
+};
+
+__host__ __device__ inline size_t ss_al(size_t x) { return (x + 255) & ~(size_t)255; }
+
+__host__ __device__ inline size_t ss_state_bytes(int cap, int capd, int budget, int E) {
+    size_t s = ss_al(8 * sizeof(int)) + ss_al(64);
+    s += ss_al((size_t)cap * 8 * 8) + ss_al((size_t)cap * 64 * 8) + 2 * ss_al((size_t)cap * 8);
+    s += 10 * ss_al((size_t)cap * 4) + ss_al((size_t)capd * 4) + 2 * ss_al((size_t)cap);
+    s += ss_al((size_t)cap * E * 4) + ss_al((size_t)cap * budget * E * 4) + ss_al((size_t)cap * capd * 8);
+    return s;
+}
+
+__host__ __device__ inline SsDev ss_carve(char* base, int cap, int capd, int budget, int E) {
+    SsDev d;
+    char* p = base;
+    d.hdr = (int*)p; p += ss_al(8 * sizeof(int));
+    d.bar = (unsigned*)p; p += ss_al(64);
+    d.mean = (double*)p; p += ss_al((size_t)cap * 8 * 8);
+    d.cov = (double*)p; p += ss_al((size_t)cap * 64 * 8);
+    d.conf = (double*)p; p += ss_al((size_t)cap * 8);
+    d.det_id = (double*)p; p += ss_al((size_t)cap * 8);
+    int** ints[10] = {&d.hits, &d.age, &d.tsu, &d.track_id, &d.cls, &d.g_count, &d.g_head, &d.list, &d.free_list, &d.conf_list};
+    for (int k = 0; k < 10; ++k) { *ints[k] = (int*)p; p += ss_al((size_t)cap * 4); }
+    d.det_rows = (int*)p; p += ss_al((size_t)capd * 4);
+    d.state = (unsigned char*)p; p += ss_al((size_t)cap);
+    d.fresh = (unsigned char*)p; p += ss_al((size_t)cap);
+    d.smooth = (float*)p; p += ss_al((size_t)cap * E * 4);
+    d.gallery = (float*)p; p += ss_al((size_t)cap * budget * E * 4);
+    d.app = (double*)p;
+    return d;
+}
+
+// sense-reversing barrier over the CTAs of one video group (all co-resident: cooperative launch)
+__device__ void group_barrier(unsigned* bar, int n) {
+    __syncthreads();
+    if (n > 1 && threadIdx.x == 0) {
+        volatile unsigned* gen = bar + 1;
+        const unsigned g = *gen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == (unsigned)(n - 1)) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == g) { __nanosleep(64); }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// float32 L2 norm of a length-E vector by one warp (np.linalg.norm on float32), result in every lane
+__device__ __forceinline__ float warp_norm(const float* x, int E) {
+    float s = 0.0f;
+    for (int k = lane_id(); k < E; k += 32) s = fmaf(x[k], x[k], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return sqrtf(s);
+}
+
+// Detection.to_xyah (sort/detection.py:45-52) from the float64 wrapper row: tlwh float32, then float32 ops
+__device__ __forceinline__ void det_boxes(const double* d, float* tlwh, double* z) {
+    const double cx = (d[0] + d[2]) / 2, cy = (d[1] + d[3]) / 2, w = d[2] - d[0], h = d[3] - d[1];   // xyxy2xywh
+    tlwh[0] = (float)(cx - w / 2.0); tlwh[1] = (float)(cy - h / 2.0); tlwh[2] = (float)w; tlwh[3] = (float)h;   // _xywh_to_tlwh
+    if (z) {
+        z[0] = (double)__fadd_rn(tlwh[0], __fdiv_rn(tlwh[2], 2.0f));
+        z[1] = (double)__fadd_rn(tlwh[1], __fdiv_rn(tlwh[3], 2.0f));
+        z[2] = (double)__fdiv_rn(tlwh[2], tlwh[3]);
+        z[3] = (double)tlwh[3];
+    }
+}
+
+struct SsShared { int lap_ok, nd, nconf, ncand, nud, npairs, n_out, n_ut; };
+
+__global__ void __launch_bounds__(SS_THREADS)
+strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int cap, int capd, int ncta,
+                        const double* __restrict__ dets, const float* __restrict__ feats, const int* __restrict__ offsets,
+                        int n_frames, double* __restrict__ out_rows, const int* __restrict__ out_start,
+                        int* __restrict__ out_frame_count, int* __restrict__ out_count, int out_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int seq = blockIdx.x / ncta, cta = blockIdx.x % ncta, tid = threadIdx.x;
+    const bool master = cta == 0;
+    const int E = prm.E;
+    SsDev S = ss_carve(state_base + (size_t)seq * state_stride, cap, capd, prm.budget, E);
+    unsigned char* sp = smem_raw;
+    auto take = [&](size_t bytes) { unsigned char* p = sp; sp += (bytes + 15) & ~(size_t)15; return p; };
+    const int side = cap > capd ? cap : capd;
+    // appearance tiles (all CTAs)
+    float* tb = (float*)take(sizeof(float) * 32 * (capd + 1));     // [32 k][capd] detections chunk
+    float* ta = (float*)take(sizeof(float) * 32 * 33);             // [32 g][32 k] gallery chunk
+    float* dmin = (float*)take(sizeof(float) * capd);
+    float* dnorm = (float*)take(sizeof(float) * capd);          // |feature| of the frame's detections
+    // master only
+    double* cost = (double*)take(sizeof(double) * (size_t)(cap + 1) * (capd + 1));
+    double* lap_u = (double*)take(sizeof(double) * side);
+    double* d_z = (double*)take(sizeof(double) * 4 * capd);
+    float* d_tlwh = (float*)take(sizeof(float) * 4 * capd);
+    double* chol = (double*)take(sizeof(double) * 24 * cap);        // per confirmed row: mean4, L(16), invd(4)
+    int* match_a = (int*)take(sizeof(int) * side);
+    int* match_b = (int*)take(sizeof(int) * side);
+    int* col4row = (int*)take(sizeof(int) * side);
+    int* row4col = (int*)take(sizeof(int) * side);
+    int* path = (int*)take(sizeof(int) * side);
+    int* cand = (int*)take(sizeof(int) * cap);
+    int* un_d = (int*)take(sizeof(int) * capd);
+    int* tmp_d = (int*)take(sizeof(int) * capd);
+    int* pair_t = (int*)take(sizeof(int) * cap);
+    int* pair_d = (int*)take(sizeof(int) * cap);
+    int* out_pos = (int*)take(sizeof(int) * cap);
+    unsigned char* t_flag = (unsigned char*)take(cap);
+    unsigned char* d_flag = (unsigned char*)take(capd);
+    SsShared* sh = (SsShared*)take(sizeof(SsShared));
+
+    int* status = &S.hdr[4];
+    const int F1 = n_frames + 1;
+    const int out_base = out_start[seq];
+    int out_n = out_count[seq];
+    const double L_app = prm.max_dist + 1e-5, L_iou = prm.max_iou_dist + 1e-5;
+
+    for (int f = 0; f < n_frames; ++f) {
+        const int r0 = offsets[seq * F1 + f], r1 = offsets[seq * F1 + f + 1];
+        const int nraw = r1 - r0;
+        if (nraw == 0) { if (master && tid == 0) out_frame_count[seq * n_frames + f] = 0; continue; }   // strong_sort_api.py:66-67
+        if (nraw > capd) { if (master && tid == 0) atomicOr(status, TK_DEV_OVERFLOW_DETS); break; }
+        const double* D = dets + (size_t)r0 * 7;
+
+        // ================= master: predict, detections, lists =================
+        if (master) {
+            const int nt = S.hdr[1];
+            for (int base = 0; base < nt; base += SS_THREADS / 8) {   // Track.predict (track.py:245-249, kalman_filter.py:80-112)
+                const int k = base + (tid >> 3), j = tid & 7;
+                const bool act = k < nt;
+                const int s = act ? S.list[k] : 0;
+                double* gm = S.mean + (size_t)s * 8;
+                double qj = 0.0;
+                if (act) {
+                    const double ref = gm[j & 3];           // noise of x,y,a,h (and their velocities) scales with x,y,a,h
+                    if (S.fresh[s]) {                         // float32 mean right after initiate
+                        const float r32 = (float)ref;
+                        const float w = (j & 3) == 2 ? (j < 4 ? 1.0f : (float)0.1) : (j < 4 ? (float)W_POS : (float)W_VEL);
+                        const float sd = ((j & 3) == 2 && j < 4) ? r32 : __fmul_rn(w, r32);
+                        qj = (double)__fmul_rn(sd, sd);
+                    } else {
+                        const double w = (j & 3) == 2 ? (j < 4 ? 1.0 : 0.1) : (j < 4 ? W_POS : W_VEL);
+                        const double sd = w * ref;
+                        qj = sd * sd;
+                    }
+                }
+                kf8_octet_predict(gm, S.cov + (size_t)s * 64, act, false, qj);
+                if (act && j == 0) { S.age[s] += 1; S.tsu[s] += 1; S.fresh[s] = 0; }
+            }
+            if (warp_id() == 0) {   // wrapper filter (strong_sort_api.py:69), detection order kept
+                const int nd_ = warp_compact(nraw, 0, [&](int i) { return D[i * 7 + 4] > prm.min_conf; }, [&](int i, int p) { S.det_rows[p] = i; });
+                if (lane_id() == 0) { sh->nd = nd_; S.hdr[6] = nd_; }
+            }
+            __syncthreads();
+            const int nd = sh->nd;
+            for (int i = tid; i < nd; i += SS_THREADS) det_boxes(D + (size_t)S.det_rows[i] * 7, d_tlwh + 4 * i, d_z + 4 * i);
+            if (warp_id() == 0) {
+                const int nc = warp_compact(nt, 0, [&](int k) { return S.state[S.list[k]] == SS_CONFIRMED; },
+                                            [&](int k, int p) { S.conf_list[p] = S.list[k]; });
+                if (lane_id() == 0) { sh->nconf = nc; S.hdr[7] = nc; }
+            }
+            __threadfence();
+        }
+        group_barrier(S.bar, ncta);
+
+        // ================= all CTAs: appearance cost (nn_matching.py:30-49,73-91,144-161) =================
+        {
+            const int nd = S.hdr[6], nconf = S.hdr[7];
+            // b = features / ||features|| (nn_matching.py:46-48): the norms once per frame, the division in the tile load
+            if (cta < nconf)
+                for (int d = warp_id(); d < nd; d += SS_THREADS / 32) {
+                    const float nf = warp_norm(feats + (size_t)(r0 + S.det_rows[d]) * E, E);
+                    if (lane_id() == 0) dnorm[d] = nf;
+                }
+            __syncthreads();
+            for (int row = cta; row < nconf && nd > 0; row += ncta) {
+                const int s = S.conf_list[row];
+                const int g = S.g_count[s];
+                const float* G = S.gallery + (size_t)s * prm.budget * E;
+                for (int i = tid; i < nd; i += SS_THREADS) dmin[i] = 3.0e38f;
+                __syncthreads();
+                for (int g0 = 0; g0 < g; g0 += 32) {
+                    const int gn = min(32, g - g0);
+                    // each thread accumulates dots for (gi = tid>>3 ... ) pattern: 256 threads -> 32 g x 8 d-lanes
+                    const int gi = tid >> 3, dl = tid & 7;
+                    float acc[32];   // up to capd/8 detections per thread (capd <= 256)
+                    const int nper = (nd + 7) >> 3;
+#pragma unroll 1
+                    for (int q = 0; q < nper; ++q) acc[q] = 0.0f;
+                    for (int k0 = 0; k0 < E; k0 += 32) {
+                        for (int e = tid; e < 32 * 32; e += SS_THREADS) {
+                            const int r = e >> 5, k = e & 31;
+                            ta[r * 33 + k] = (r < gn && k0 + k < E) ? G[(size_t)(g0 + r) * E + k0 + k] : 0.0f;
+                        }
+                        for (int e = tid; e < nd * 32; e += SS_THREADS) {
+                            const int d = e >> 5, k = e & 31;
+                            tb[k * (capd + 1) + d] = (k0 + k < E) ? __fdiv_rn(feats[(size_t)(r0 + S.det_rows[d]) * E + k0 + k], dnorm[d]) : 0.0f;
+                        }
+                        __syncthreads();
+                        if (gi < gn) {
+#pragma unroll 1
+                            for (int q = 0; q < nper; ++q) {
+                                const int d = dl + 8 * q;
+                                if (d < nd) {
+                                    float a = acc[q];
+#pragma unroll
+                                    for (int k = 0; k < 32; ++k) a = fmaf(ta[gi * 33 + k], tb[k * (capd + 1) + d], a);
+                                    acc[q] = a;
+                                }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                    if (gi < gn) {
+#pragma unroll 1
+                        for (int q = 0; q < nper; ++q) {
+                            const int d = dl + 8 * q;
+                            if (d < nd) {
+                                const float dist = __fsub_rn(1.0f, acc[q]);
+                                // min over the gallery; float min via ordered-int trick (dist may be -1e-7)
+                                int key = __float_as_int(dist);
+                                key = key >= 0 ? key : key ^ 0x7fffffff;
+                                atomicMin((int*)&dmin[d], key >= 0 ? key : key);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                for (int i = tid; i < nd; i += SS_THREADS) {
+                    int key = ((int*)dmin)[i];
+                    key = key >= 0 ? key : key ^ 0x7fffffff;
+                    S.app[(size_t)row * capd + i] = (double)__int_as_float(key);
+                }
+                __syncthreads();
+            }
+            __threadfence();
+        }
+        group_barrier(S.bar, ncta);
+        if (!master) continue;
+
+        // ================= master: gating, fusion, assignments, updates =================
+        const int nd = sh->nd, nconf = sh->nconf, nt = S.hdr[1];
+        // ---- stage A: confirmed tracks x all detections (tracker.py:152-170, linear_assignment.py:131-174)
+        for (int r = tid; r < nconf; r += SS_THREADS) {   // projected distribution of each confirmed track (confidence 0)
+            const int s = S.conf_list[r];
+            const double* m = S.mean + (size_t)s * 8;
+            const double* P = S.cov + (size_t)s * 64;
+            const double sp_ = W_POS * m[3];
+            const double rr[4] = {sp_ * sp_, sp_ * sp_, 1e-1 * 1e-1, sp_ * sp_};
+            double Pl[64];
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Pl[i * 8 + j] = P[i * 8 + j];
+            double L[16], Sm[16], invd[4];
+            if (!kf8_chol4(Pl, rr, L, Sm, invd)) atomicOr(status, TK_DEV_BAD_CHOLESKY);
+            double* c = chol + 24 * r;
+            for (int i = 0; i < 4; ++i) c[i] = m[i];
+            for (int i = 0; i < 16; ++i) c[4 + i] = L[i];
+            for (int i = 0; i < 4; ++i) c[20 + i] = invd[i];
+        }
+        __syncthreads();
+        {
+            const bool a_rows = nconf <= nd;
+            const int ld = lap_pitch(a_rows ? nd : nconf);
+            for (int e = tid; e < nconf * nd; e += SS_THREADS) {
+                const int r = e / nd, d = e - r * nd;
+                const double* c = chol + 24 * r;
+                const double g = kf8_maha(c, c + 4, c + 20, d_z + 4 * d);
+                double a = S.app[(size_t)r * capd + d];
+                if (g > CHI2_4) a = INFTY_COST;
+                const double fused = __dadd_rn(__dmul_rn(prm.mc_lambda, a), __dmul_rn(1.0 - prm.mc_lambda, g));
+                const double red = fused > prm.max_dist ? 0.0 : fused - L_app;   // cost[cost > max] = max + 1e-5, pairs above max dropped
+                if (a_rows) cost[(size_t)r * ld + d] = red; else cost[(size_t)d * ld + r] = red;
+            }
+            for (int i = tid; i < nconf; i += SS_THREADS) match_a[i] = -1;
+            for (int i = tid; i < nd; i += SS_THREADS) match_b[i] = -1;
+            __syncthreads();
+            if (nconf > 0 && nd > 0) {
+                const int nr = a_rows ? nconf : nd, nc = a_rows ? nd : nconf;
+                if (!lap_solve_cta(cost, ld, nr, nc, true, lap_u, col4row, row4col, path, &sh->lap_ok)) { if (tid == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); }
+                else for (int r = tid; r < nr; r += SS_THREADS) {
+                    const int c = col4row[r];
+                    if (c >= 0 && cost[(size_t)r * ld + c] < 0.0) { if (a_rows) { match_a[r] = c; match_b[c] = r; } else { match_a[c] = r; match_b[r] = c; } }
+                }
+            }
+            __syncthreads();
+        }
+        // record stage-A pairs, build stage-B candidates: unconfirmed + unmatched confirmed with tsu == 1 (tracker.py:171-178)
+        if (warp_id() == 0) {
+            const int np_ = warp_compact(nconf, 0, [&](int r) { return match_a[r] >= 0; },
+                                         [&](int r, int p) { pair_t[p] = S.conf_list[r]; pair_d[p] = match_a[r]; });
+            int nc = warp_compact(nt, 0, [&](int k) { return S.state[S.list[k]] != SS_CONFIRMED; }, [&](int k, int p) { cand[p] = S.list[k]; });
+            nc = warp_compact(nconf, nc, [&](int r) { return match_a[r] < 0 && S.tsu[S.conf_list[r]] == 1; },
+                              [&](int r, int p) { cand[p] = S.conf_list[r]; });
+            const int nu = warp_compact(nd, 0, [&](int d) { return match_b[d] < 0; }, [&](int d, int p) { un_d[p] = d; });
+            if (lane_id() == 0) { sh->npairs = np_; sh->ncand = nc; sh->nud = nu; }
+        }
+        for (int k = tid; k < cap; k += SS_THREADS) t_flag[k] = 0;     // t_flag[slot] = 1 when the track got a detection this frame
+        __syncthreads();
+        for (int p = tid; p < sh->npairs; p += SS_THREADS) t_flag[pair_t[p]] = 1;
+        // ---- stage B: IoU cost on the candidates (iou_matching.py:42-82, linear_assignment.py:11-72)
+        {
+            const int ncand = sh->ncand, nud = sh->nud;
+            const bool a_rows = ncand <= nud;
+            const int ld = lap_pitch(a_rows ? nud : ncand);
+            for (int e = tid; e < ncand * nud; e += SS_THREADS) {
+                const int r = e / nud, c = e - r * nud;
+                const int s = cand[r];
+                double v;
+                if (S.tsu[s] > 1) v = INFTY_COST;
+                else {
+                    const double* m = S.mean + (size_t)s * 8;
+                    const double w = m[2] * m[3];
+                    const double bx = m[0] - w / 2, by = m[1] - m[3] / 2;            // Track.to_tlwh (track.py:97-101)
+                    const float* cb = d_tlwh + 4 * un_d[c];
+                    const double x0 = fmax(bx, (double)cb[0]), y0 = fmax(by, (double)cb[1]);
+                    const double x1 = fmin(bx + w, (double)__fadd_rn(cb[0], cb[2])), y1 = fmin(by + m[3], (double)__fadd_rn(cb[1], cb[3]));
+                    const double iw = fmax(0.0, x1 - x0), ih = fmax(0.0, y1 - y0);
+                    const double inter = __dmul_rn(iw, ih);
+                    const double uni = __dsub_rn(__dadd_rn(__dmul_rn(w, m[3]), (double)__fmul_rn(cb[2], cb[3])), inter);
+                    v = 1.0 - inter / uni;
+                }
+                const double red = v > prm.max_iou_dist ? 0.0 : v - L_iou;
+                if (a_rows) cost[(size_t)r * ld + c] = red; else cost[(size_t)c * ld + r] = red;
+            }
+            for (int i = tid; i < ncand; i += SS_THREADS) match_a[i] = -1;
+            for (int i = tid; i < nud; i += SS_THREADS) match_b[i] = -1;
+            __syncthreads();
+            if (ncand > 0 && nud > 0) {
+                const int nr = a_rows ? ncand : nud, nc = a_rows ? nud : ncand;
+                if (!lap_solve_cta(cost, ld, nr, nc, true, lap_u, col4row, row4col, path, &sh->lap_ok)) { if (tid == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); }
+                else for (int r = tid; r < nr; r += SS_THREADS) {
+                    const int c = col4row[r];
+                    if (c >= 0 && cost[(size_t)r * ld + c] < 0.0) { if (a_rows) { match_a[r] = c; match_b[c] = r; } else { match_a[c] = r; match_b[r] = c; } }
+                }
+            }
+            __syncthreads();
+            if (warp_id() == 0) {
+                const int np_ = warp_compact(ncand, sh->npairs, [&](int r) { return match_a[r] >= 0; },
+                                             [&](int r, int p) { pair_t[p] = cand[r]; pair_d[p] = un_d[match_a[r]]; });
+                // detections that stay unmatched, in the reference's order: untouched columns first, then the rejected pairs
+                int nu = warp_compact(nud, 0, [&](int c) { return match_b[c] < 0; }, [&](int c, int p) { tmp_d[p] = un_d[c]; });
+                if (lane_id() == 0) { sh->npairs = np_; sh->nud = nu; }
+            }
+            __syncthreads();
+            for (int p = tid; p < sh->npairs; p += SS_THREADS) t_flag[pair_t[p]] = 1;
+            __syncthreads();
+        }
+        // ---- Track.update for every pair (track.py:272-301, kalman_filter.py:114-174)
+        {
+            const int np_ = sh->npairs;
+            for (int base = 0; base < np_; base += SS_THREADS / 8) {
+                const int p = base + (tid >> 3);
+                const bool act = p < np_;
+                const int s = act ? pair_t[p] : 0, d = act ? pair_d[p] : 0;
+                double z[4] = {0, 0, 0, 0}, r[4] = {1, 1, 1, 1};
+                if (act) {
+                    const double* dz = d_z + 4 * d;
+                    z[0] = dz[0]; z[1] = dz[1]; z[2] = dz[2]; z[3] = dz[3];
+                    const double cf = D[(size_t)S.det_rows[d] * 7 + 4];
+                    const double h = S.mean[(size_t)s * 8 + 3];
+                    const double sp_ = (1 - cf) * (W_POS * h), sa = (1 - cf) * 1e-1;
+                    r[0] = sp_ * sp_; r[1] = sp_ * sp_; r[2] = sa * sa; r[3] = sp_ * sp_;
+                }
+                if (!kf8_octet_update(S.mean + (size_t)s * 8, S.cov + (size_t)s * 64, act, z, r)) atomicOr(status, TK_DEV_BAD_CHOLESKY);
+                if (act && (tid & 7) == 0) {
+                    const double* dr = D + (size_t)S.det_rows[d] * 7;
+                    S.conf[s] = dr[4]; S.cls[s] = (int)dr[5]; S.det_id[s] = dr[6];
+                    S.hits[s] += 1; S.tsu[s] = 0;
+                    if (S.state[s] == SS_TENTATIVE && S.hits[s] >= prm.n_init) S.state[s] = SS_CONFIRMED;
+                }
+            }
+            // EMA appearance (track.py:284-288): one warp per pair, float32
+            for (int p = warp_id(); p < np_; p += SS_THREADS / 32) {
+                const int s = pair_t[p];
+                const float* fv = feats + (size_t)(r0 + S.det_rows[pair_d[p]]) * E;
+                float* sm = S.smooth + (size_t)s * E;
+                const float nf = warp_norm(fv, E);
+                for (int k = lane_id(); k < E; k += 32)
+                    sm[k] = __fadd_rn(__fmul_rn(prm.ema_alpha, sm[k]), __fmul_rn(prm.ema_beta, __fdiv_rn(fv[k], nf)));
+                __syncwarp();
+                const float ns = warp_norm(sm, E);
+                for (int k = lane_id(); k < E; k += 32) sm[k] = __fdiv_rn(sm[k], ns);
+            }
+            __syncthreads();
+        }
+        // ---- mark_missed (track.py:303-309), births (tracker.py:189-193), prune, gallery append (nn_matching.py:127-142)
+        if (warp_id() == 0) {
+            const int lane = lane_id();
+            for (int k = lane; k < nt; k += 32) {
+                const int s = S.list[k];
+                if (!t_flag[s]) { if (S.state[s] == SS_TENTATIVE || S.tsu[s] > prm.max_age) S.state[s] = SS_DELETED; }
+            }
+            __syncwarp();
+            // births in the order of the reference's unmatched_detections: untouched columns (tmp_d), then rejected pairs — the
+            // device solver never returns rejected pairs (they are cost 0 and dropped), so those detections are exactly the
+            // columns without a match; their relative order is the solver-tie caveat of DESIGN.md §3.
+            const int nfree = S.hdr[5];
+            const int nb = sh->nud < nfree ? sh->nud : nfree;
+            if (sh->nud > nfree && lane == 0) atomicOr(status, TK_DEV_OVERFLOW_TRACKS);
+            const int id0 = S.hdr[0];
+            int n = nt;
+            for (int k = lane; k < nb; k += 32) {
+                const int s = S.free_list[nfree - 1 - k];
+                const int d = tmp_d[k];
+                const double* dr = D + (size_t)S.det_rows[d] * 7;
+                S.list[nt + k] = s;
+                S.track_id[s] = id0 + k; S.cls[s] = (int)dr[5]; S.conf[s] = dr[4]; S.det_id[s] = dr[6];
+                S.hits[s] = 1; S.age[s] = 1; S.tsu[s] = 0; S.state[s] = SS_TENTATIVE; S.fresh[s] = 1;
+                S.g_count[s] = 0; S.g_head[s] = 0;
+                pair_t[k] = s; pair_d[k] = d;     // reuse as the birth list for the parallel initialisation below
+            }
+            n += nb;
+            if (lane == 0) { S.hdr[0] = id0 + nb; S.hdr[5] = nfree - nb; sh->n_ut = nb; sh->npairs = n; }
+        }
+        __syncthreads();
+        {
+            const int nb = sh->n_ut;
+            for (int k = tid; k < nb; k += SS_THREADS) {   // KalmanFilter.initiate on the float32 measurement (kalman_filter.py:47-78)
+                const int s = pair_t[k];
+                const double* z = d_z + 4 * pair_d[k];
+                double* m = S.mean + (size_t)s * 8;
+                double* P = S.cov + (size_t)s * 64;
+                for (int i = 0; i < 4; ++i) { m[i] = z[i]; m[4 + i] = 0.0; }
+                for (int i = 0; i < 64; ++i) P[i] = 0.0;
+                const float zf[4] = {(float)z[0], (float)z[1], (float)z[2], (float)z[3]};
+                const float sd[8] = {__fmul_rn((float)(2 * W_POS), zf[0]), __fmul_rn((float)(2 * W_POS), zf[1]), zf[2], __fmul_rn((float)(2 * W_POS), zf[3]),
+                                     __fmul_rn((float)(10 * W_VEL), zf[0]), __fmul_rn((float)(10 * W_VEL), zf[1]), __fmul_rn((float)0.1, zf[2]),
+                                     __fmul_rn((float)(10 * W_VEL), zf[3])};
+                for (int i = 0; i < 8; ++i) P[i * 9] = (double)__fmul_rn(sd[i], sd[i]);
+            }
+            for (int k = warp_id(); k < nb; k += SS_THREADS / 32) {   // feature /= norm (track.py:84)
+                const int s = pair_t[k];
+                const float* fv = feats + (size_t)(r0 + S.det_rows[pair_d[k]]) * E;
+                const float nf = warp_norm(fv, E);
+                for (int e = lane_id(); e < E; e += 32) S.smooth[(size_t)s * E + e] = __fdiv_rn(fv[e], nf);
+            }
+        }
+        __syncthreads();
+        if (warp_id() == 0) {   // tracks = [t for t in tracks if not deleted] (order kept); free the deleted slots
+            const int n0 = sh->npairs;
+            int nfree = S.hdr[5];
+            nfree = warp_compact(n0, nfree, [&](int k) { return S.state[S.list[k]] == SS_DELETED; },
+                                 [&](int k, int p) { const int s = S.list[k]; S.free_list[p] = s; });
+            const int n = warp_compact(n0, 0, [&](int k) { return S.state[S.list[k]] != SS_DELETED; },
+                                       [&](int k, int p) { const int s = S.list[k]; cand[p] = s; });
+            for (int k = lane_id(); k < n; k += 32) S.list[k] = cand[k];
+            __syncwarp();
+            for (int k = lane_id(); k < n; k += 32) out_pos[k] = -1;
+            __syncwarp();
+            const int cnt = warp_compact(n, 0, [&](int k) { const int s = S.list[k]; return S.state[s] == SS_CONFIRMED && S.tsu[s] <= 1; },
+                                         [&](int k, int p) { out_pos[k] = p; });
+            if (lane_id() == 0) {
+                S.hdr[1] = n; S.hdr[5] = nfree; sh->n_out = cnt;
+                out_frame_count[seq * n_frames + f] = cnt;
+                if (out_n + cnt > out_cap) atomicOr(status, TK_DEV_OVERFLOW_OUT);
+            }
+        }
+        __syncthreads();
+        {
+            const int n = S.hdr[1];
+            // gallery append for confirmed tracks: re-normalised copy of the EMA feature (what _cosine_distance uses)
+            for (int k = warp_id(); k < n; k += SS_THREADS / 32) {
+                const int s = S.list[k];
+                if (S.state[s] != SS_CONFIRMED) continue;
+                const float* sm = S.smooth + (size_t)s * E;
+                const int h = S.g_head[s];
+                float* dst = S.gallery + ((size_t)s * prm.budget + h) * E;
+                const float ns = warp_norm(sm, E);
+                for (int e = lane_id(); e < E; e += 32) dst[e] = __fdiv_rn(sm[e], ns);
+                if (lane_id() == 0) { S.g_head[s] = (h + 1) % prm.budget; if (S.g_count[s] < prm.budget) S.g_count[s] += 1; }
+            }
+            // output rows (strong_sort.py:70-82,110-121)
+            if (out_n + sh->n_out <= out_cap)
+                for (int k = tid; k < n; k += SS_THREADS) {
+                    if (out_pos[k] < 0) continue;
+                    const int s = S.list[k];
+                    const double* m = S.mean + (size_t)s * 8;
+                    const double w = m[2] * m[3];
+                    const double x = m[0] - w / 2, y = m[1] - m[3] / 2;
+                    double* o = out_rows + (size_t)(out_base + out_n + out_pos[k]) * 8;
+                    o[0] = (double)max((int)x, 0); o[2] = (double)min((int)(x + w), prm.width - 1);
+                    o[1] = (double)max((int)y, 0); o[3] = (double)min((int)(y + m[3]), prm.height - 1);
+                    o[4] = (double)S.track_id[s]; o[5] = (double)S.cls[s]; o[6] = S.conf[s]; o[7] = S.det_id[s];
+                }
+            out_n += sh->n_out;
+        }
+        __syncthreads();
+        __threadfence();
+    }
+    if (master && tid == 0) out_count[seq] = out_n;
+}
+
+struct SsHandle {
+    SsParams prm;
+    int n_seq, cap, capd, ncta;
+    char* state;
+    size_t state_stride, smem_bytes;
+};
+
+__global__ void strongsort_reset_kernel(char* base, size_t stride, int cap, int capd, int budget, int E) {
+    SsDev S = ss_carve(base + (size_t)blockIdx.x * stride, cap, capd, budget, E);
+    if (threadIdx.x == 0) { S.hdr[0] = 1; S.hdr[1] = 0; S.hdr[4] = 0; S.hdr[5] = cap; S.hdr[6] = 0; S.hdr[7] = 0; S.bar[0] = 0; S.bar[1] = 0; }
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) { S.free_list[i] = cap - 1 - i; S.state[i] = SS_FREE; S.fresh[i] = 0; S.g_count[i] = 0; S.g_head[i] = 0; }
+}
+
+size_t ss_smem(int cap, int capd) {
+    const int side = cap > capd ? cap : capd;
+    auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    size_t s = al(4 * 32 * (capd + 1)) + al(4 * 32 * 33) + 2 * al(4 * capd);
+    s += al(8 * (size_t)(cap + 1) * (capd + 1)) + al(8 * side) + al(8 * 4 * capd) + al(4 * 4 * capd) + al(8 * 24 * cap);
+    s += 5 * al(4 * side) + al(4 * cap) + 2 * al(4 * capd) + 3 * al(4 * cap) + al(cap) + al(capd) + al(sizeof(SsShared));
+    return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tk_strongsort_create(const tk_strongsort_params* p, int n_seq, int cap_tracks, int cap_dets, void** handle) {
+    if (!p || !handle || n_seq <= 0 || cap_tracks <= 0 || cap_dets <= 0 || p->feature_dim <= 0 || p->nn_budget <= 0) return TK_ERR_ARG;
+    if (cap_tracks > tk::LAP_MAX_COLS || cap_dets > tk::LAP_MAX_COLS) return TK_ERR_CAPACITY;
+    if (p->max_unmatched_preds != 0) return TK_ERR_ARG;   // only the reference configuration (strong_sort.yaml:19)
+    SsHandle* h = new SsHandle();
+    h->prm.max_dist = p->max_dist; h->prm.max_iou_dist = p->max_iou_dist; h->prm.mc_lambda = p->mc_lambda;
+    h->prm.min_conf = p->min_confidence; h->prm.ema_alpha = (float)p->ema_alpha; h->prm.ema_beta = (float)(1 - p->ema_alpha);
+    h->prm.max_age = p->max_age; h->prm.n_init = p->n_init; h->prm.budget = p->nn_budget;
+    h->prm.width = p->image_width; h->prm.height = p->image_height; h->prm.E = p->feature_dim;
+    h->n_seq = n_seq; h->cap = cap_tracks; h->capd = cap_dets;
+    h->ncta = p->ctas_per_video > 0 ? p->ctas_per_video : 8;
+    h->state_stride = (ss_state_bytes(cap_tracks, cap_dets, p->nn_budget, p->feature_dim) + 255) & ~(size_t)255;
+    h->smem_bytes = ss_smem(cap_tracks, cap_dets);
+    h->state = nullptr;
+    if (h->smem_bytes > 220 * 1024) { delete h; return TK_ERR_CAPACITY; }
+    cudaError_t e = cudaMalloc((void**)&h->state, h->state_stride * n_seq);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(strongsort_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
+    if (e != cudaSuccess) { tk_set_last_cuda_error((int)e); if (h->state) cudaFree(h->state); delete h; return TK_ERR_CUDA; }
+    *handle = h;
+    return tk_strongsort_reset(h, 0, nullptr);
+}
+
+int tk_strongsort_reset(void* handle, int keep_id_counter, void* stream) {
+    (void)keep_id_counter;   // Tracker._next_id restarts with every StrongSORT() (tracker.py:51)
+    if (!handle) return TK_ERR_ARG;
+    SsHandle* h = (SsHandle*)handle;
+    strongsort_reset_kernel<<<h->n_seq, 128, 0, (cudaStream_t)stream>>>(h->state, h->state_stride, h->cap, h->capd, h->prm.budget, h->prm.E);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_strongsort_run(void* handle, const double* dets, const float* features, const int* offsets, int n_frames, double* out_rows,
+                      const int* out_start, int* out_frame_count, int* out_count, int out_capacity_rows, void* stream) {
+    if (!handle || !offsets || !out_rows || !out_start || !out_frame_count || !out_count || n_frames < 0) return TK_ERR_ARG;
+    SsHandle* h = (SsHandle*)handle;
+    if (n_frames == 0) return TK_OK;
+    int cap = h->cap, capd = h->capd, ncta = h->ncta;
+    void* args[] = {&h->prm, &h->state, &h->state_stride, &cap, &capd, &ncta, &dets, &features, &offsets, &n_frames,
+                    &out_rows, &out_start, &out_frame_count, &out_count, &out_capacity_rows};
+    // cooperative launch: every CTA of a video group must be co-resident for the group barrier
+    TK_CUDA_TRY(cudaLaunchCooperativeKernel((void*)strongsort_video_kernel, dim3(h->n_seq * ncta), dim3(SS_THREADS), args,
+                                            h->smem_bytes, (cudaStream_t)stream));
+    return TK_OK;
+}
+
+int tk_strongsort_status(void* handle, int* status_host, void* stream) {
+    if (!handle || !status_host) return TK_ERR_ARG;
+    SsHandle* h = (SsHandle*)handle;
+    for (int s = 0; s < h->n_seq; ++s)
+        TK_CUDA_TRY(cudaMemcpyAsync(status_host + s, h->state + (size_t)s * h->state_stride + 4 * sizeof(int), sizeof(int),
+                                    cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    TK_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return TK_OK;
+}
+
+int tk_strongsort_destroy(void* handle) {
+    if (!handle) return TK_ERR_ARG;
+    SsHandle* h = (SsHandle*)handle;
+    cudaFree(h->state);
+    delete h;
+    return TK_OK;
+}
+
+}  // extern "C"

@@ -122,6 +122,49 @@ class OCSortDevice(_VideoTrackerDevice):
                                        _lib.ASSO_CODES[asso_func], int(bool(use_byte))), n_seq, cap_tracks, cap_dets, device)
 
 
+class StrongSortDevice(_VideoTrackerDevice):
+    """StrongSORT association for ``n_seq`` videos with externally supplied ReID features (C ABI: tk_strongsort_*).
+
+    Mirrors StrongSORT(**hyperparams).update minus the in-tracker ReID forward and ECC
+    (/root/reference/plugins/track/strong_sort/strong_sort.py:23-85, /root/reference/tracklab/wrappers/track/strong_sort_api.py:66-93)."""
+
+    _prefix = "strongsort"
+
+    def __init__(self, feature_dim, max_dist=0.1594374041012136, max_iou_dist=0.5431835667667874, max_age=40,
+                 max_unmatched_preds=0, n_init=3, nn_budget=100, mc_lambda=0.995, ema_alpha=0.8962157769329083,
+                 min_confidence=0.4, image_size=(1920, 1080), ctas_per_video=8, n_seq=1, cap_tracks=128, cap_dets=128,
+                 device="cuda:0"):
+        self.feature_dim = feature_dim
+        self._create(_lib.StrongsortParams(max_dist, max_iou_dist, mc_lambda, ema_alpha, min_confidence, max_age, n_init,
+                                           nn_budget, max_unmatched_preds, feature_dim, image_size[0], image_size[1],
+                                           ctas_per_video), n_seq, cap_tracks, cap_dets, device)
+
+    def run(self, dets: torch.Tensor, offsets: torch.Tensor, features: torch.Tensor, out_rows: torch.Tensor | None = None,
+            out_start: torch.Tensor | None = None, out_count: torch.Tensor | None = None):
+        """features float32 [N, E] aligned with dets rows. Output capacity: 2 rows per detection per video by default."""
+        _require_cuda(dets, "dets"); _require_cuda(offsets, "offsets"); _require_cuda(features, "features")
+        assert dets.dtype == torch.float64 and dets.is_contiguous() and features.dtype == torch.float32 and features.is_contiguous()
+        assert features.shape == (dets.shape[0], self.feature_dim)
+        assert offsets.dtype == torch.int32 and offsets.is_contiguous() and offsets.shape[0] == self.n_seq
+        n_frames = offsets.shape[1] - 1
+        cap_rows = 2 * max(1, dets.shape[0])
+        if out_rows is None:
+            assert self.n_seq == 1, "pass out_rows/out_start for several videos"
+            out_rows = torch.empty((cap_rows, 8), dtype=torch.float64, device=dets.device)
+        else:
+            cap_rows = out_rows.shape[0] // self.n_seq
+        if out_start is None:
+            out_start = torch.zeros(self.n_seq, dtype=torch.int32, device=dets.device)
+        if out_count is None:
+            out_count = torch.zeros(self.n_seq, dtype=torch.int32, device=dets.device)
+        out_fc = torch.empty((self.n_seq, n_frames), dtype=torch.int32, device=dets.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._fn["run"](self.handle, dets.data_ptr(), features.data_ptr(), offsets.data_ptr(), n_frames,
+                                       out_rows.data_ptr(), out_start.data_ptr(), out_fc.data_ptr(), out_count.data_ptr(),
+                                       cap_rows, _stream_ptr()), "tk_strongsort_run")
+        return out_rows, out_fc, out_count
+
+
 def rows_to_frames(out_rows: torch.Tensor, out_fc: torch.Tensor, out_start: torch.Tensor, seq: int = 0):
     """Host helper: split the rows of video ``seq`` per frame -> (rows float64[R,8], frame int32[R])."""
     fc = out_fc[seq].cpu().numpy()
