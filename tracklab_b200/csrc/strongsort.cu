@@ -41,7 +41,9 @@ struct SsDev {
     int *hits, *age, *tsu, *track_id, *cls, *g_count, *g_head, *list, *free_list, *conf_list, *det_rows;
     unsigned char *state, *fresh;
     float *smooth, *gallery;   // [cap][E], [cap][budget][E] (gallery rows are stored re-normalised)
-    double* app;               // [cap][capd] appearance cost of the current frame (row = position in conf_list)
+    int* app_key;              // [cap][capd] appearance cost of the current frame as ordered-int float keys (row = position in conf_list)
+    int *row_trk, *row_start;  // stacked gallery rows of the frame -> confirmed-track position; first row of each track
+    float* dnorm_g;            // [capd] norms of the frame's detection features
     unsigned* bar;             // group barrier: count, generation
 };
 
@@ -52,6 +54,7 @@ __host__ __device__ inline size_t ss_state_bytes(int cap, int capd, int budget, 
     s += ss_al((size_t)cap * 8 * 8) + ss_al((size_t)cap * 64 * 8) + 2 * ss_al((size_t)cap * 8);
     s += 10 * ss_al((size_t)cap * 4) + ss_al((size_t)capd * 4) + 2 * ss_al((size_t)cap);
     s += ss_al((size_t)cap * E * 4) + ss_al((size_t)cap * budget * E * 4) + ss_al((size_t)cap * capd * 8);
+    s += ss_al((size_t)cap * budget * 4) + ss_al((size_t)(cap + 1) * 4) + ss_al((size_t)capd * 4);
     return s;
 }
 
@@ -71,7 +74,10 @@ __host__ __device__ inline SsDev ss_carve(char* base, int cap, int capd, int bud
     d.fresh = (unsigned char*)p; p += ss_al((size_t)cap);
     d.smooth = (float*)p; p += ss_al((size_t)cap * E * 4);
     d.gallery = (float*)p; p += ss_al((size_t)cap * budget * E * 4);
-    d.app = (double*)p;
+    d.app_key = (int*)p; p += ss_al((size_t)cap * capd * 8);
+    d.row_trk = (int*)p; p += ss_al((size_t)cap * budget * 4);
+    d.row_start = (int*)p; p += ss_al((size_t)(cap + 1) * 4);
+    d.dnorm_g = (float*)p;
     return d;
 }
 
@@ -131,10 +137,10 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
     auto take = [&](size_t bytes) { unsigned char* p = sp; sp += (bytes + 15) & ~(size_t)15; return p; };
     const int side = cap > capd ? cap : capd;
     // appearance tiles (all CTAs)
-    float* tb = (float*)take(sizeof(float) * 32 * (capd + 1));     // [32 k][capd] detections chunk
-    float* ta = (float*)take(sizeof(float) * 32 * 33);             // [32 g][32 k] gallery chunk
-    float* dmin = (float*)take(sizeof(float) * capd);
-    float* dnorm = (float*)take(sizeof(float) * capd);          // |feature| of the frame's detections
+    float* tb = (float*)take(sizeof(float) * 16 * 68);             // [16 k][64 d (+4 pad)] detections chunk
+    float* ta = (float*)take(sizeof(float) * 16 * 68);             // [16 k][64 rows (+4 pad)] gallery chunk
+    float* bmin = (float*)take(sizeof(float) * 64 * 64);           // per-tile min keys [track in tile][d]
+    float* dnorm = (float*)take(sizeof(float) * capd);             // |feature| of the frame's detections
     // master only
     double* cost = (double*)take(sizeof(double) * (size_t)(cap + 1) * (capd + 1));
     double* lap_u = (double*)take(sizeof(double) * side);
@@ -205,78 +211,108 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
                 const int nc = warp_compact(nt, 0, [&](int k) { return S.state[S.list[k]] == SS_CONFIRMED; },
                                             [&](int k, int p) { S.conf_list[p] = S.list[k]; });
                 if (lane_id() == 0) { sh->nconf = nc; S.hdr[7] = nc; }
+                // first stacked row of every confirmed track (exclusive scan of the gallery sizes)
+                int run = 0;
+                for (int c0 = 0; c0 < nc; c0 += 32) {
+                    const int c = c0 + lane_id();
+                    const int g = c < nc ? S.g_count[S.conf_list[c]] : 0;
+                    int incl = g;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane_id() >= o) incl += v; }
+                    if (c < nc) S.row_start[c] = run + incl - g;
+                    run += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane_id() == 0) { S.row_start[nc] = run; S.hdr[2] = run; }
+            }
+            __syncthreads();
+            {
+                const int nc = sh->nconf, nd2 = sh->nd;
+                for (int c = warp_id(); c < nc; c += SS_THREADS / 32) {
+                    const int r_lo = S.row_start[c], r_hi = S.row_start[c + 1];
+                    for (int r = r_lo + lane_id(); r < r_hi; r += 32) S.row_trk[r] = c;
+                }
+                for (int e = tid; e < nc * nd2; e += SS_THREADS) S.app_key[(size_t)(e / nd2) * capd + (e % nd2)] = 0x7fffffff;
+                for (int d = warp_id(); d < nd2; d += SS_THREADS / 32) {   // b = features / ||features|| (nn_matching.py:46-48)
+                    const float nf = warp_norm(feats + (size_t)(r0 + S.det_rows[d]) * E, E);
+                    if (lane_id() == 0) S.dnorm_g[d] = nf;
+                }
             }
             __threadfence();
         }
         group_barrier(S.bar, ncta);
 
         // ================= all CTAs: appearance cost (nn_matching.py:30-49,73-91,144-161) =================
+        // One stacked fp32 GEMM per frame: rows = every gallery sample of every confirmed track (row_trk maps a row to its
+        // track), columns = the frame's detections (normalised on load). 64x64 output tiles, 4x4 register micro-tiles,
+        // k walked in chunks of 16 through shared memory; the min over a track's samples is taken with ordered-int
+        // atomics, first in shared memory per tile, then once per (track, detection) in global memory.
         {
-            const int nd = S.hdr[6], nconf = S.hdr[7];
-            // b = features / ||features|| (nn_matching.py:46-48): the norms once per frame, the division in the tile load
-            if (cta < nconf)
-                for (int d = warp_id(); d < nd; d += SS_THREADS / 32) {
-                    const float nf = warp_norm(feats + (size_t)(r0 + S.det_rows[d]) * E, E);
-                    if (lane_id() == 0) dnorm[d] = nf;
-                }
+            const int nd = S.hdr[6], nconf = S.hdr[7], nrows = S.hdr[2];
+            for (int d = tid; d < nd; d += SS_THREADS) dnorm[d] = S.dnorm_g[d];
             __syncthreads();
-            for (int row = cta; row < nconf && nd > 0; row += ncta) {
-                const int s = S.conf_list[row];
-                const int g = S.g_count[s];
-                const float* G = S.gallery + (size_t)s * prm.budget * E;
-                for (int i = tid; i < nd; i += SS_THREADS) dmin[i] = 3.0e38f;
-                __syncthreads();
-                for (int g0 = 0; g0 < g; g0 += 32) {
-                    const int gn = min(32, g - g0);
-                    // each thread accumulates dots for (gi = tid>>3 ... ) pattern: 256 threads -> 32 g x 8 d-lanes
-                    const int gi = tid >> 3, dl = tid & 7;
-                    float acc[32];   // up to capd/8 detections per thread (capd <= 256)
-                    const int nper = (nd + 7) >> 3;
-#pragma unroll 1
-                    for (int q = 0; q < nper; ++q) acc[q] = 0.0f;
-                    for (int k0 = 0; k0 < E; k0 += 32) {
-                        for (int e = tid; e < 32 * 32; e += SS_THREADS) {
-                            const int r = e >> 5, k = e & 31;
-                            ta[r * 33 + k] = (r < gn && k0 + k < E) ? G[(size_t)(g0 + r) * E + k0 + k] : 0.0f;
-                        }
-                        for (int e = tid; e < nd * 32; e += SS_THREADS) {
-                            const int d = e >> 5, k = e & 31;
-                            tb[k * (capd + 1) + d] = (k0 + k < E) ? __fdiv_rn(feats[(size_t)(r0 + S.det_rows[d]) * E + k0 + k], dnorm[d]) : 0.0f;
-                        }
-                        __syncthreads();
-                        if (gi < gn) {
-#pragma unroll 1
-                            for (int q = 0; q < nper; ++q) {
-                                const int d = dl + 8 * q;
-                                if (d < nd) {
-                                    float a = acc[q];
+            const int tx = tid & 15, ty = tid >> 4;
+            const int ntile_r = (nrows + 63) >> 6, ntile_c = (nd + 63) >> 6;
+            for (int tile = cta; tile < ntile_r * ntile_c && nconf > 0; tile += ncta) {
+                const int tr0 = (tile / ntile_c) * 64, tc0 = (tile % ntile_c) * 64;
+                const int c_first = S.row_trk[tr0];
+                for (int e = tid; e < 64 * 64; e += SS_THREADS) ((int*)bmin)[e] = 0x7fffffff;
+                float acc[4][4];
 #pragma unroll
-                                    for (int k = 0; k < 32; ++k) a = fmaf(ta[gi * 33 + k], tb[k * (capd + 1) + d], a);
-                                    acc[q] = a;
-                                }
-                            }
-                        }
-                        __syncthreads();
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+                // per-thread load coordinates: 64 rows x 16 k per chunk = 1024 floats of A and of B, 4 each
+                const int lr = tid >> 2, lk = (tid & 3) * 4;
+                const int arow = tr0 + lr;
+                const float* ap = nullptr;
+                if (arow < nrows) {
+                    const int c = S.row_trk[arow];
+                    const int slot = S.conf_list[c];
+                    ap = S.gallery + ((size_t)slot * prm.budget + (arow - S.row_start[c])) * E;
+                }
+                const int bd = tc0 + lr;
+                const float* bp = bd < nd ? feats + (size_t)(r0 + S.det_rows[bd]) * E : nullptr;
+                const float bnorm = bd < nd ? dnorm[bd] : 1.0f;
+                __syncthreads();
+                for (int k0 = 0; k0 < E; k0 += 16) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = k0 + lk + q;
+                        ta[(lk + q) * 68 + lr] = (ap && k < E) ? ap[k] : 0.0f;
+                        tb[(lk + q) * 68 + lr] = (bp && k < E) ? __fdiv_rn(bp[k], bnorm) : 0.0f;
                     }
-                    if (gi < gn) {
-#pragma unroll 1
-                        for (int q = 0; q < nper; ++q) {
-                            const int d = dl + 8 * q;
-                            if (d < nd) {
-                                const float dist = __fsub_rn(1.0f, acc[q]);
-                                // min over the gallery; float min via ordered-int trick (dist may be -1e-7)
-                                int key = __float_as_int(dist);
-                                key = key >= 0 ? key : key ^ 0x7fffffff;
-                                atomicMin((int*)&dmin[d], key >= 0 ? key : key);
-                            }
-                        }
+                    __syncthreads();
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float4 av = *reinterpret_cast<const float4*>(ta + k * 68 + ty * 4);
+                        const float4 bv = *reinterpret_cast<const float4*>(tb + k * 68 + tx * 4);
+                        const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                        for (int a = 0; a < 4; ++a)
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
                     }
                     __syncthreads();
                 }
-                for (int i = tid; i < nd; i += SS_THREADS) {
-                    int key = ((int*)dmin)[i];
-                    key = key >= 0 ? key : key ^ 0x7fffffff;
-                    S.app[(size_t)row * capd + i] = (double)__int_as_float(key);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int r = tr0 + ty * 4 + a;
+                    if (r >= nrows) continue;
+                    const int lt = S.row_trk[r] - c_first;          // < 64: a 64-row tile spans at most 64 tracks
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int d = tx * 4 + b;
+                        if (tc0 + d >= nd) continue;
+                        int key = __float_as_int(__fsub_rn(1.0f, acc[a][b]));
+                        key = key >= 0 ? key : key ^ 0x7fffffff;
+                        atomicMin(&((int*)bmin)[lt * 64 + d], key);
+                    }
+                }
+                __syncthreads();
+                const int c_last = S.row_trk[min(tr0 + 63, nrows - 1)];
+                for (int e = tid; e < (c_last - c_first + 1) * 64; e += SS_THREADS) {
+                    const int lt = e >> 6, d = e & 63;
+                    if (tc0 + d < nd) atomicMin(&S.app_key[(size_t)(c_first + lt) * capd + tc0 + d], ((int*)bmin)[e]);
                 }
                 __syncthreads();
             }
@@ -311,7 +347,9 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
                 const int r = e / nd, d = e - r * nd;
                 const double* c = chol + 24 * r;
                 const double g = kf8_maha(c, c + 4, c + 20, d_z + 4 * d);
-                double a = S.app[(size_t)r * capd + d];
+                int akey = S.app_key[(size_t)r * capd + d];
+                akey = akey >= 0 ? akey : akey ^ 0x7fffffff;
+                double a = (double)__int_as_float(akey);
                 if (g > CHI2_4) a = INFTY_COST;
                 const double fused = __dadd_rn(__dmul_rn(prm.mc_lambda, a), __dmul_rn(1.0 - prm.mc_lambda, g));
                 const double red = fused > prm.max_dist ? 0.0 : fused - L_app;   // cost[cost > max] = max + 1e-5, pairs above max dropped
@@ -552,7 +590,7 @@ __global__ void strongsort_reset_kernel(char* base, size_t stride, int cap, int 
 size_t ss_smem(int cap, int capd) {
     const int side = cap > capd ? cap : capd;
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    size_t s = al(4 * 32 * (capd + 1)) + al(4 * 32 * 33) + 2 * al(4 * capd);
+    size_t s = 2 * al(4 * 16 * 68) + al(4 * 64 * 64) + al(4 * capd);
     s += al(8 * (size_t)(cap + 1) * (capd + 1)) + al(8 * side) + al(8 * 4 * capd) + al(4 * 4 * capd) + al(8 * 24 * cap);
     s += 5 * al(4 * side) + al(4 * cap) + 2 * al(4 * capd) + 3 * al(4 * cap) + al(cap) + al(capd) + al(sizeof(SsShared));
     return s;
