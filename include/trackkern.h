@@ -52,6 +52,19 @@ int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, int W, long l
                     void* dst, int out_dtype, int out_layout, int S, int pad_value, int swap_rb, double* ratio_out,
                     void* stream);
 
+/* ---- ReID input: crop gather + resize + normalise -------------------------------------------------------
+ * Replaces the per-crop CPU path of the in-tracker ReID:
+ *   /root/reference/plugins/track/strong_sort/strong_sort.py:102-108,135-145       (int()-truncated, clipped crop)
+ *   /root/reference/plugins/track/strong_sort/reid_multibackend.py:45-52,184-195   (PIL Resize((256,128)) bilinear with
+ *                                                                                   antialias, ToTensor, Normalize)
+ * frames: device uint8 [F,H,W,3] RGB; dets: device double [N,7] wrapper rows (only l,t,r,b are read); det_frame:
+ * device int[N] frame index of each row; out: device [N,3,out_h,out_w] (out_nhwc=1: [N,out_h,out_w,3]) of out_dtype.
+ * mean3/std3: HOST float[3]. Pixel values are integer-exact vs Pillow's resampler.
+ */
+int tk_crop_resize_norm(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,
+                        const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,
+                        const float* mean3, const float* std3, void* stream);
+
 /* ---- Detector post-processing: YOLOX decode + threshold + class-aware NMS --------------------------
  * Replaces rtmlib YOLOX.postprocess / multiclass_nms behind rtmlib_api.py:30 (score_thr 0.7, nms_thr 0.45).
  * pred: device [n_images, n_anchors, 5+n_classes] (reg xywh raw, obj, cls; logits=1 -> sigmoid applied here),

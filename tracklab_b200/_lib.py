@@ -52,6 +52,7 @@ def _declare(lib):
         "tk_abi_version": ([], ci),
         "tk_last_cuda_error": ([], ci),
         "tk_letterbox_u8": ([vp, ci, ci, ci, ctypes.c_longlong, vp, ci, ci, ci, ci, ci, P(cd), vp], ci),
+        "tk_crop_resize_norm": ([vp, ci, ci, ctypes.c_longlong, vp, vp, ci, vp, ci, ci, ci, ci, P(ctypes.c_float), P(ctypes.c_float), vp], ci),
         "tk_yolox_nms": ([vp, ci, ci, ci, ci, ci, ci, ctypes.c_float, ctypes.c_float, ctypes.c_float, ci, vp, vp, vp, vp, vp, vp], ci),
         "tk_pack_detections": ([vp, vp, vp, vp, ci, ci, ci, ci, ci, cd, cd, vp, vp, vp, ci, ci, vp, vp], ci),
         "tk_bias_act_nhwc": ([vp, vp, vp, vp, ctypes.c_longlong, ci, ci, ci, ci, ci, ci, vp], ci),

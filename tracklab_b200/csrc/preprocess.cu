@@ -198,3 +198,116 @@ extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, in
     TK_CUDA_TRY(cudaGetLastError());
     return TK_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ReID crop gather: crop (StrongSORT rule) -> PIL-exact antialiased bilinear resize to out_h x out_w -> /255 -> mean/std
+// Replaces the per-crop CPU path /root/reference/plugins/track/strong_sort/strong_sort.py:102-108,135-145 +
+// /root/reference/plugins/track/strong_sort/reid_multibackend.py:45-52,184-195 (T.Resize on a PIL image, ToTensor,
+// Normalize). Pillow's resampler is two-pass (horizontal then vertical) with 22-bit fixed-point coefficients and a
+// uint8 intermediate image; the kernel evaluates out(y,x) = clip8(sum_ky kv[ky] * clip8(sum_kx kh[kx] * src)) directly,
+// re-deriving the few horizontal taps per vertical tap instead of materialising the intermediate — integer-exact.
+// One CTA per (output row, crop): the vertical taps are shared by the row, each thread owns one output column.
+namespace {
+
+constexpr int CR_KMAX = 64;   // taps per axis: 2*ceil(scale)+1 -> crops up to ~31x the output size (a full 4K row into 128 px)
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for one output index (bilinear filter, support 1)
+__device__ __forceinline__ int pil_taps(int in_size, int out_size, int xx, int* k_int, int& xmin_out) {
+    const double scale = (double)in_size / (double)out_size;
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = 1.0 * filterscale;
+    const double center = __dmul_rn((double)xx + 0.5, scale);
+    const double ss = 1.0 / filterscale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    if (xmax > CR_KMAX) xmax = CR_KMAX;
+    double w[CR_KMAX];
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+        const double a = fabs(__dmul_rn(__dadd_rn((double)(x + xmin) - center, 0.5), ss));
+        const double v = a < 1.0 ? 1.0 - a : 0.0;
+        w[x] = v;
+        ww += v;
+    }
+    for (int x = 0; x < xmax; ++x) {
+        const double v = ww != 0.0 ? w[x] / ww : w[x];
+        k_int[x] = v < 0 ? (int)(-0.5 + v * 4194304.0) : (int)(0.5 + v * 4194304.0);
+    }
+    xmin_out = xmin;
+    return xmax;
+}
+
+__device__ __forceinline__ int clip8(int v) { v >>= 22; return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(128)
+crop_resize_norm_kernel(const unsigned char* __restrict__ frames, size_t frame_stride, int H, int W,
+                        const double* __restrict__ dets, const int* __restrict__ det_frame, OutT* __restrict__ out,
+                        int out_h, int out_w, float m0, float m1, float m2, float s0, float s1, float s2, int nhwc) {
+    __shared__ int kv[CR_KMAX];
+    __shared__ int s_ymin, s_ny;
+    const int n = blockIdx.y, yy = blockIdx.x;
+    const double* d = dets + (size_t)n * 7;
+    // StrongSORT crop rule (strong_sort.py:102-108): centre box -> int() truncation -> clip
+    const double cx = (d[0] + d[2]) / 2, cy = (d[1] + d[3]) / 2, bw = d[2] - d[0], bh = d[3] - d[1];
+    const int x1 = max((int)(cx - bw / 2), 0), x2 = min((int)(cx + bw / 2), W - 1);
+    const int y1 = max((int)(cy - bh / 2), 0), y2 = min((int)(cy + bh / 2), H - 1);
+    const int cw = x2 - x1, ch = y2 - y1;
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+    const unsigned char* img = frames + (size_t)det_frame[n] * frame_stride;
+    if (threadIdx.x == 0 && cw > 0 && ch > 0) { int ym; s_ny = pil_taps(ch, out_h, yy, kv, ym); s_ymin = ym; }
+    __syncthreads();
+    for (int xx = threadIdx.x; xx < out_w; xx += blockDim.x) {
+        int v[3] = {0, 0, 0};
+        if (cw > 0 && ch > 0) {
+            int kh[CR_KMAX], xmin;
+            const int nx = pil_taps(cw, out_w, xx, kh, xmin);
+            int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+            for (int ky = 0; ky < s_ny; ++ky) {
+                const unsigned char* row = img + ((size_t)(y1 + s_ymin + ky) * W + (x1 + xmin)) * 3;
+                int h[3] = {1 << 21, 1 << 21, 1 << 21};
+                // (when a size already matches, Pillow skips that pass; the taps then are {1<<22, 0}, i.e. the identity)
+                for (int kx = 0; kx < nx; ++kx) {
+                    h[0] += row[kx * 3 + 0] * kh[kx]; h[1] += row[kx * 3 + 1] * kh[kx]; h[2] += row[kx * 3 + 2] * kh[kx];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[c] += clip8(h[c]) * kv[ky];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = clip8(acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float t = __fdiv_rn((float)v[c], 255.0f);                 // ToTensor
+            const float o = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);      // Normalize
+            const size_t idx = nhwc ? (((size_t)n * out_h + yy) * out_w + xx) * 3 + c
+                                    : (((size_t)n * 3 + c) * out_h + yy) * out_w + xx;
+            out[idx] = cvt_out<OutT>(o);
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int tk_crop_resize_norm(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,
+                                   const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,
+                                   const float* mean3, const float* std3, void* stream) {
+    if (!frames || !dets || !det_frame || !out || !mean3 || !std3 || n_dets < 0 || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0) return TK_ERR_ARG;
+    if (out_dtype != TK_DTYPE_F32 && out_dtype != TK_DTYPE_BF16) return TK_ERR_ARG;
+    if (n_dets == 0) return TK_OK;
+    if (2 * ((W + out_w - 1) / out_w) + 1 > CR_KMAX || 2 * ((H + out_h - 1) / out_h) + 1 > CR_KMAX) return TK_ERR_CAPACITY;
+    dim3 grid(out_h, n_dets);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == TK_DTYPE_F32)
+        crop_resize_norm_kernel<float><<<grid, 128, 0, st>>>(frames, (size_t)frame_stride_bytes, H, W, dets, det_frame, (float*)out, out_h,
+                                                            out_w, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], out_nhwc);
+    else
+        crop_resize_norm_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(frames, (size_t)frame_stride_bytes, H, W, dets, det_frame,
+                                                                    (__nv_bfloat16*)out, out_h, out_w, mean3[0], mean3[1], mean3[2],
+                                                                    std3[0], std3[1], std3[2], out_nhwc);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
