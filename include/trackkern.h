@@ -58,7 +58,8 @@ int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, int W, long l
  *   /root/reference/plugins/track/strong_sort/reid_multibackend.py:45-52,184-195   (PIL Resize((256,128)) bilinear with
  *                                                                                   antialias, ToTensor, Normalize)
  * frames: device uint8 [F,H,W,3] RGB; dets: device double [N,7] wrapper rows (only l,t,r,b are read); det_frame:
- * device int[N] frame index of each row; out: device [N,3,out_h,out_w] (out_nhwc=1: [N,out_h,out_w,3]) of out_dtype.
+ * device int[N] frame index of each row; out: device [N,3,out_h,out_w] (out_nhwc=P>0: channels-last [N,out_h,out_w,P], P = channel pitch 3 or
+ * e.g. 8 with caller-zeroed padding channels) of out_dtype.
  * mean3/std3: HOST float[3]. Pixel values are integer-exact vs Pillow's resampler.
  */
 int tk_crop_resize_norm(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,

@@ -283,7 +283,7 @@ crop_resize_norm_kernel(const unsigned char* __restrict__ frames, size_t frame_s
         for (int c = 0; c < 3; ++c) {
             const float t = __fdiv_rn((float)v[c], 255.0f);                 // ToTensor
             const float o = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);      // Normalize
-            const size_t idx = nhwc ? (((size_t)n * out_h + yy) * out_w + xx) * 3 + c
+            const size_t idx = nhwc ? (((size_t)n * out_h + yy) * out_w + xx) * nhwc + c   // nhwc = channel pitch (3, or 8 with zero padding)
                                     : (((size_t)n * 3 + c) * out_h + yy) * out_w + xx;
             out[idx] = cvt_out<OutT>(o);
         }

@@ -182,18 +182,24 @@ REID_STD = (0.229, 0.224, 0.225)
 
 
 def crop_resize_norm(frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.Tensor, out_hw=(256, 128),
-                     out_dtype=torch.float32, channels_last: bool = False, mean=REID_MEAN, std=REID_STD):
-    """frames uint8 [F,H,W,3], dets float64 [N,7], det_frame int32 [N] -> ReID input [N,3,h,w] (C ABI: tk_crop_resize_norm)."""
+                     out_dtype=torch.float32, channels_last: bool = False, mean=REID_MEAN, std=REID_STD, pad_channels_to: int = 3):
+    """frames uint8 [F,H,W,3], dets float64 [N,7], det_frame int32 [N] -> ReID input [N,3,h,w] (C ABI: tk_crop_resize_norm).
+    pad_channels_to=8 (channels-last only) returns [N,8,h,w] with zero channels 3..7 for the fused backbone."""
     lib = _lib.load()
     _cuda(frames, "frames"); _cuda(dets, "dets"); _cuda(det_frame, "det_frame")
     F, H, W, _ = frames.shape
     N = dets.shape[0]
-    out = torch.empty((N, 3, out_hw[0], out_hw[1]), dtype=out_dtype, device=frames.device,
-                      memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    if pad_channels_to != 3:
+        assert channels_last
+        out = torch.zeros((N, pad_channels_to, out_hw[0], out_hw[1]), dtype=out_dtype,
+                          device=frames.device).contiguous(memory_format=torch.channels_last)
+    else:
+        out = torch.empty((N, 3, out_hw[0], out_hw[1]), dtype=out_dtype, device=frames.device,
+                          memory_format=torch.channels_last if channels_last else torch.contiguous_format)
     m = (ctypes.c_float * 3)(*mean)
     sd = (ctypes.c_float * 3)(*std)
     with torch.cuda.device(frames.device):
         _lib.check(lib.tk_crop_resize_norm(frames.data_ptr(), H, W, frames.stride(0), dets.data_ptr(), det_frame.data_ptr(), N,
-                                           out.data_ptr(), _dtype_code(out_dtype), int(channels_last), out_hw[0], out_hw[1], m, sd,
+                                           out.data_ptr(), _dtype_code(out_dtype), (pad_channels_to if channels_last else 0), out_hw[0], out_hw[1], m, sd,
                                            _stream()), "tk_crop_resize_norm")
     return out

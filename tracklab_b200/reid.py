@@ -1,0 +1,47 @@
+"""Device-resident ReID stage: frames + detection rows (HBM) -> appearance features float32 [N, E] (HBM).
+
+crop gather (tk_crop_resize_norm, PIL-exact) -> ResNet-50 in bf16 channels-last (cuDNN convolutions + libtrackkern
+epilogues). Stands in for the in-tracker ReID forward of the StrongSORT plugin
+(/root/reference/plugins/track/strong_sort/strong_sort.py:135-145, reid_multibackend.py:184-237) for all detections of a
+batch of frames at once; the features feed tk_strongsort_run.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, kernels
+from .nets.resnet_reid import build_resnet50_reid
+
+
+class ReidStageDevice:
+    def __init__(self, device="cuda:0", max_crops=2048, seed=1234, model=None, fused=True):
+        if not torch.cuda.is_available():
+            raise _lib.TrackKernError("ReidStageDevice needs a CUDA device (no CPU path)")
+        _lib.load()
+        self.device = torch.device(device)
+        self.model = (model if model is not None else build_resnet50_reid(seed)).to(self.device).eval()
+        self.feature_dim = self.model.feature_dim
+        self.max_crops = max_crops
+        self.fused = None
+        if fused:
+            from .nets.resnet_fused import ResNet50Fused
+            self.fused = ResNet50Fused(self.model, self.device)
+        else:
+            self.model = self.model.to(torch.bfloat16).to(memory_format=torch.channels_last)
+        torch.backends.cudnn.benchmark = True
+
+    @torch.no_grad()
+    def features(self, frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.Tensor) -> torch.Tensor:
+        """frames uint8 [F,H,W,3], dets float64 [N,7], det_frame int32 [N] (frame index of each row) -> float32 [N,E]."""
+        N = dets.shape[0]
+        out = torch.empty((N, self.feature_dim), dtype=torch.float32, device=self.device)
+        for i in range(0, N, self.max_crops):
+            j = min(N, i + self.max_crops)
+            if self.fused is not None:
+                x = kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.bfloat16, channels_last=True,
+                                             pad_channels_to=8)
+                out[i:j] = self.fused(x)
+            else:
+                x = kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.bfloat16, channels_last=True)
+                out[i:j] = self.model(x).float()
+        return out
