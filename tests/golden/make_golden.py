@@ -97,6 +97,59 @@ def run_reference(tracker, video, hyper):
     return np.concatenate(rows), np.concatenate(frames)
 
 
+def run_strongsort_end_to_end(name="strongsort_e2e_s5000"):
+    """The UNMODIFIED StrongSORT plugin incl. its in-tracker ReID (vendored ResNet-50, PIL crops) on synthetic frames.
+    Weights: tracklab_b200.nets.resnet_reid.build_resnet50_reid(seed) exported into the reference's conv+BN format
+    (identity BatchNorm statistics), so both sides hold the same function without committing 94 MB of weights."""
+    import tempfile
+    from pathlib import Path
+
+    from strong_sort.strong_sort import StrongSORT
+
+    from tracklab_b200.nets.resnet_reid import build_resnet50_reid
+    from tracklab_b200.synth import make_frames
+    gen = dict(seed=5000, n_frames=30, n_ids=12)
+    hyper = dict(max_dist=0.1594374041012136, max_iou_dist=0.5431835667667874, max_age=40, max_unmatched_preds=0,
+                 n_init=3, nn_budget=100, mc_lambda=0.995, ema_alpha=0.8962157769329083)
+    video = make_video(**gen)
+    mine = build_resnet50_reid(1234)
+    sd = {}
+    eps = 1e-5
+
+    def put(conv_key, bn_key, m):
+        sd[conv_key + ".weight"] = m.conv.weight.detach() * (1.0 + eps) ** 0.5
+        c = m.conv.weight.shape[0]
+        sd[bn_key + ".weight"], sd[bn_key + ".bias"] = torch.ones(c), m.conv.bias.detach().clone()
+        sd[bn_key + ".running_mean"], sd[bn_key + ".running_var"] = torch.zeros(c), torch.ones(c)
+        sd[bn_key + ".num_batches_tracked"] = torch.tensor(0)
+
+    put("conv1", "bn1", mine.conv1)
+    for li, layer in enumerate((mine.layer1, mine.layer2, mine.layer3, mine.layer4), start=1):
+        for bi, blk in enumerate(layer):
+            q = f"layer{li}.{bi}"
+            put(q + ".conv1", q + ".bn1", blk.conv1); put(q + ".conv2", q + ".bn2", blk.conv2); put(q + ".conv3", q + ".bn3", blk.conv3)
+            if blk.down is not None:
+                put(q + ".downsample.0", q + ".downsample.1", blk.down)
+    tmp = Path(tempfile.mkdtemp()) / "resnet50_synth.pt"
+    torch.save(sd, tmp)
+    model = StrongSORT(tmp, torch.device("cpu"), False, **hyper)
+    rows, frames = [], []
+    for f in range(video.n_frames):
+        d = video.frame(f)
+        d = d[d[:, 4] > MIN_CONF]
+        img = make_frames(video, f, f + 1, device="cpu")[0].numpy()
+        with torch.no_grad():
+            res = np.asarray(model.update(torch.from_numpy(d.copy()), img))
+        if res.size:
+            res = res[:, [0, 1, 2, 3, 4, 5, 6, 8]].astype(np.float64)
+            rows.append(res); frames.append(np.full(len(res), f, dtype=np.int32))
+    rows, frames = np.concatenate(rows), np.concatenate(frames)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), rows=rows, frames=frames,
+                        dets_sha=np.frombuffer(__import__("hashlib").sha256(video.dets.tobytes()).digest(), dtype=np.uint8),
+                        tracker="strongsort_e2e", gen=repr(gen), hyper=repr(hyper), min_conf=MIN_CONF)
+    print(f"{name}: {video.n_dets} dets -> {rows.shape[0]} rows, {len(np.unique(rows[:, 4]))} ids")
+
+
 def main(names):
     for name in names:
         tracker, gen, hyper = CASES[name]
@@ -110,4 +163,10 @@ def main(names):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:] or list(CASES))
+    args = sys.argv[1:]
+    if "strongsort_e2e" in args:
+        run_strongsort_end_to_end()
+        args.remove("strongsort_e2e")
+        if not args:
+            sys.exit(0)
+    main(args or list(CASES))

@@ -40,3 +40,24 @@ def test_strongsort_matches_oracle_fresh_seed():
         video.dets, video.offsets, video.embeddings)
     rows, frames = _run_device(video, hyper, 0.4)
     assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1.0, allow_relabel=True)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_strongsort_end_to_end_with_reid_matches_reference_plugin(precision):
+    """frames -> crop kernel -> ResNet-50 -> StrongSORT kernel vs the UNMODIFIED plugin incl. its in-tracker ReID on the
+    same synthetic frames (tests/golden/strongsort_e2e_s5000.npz, make_golden.py: run_strongsort_end_to_end)."""
+    from tracklab_b200.device_trackers import StrongSortDevice, rows_to_frames
+    from tracklab_b200.reid import ReidStageDevice
+    from tracklab_b200.synth import make_frames
+    g = load_golden("strongsort_e2e_s5000")
+    video = make_video(**g["gen"])
+    frames = make_frames(video, 0, video.n_frames, device="cuda")
+    dets = torch.from_numpy(video.dets).cuda()
+    offs = torch.from_numpy(video.offsets.astype(np.int32))[None].cuda()
+    det_frame = torch.from_numpy(np.repeat(np.arange(video.n_frames), np.diff(video.offsets)).astype(np.int32)).cuda()
+    feats = ReidStageDevice(precision=precision).features(frames, dets, det_frame)
+    trk = StrongSortDevice(feats.shape[1], **g["hyper"], min_confidence=g["min_conf"], image_size=(video.width, video.height))
+    rows, fc, cnt = trk.run(dets, offs, feats)
+    trk.check_status()
+    got, gf = rows_to_frames(rows, fc, torch.zeros(1, dtype=torch.int32))
+    assert_rows_match(got, gf, g["rows"], g["frames"], box_tol=1.0, allow_relabel=True)

@@ -17,6 +17,8 @@ There is no CPU fallback: constructing these modules without CUDA raises.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import pandas as pd
 import torch
@@ -185,3 +187,142 @@ class OCSORT(ImageLevelModule):
     collate_fn = None
     _device_cls = OCSortDevice
     _continue_ids = False
+
+
+# ---- StrongSORT: detect -> ReID -> associate inside one module, like the reference wrapper ---------------------------
+class _StrongSortImpl:
+    """Shared implementation bound into ``StrongSORT`` (see _bind). Replaces
+    /root/reference/tracklab/wrappers/track/strong_sort_api.py:16-93: the reference decodes the frame in ``process``, crops
+    and runs the ReID network inside the tracker for every frame; here the video's frames are decoded once per batch of
+    images, all crops of the batch go through the crop-gather kernel + backbone together, and the whole video is
+    associated by one tk_strongsort_run launch. ``cfg.ecc`` must be false (camera compensation is out of scope)."""
+
+    def __init__(self, cfg, device, **kwargs):
+        ImageLevelModule.__init__(self, batch_size=1)
+        if not torch.cuda.is_available():
+            raise _lib.TrackKernError(f"{type(self).__name__} needs a CUDA device: tracklab_b200 has no CPU path")
+        if bool(_cfg_get(cfg, "ecc", False)):
+            raise _lib.TrackKernError("ecc=True (cv2.findTransformECC camera compensation) is not implemented on device")
+        from .device_trackers import StrongSortDevice
+        from .reid import ReidStageDevice
+        self.cfg = cfg
+        self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
+        self.cap_tracks = int(_cfg_get(cfg, "cap_tracks", 128))
+        self.cap_dets = int(_cfg_get(cfg, "cap_dets", 128))
+        self.frames_per_batch = _cfg_get(cfg, "frames_per_batch", None)
+        self.decode_batch = int(_cfg_get(cfg, "decode_batch", 16))
+        self.hyper = dict(_cfg_get(cfg, "hyperparams", {}) or {})
+        self.min_confidence = float(_cfg_get(cfg, "min_confidence", 0.4))
+        model = None
+        weights = _cfg_get(cfg, "model_weights", None)
+        if weights is not None and os.path.isfile(str(weights)):   # a reference-format ResNet-50 state_dict (conv + BN)
+            from .nets.resnet_reid import ResNet50ReID
+            sd = torch.load(str(weights), map_location="cpu")
+            model = ResNet50ReID().eval().from_reference_state_dict(sd.get("state_dict", sd))
+        self.reid = ReidStageDevice(device=self.device, model=model, precision=_cfg_get(cfg, "reid_precision", "bf16"))
+        self._trk_cls = StrongSortDevice
+        self.tracker = None
+        self._pipe = _TrackerDatapipe(self, self.frames_per_batch)
+        self._result = None
+
+    def reset(self):
+        self._result = None
+        if self.tracker is not None:
+            self.tracker.reset()
+
+    def datapipe(self):
+        return self._pipe
+
+    def dataloader(self, engine=None):
+        return _VideoBatches(self._pipe)
+
+    def preprocess(self, image, detections, metadata):   # never called: the datapipe is overridden
+        return {"input": []}
+
+    def _track_video(self, img_metadatas, detections):
+        import cv2
+        image_ids = np.asarray(img_metadatas.index)
+        if detections is None or len(detections) == 0:
+            self._result = pd.DataFrame(columns=["image_id"] + self.output_columns)
+            return
+        rows, offsets, _ = _rows_from_detections(image_ids, detections, self.cap_dets)
+        paths = list(img_metadatas["file_path"])
+        first = cv2.imread(paths[0])
+        H, W = first.shape[:2]
+        if self.tracker is None or self.tracker.params.image_width != W or self.tracker.params.image_height != H:
+            self.tracker = self._trk_cls(self.reid.feature_dim, **self.hyper, min_confidence=self.min_confidence,
+                                         image_size=(W, H), cap_tracks=self.cap_tracks, cap_dets=self.cap_dets, device=self.device)
+        d_dev = torch.from_numpy(rows).to(self.device)
+        feats = torch.empty((len(rows), self.reid.feature_dim), dtype=torch.float32, device=self.device)
+        for f0 in range(0, len(paths), self.decode_batch):   # decode once per image (cv2_load_image: BGR -> RGB, utils/cv2.py:54-66)
+            f1 = min(len(paths), f0 + self.decode_batch)
+            batch = np.stack([cv2.cvtColor(cv2.imread(p), cv2.COLOR_BGR2RGB) for p in paths[f0:f1]])
+            fr = torch.from_numpy(batch).to(self.device)
+            r0, r1 = int(offsets[f0]), int(offsets[f1])
+            if r1 > r0:
+                det_frame = torch.from_numpy(np.repeat(np.arange(f1 - f0), np.diff(offsets[f0:f1 + 1])).astype(np.int32)).to(self.device)
+                feats[r0:r1] = self.reid.features(fr, d_dev[r0:r1], det_frame)
+        o_dev = torch.from_numpy(offsets)[None].to(self.device)
+        out_rows, out_fc, out_cnt = self.tracker.run(d_dev, o_dev, feats)
+        self.tracker.check_status()
+        n = int(out_cnt[0].item())
+        res = out_rows[:n].cpu().numpy()
+        fc = out_fc[0].cpu().numpy()
+        frame_of_row = np.repeat(np.arange(len(fc)), fc)
+        ltrb = res[:, :4]
+        self._result = pd.DataFrame({
+            "track_bbox_ltwh": list(np.column_stack([ltrb[:, 0], ltrb[:, 1], ltrb[:, 2] - ltrb[:, 0], ltrb[:, 3] - ltrb[:, 1]])),
+            "track_bbox_conf": res[:, 6], "track_id": res[:, 4], "image_id": image_ids[frame_of_row],
+        }, index=pd.Index(res[:, 7].astype(int), name="idxs"))
+
+    def process(self, batch, detections, metadatas):
+        if len(detections) == 0 or self._result is None or len(self._result) == 0:
+            return []
+        sel = self._result[self._result["image_id"].isin(list(metadatas.index))]
+        if len(sel) == 0:
+            return []
+        # a track is reported up to one frame after its last update with the detection id of that update, so a row may
+        # point at a detection of the previous image — the reference wrapper lets the override happen (strong_sort_api.py:78-82)
+        sel = sel[~sel.index.duplicated(keep="last")]
+        return sel[["track_bbox_ltwh", "track_bbox_conf", "track_id"]]
+
+
+def _rows_from_detections(image_ids, detections, cap_dets):
+    """DataFrame rows of one video -> float64 [N,7] = [l,t,r,b,conf,cls,det_id] grouped by frame + int32 offsets."""
+    pos = {int(i): k for k, i in enumerate(image_ids)}
+    img = detections["image_id"].to_numpy()
+    keep = np.fromiter((int(i) in pos for i in img), dtype=bool, count=len(img))
+    det = detections[keep]
+    frame = np.fromiter((pos[int(i)] for i in det["image_id"].to_numpy()), dtype=np.int64, count=len(det))
+    order = np.argsort(frame, kind="stable")
+    ltwh = np.stack(det["bbox_ltwh"].to_numpy()).astype(np.float64).reshape(-1, 4)[order]
+    rows = np.empty((len(det), 7), dtype=np.float64)
+    rows[:, 0], rows[:, 1] = ltwh[:, 0], ltwh[:, 1]
+    rows[:, 2], rows[:, 3] = ltwh[:, 0] + ltwh[:, 2], ltwh[:, 1] + ltwh[:, 3]
+    rows[:, 4] = det["bbox_conf"].to_numpy(dtype=np.float64)[order]
+    rows[:, 5] = det["category_id"].to_numpy(dtype=np.float64)[order]
+    rows[:, 6] = np.asarray(det.index, dtype=np.float64)[order]
+    counts = np.bincount(frame, minlength=len(image_ids))
+    offsets = np.zeros(len(image_ids) + 1, dtype=np.int32)
+    np.cumsum(counts, out=offsets[1:])
+    if len(counts) and counts.max() > cap_dets:
+        raise _lib.TrackKernError(f"{counts.max()} detections in one frame exceed cap_dets={cap_dets}")
+    return rows, offsets, frame[order]
+
+
+def _bind_from(cls, impl):
+    for name in ("__init__", "reset", "dataloader", "preprocess", "_track_video", "process"):
+        setattr(cls, name, impl.__dict__[name])
+    cls.datapipe = property(impl.__dict__["datapipe"])
+    cls.__abstractmethods__ = frozenset()
+    return cls
+
+
+class StrongSORT(ImageLevelModule):
+    """Drop-in for tracklab.wrappers.track.strong_sort_api.StrongSORT (ReID + association on device, ecc off)."""
+    input_columns = list(_IN_COLS)
+    output_columns = list(_OUT_COLS)
+    collate_fn = None
+
+
+_bind_from(StrongSORT, _StrongSortImpl)

@@ -14,7 +14,7 @@ from .nets.resnet_reid import build_resnet50_reid
 
 
 class ReidStageDevice:
-    def __init__(self, device="cuda:0", max_crops=2048, seed=1234, model=None, fused=True):
+    def __init__(self, device="cuda:0", max_crops=2048, seed=1234, model=None, fused=True, precision="bf16"):
         if not torch.cuda.is_available():
             raise _lib.TrackKernError("ReidStageDevice needs a CUDA device (no CPU path)")
         _lib.load()
@@ -23,7 +23,10 @@ class ReidStageDevice:
         self.feature_dim = self.model.feature_dim
         self.max_crops = max_crops
         self.fused = None
-        if fused:
+        self.precision = precision
+        if precision == "fp32":     # parity mode: plain fp32 module, TF32 off (features within ~1e-5 of the CPU reference)
+            self.model = self.model.float()
+        elif fused:
             from .nets.resnet_fused import ResNet50Fused
             self.fused = ResNet50Fused(self.model, self.device)
         else:
@@ -37,7 +40,15 @@ class ReidStageDevice:
         out = torch.empty((N, self.feature_dim), dtype=torch.float32, device=self.device)
         for i in range(0, N, self.max_crops):
             j = min(N, i + self.max_crops)
-            if self.fused is not None:
+            if self.precision == "fp32":
+                x = kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.float32)
+                tf32 = torch.backends.cudnn.allow_tf32
+                torch.backends.cudnn.allow_tf32 = False
+                try:
+                    out[i:j] = self.model(x)
+                finally:
+                    torch.backends.cudnn.allow_tf32 = tf32
+            elif self.fused is not None:
                 x = kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.bfloat16, channels_last=True,
                                              pad_channels_to=8)
                 out[i:j] = self.fused(x)
