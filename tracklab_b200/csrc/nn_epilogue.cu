@@ -28,41 +28,60 @@ __device__ __forceinline__ float silu_f(float x) {
 }
 
 // src [n_pix, C] contiguous; dst / res rows of pitch dst_pitch / res_pitch elements, channel offsets given.
+// Grid-stride over 16-byte vectors, two vectors in flight per thread; (pixel, channel-vector) coordinates are advanced
+// incrementally (stride = q * c_vec + r) so the loop has no integer division — the first version spent ~200 instructions
+// per vector on a 64-bit divide and was issue-bound at 45 % of HBM peak (profiles/r01_ncu_summary.md).
+__device__ __forceinline__ void epi_one(const __nv_bfloat16* __restrict__ src, const float* __restrict__ bias,
+                                        __nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ res, long long i,
+                                        long long pix, int cv, int dst_pitch, int dst_off, int res_pitch, int res_off, int act) {
+    const bf16x8 x = *reinterpret_cast<const bf16x8*>(src + i * 8);
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + cv * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + cv * 8 + 4);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(x.v[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
+    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    if (act == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
+    } else if (act == 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+    }
+    if (res) {
+        const bf16x8 r = *reinterpret_cast<const bf16x8*>(res + pix * res_pitch + res_off + cv * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(r.v[k]); f[2 * k] += t.x; f[2 * k + 1] += t.y; }
+        if (act == 3) {   // residual first, then ReLU (ResNet bottleneck tail)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+        }
+    }
+    bf16x8 o;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+    *reinterpret_cast<bf16x8*>(dst + pix * dst_pitch + dst_off + cv * 8) = o;
+}
+
 __global__ void __launch_bounds__(256)
 bias_act_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst,
                 const __nv_bfloat16* __restrict__ res, long long n_vec, int c_vec, int dst_pitch, int dst_off,
                 int res_pitch, int res_off, int act) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
-        const long long pix = i / c_vec;
-        const int cv = (int)(i - pix * c_vec);
-        const bf16x8 x = *reinterpret_cast<const bf16x8*>(src + i * 8);
-        const float4 b0 = *reinterpret_cast<const float4*>(bias + cv * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(bias + cv * 8 + 4);
-        float f[8];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(x.v[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
-        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w; f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-        if (act == 1) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = silu_f(f[k]);
-        } else if (act == 2) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
-        }
-        if (res) {
-            const bf16x8 r = *reinterpret_cast<const bf16x8*>(res + pix * res_pitch + res_off + cv * 8);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(r.v[k]); f[2 * k] += t.x; f[2 * k + 1] += t.y; }
-            if (act == 3) {   // residual first, then ReLU (ResNet bottleneck tail)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
-            }
-        }
-        bf16x8 o;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o.v[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
-        *reinterpret_cast<bf16x8*>(dst + pix * dst_pitch + dst_off + cv * 8) = o;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long sq = stride / c_vec;
+    const int sr = (int)(stride - sq * c_vec);
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long pix = i / c_vec;
+    int cv = (int)(i - pix * c_vec);
+    for (; i + stride < n_vec; i += 2 * stride) {
+        long long pix2 = pix + sq; int cv2 = cv + sr;
+        if (cv2 >= c_vec) { cv2 -= c_vec; ++pix2; }
+        epi_one(src, bias, dst, res, i, pix, cv, dst_pitch, dst_off, res_pitch, res_off, act);
+        epi_one(src, bias, dst, res, i + stride, pix2, cv2, dst_pitch, dst_off, res_pitch, res_off, act);
+        pix = pix2 + sq; cv = cv2 + sr;
+        if (cv >= c_vec) { cv -= c_vec; ++pix; }
     }
+    if (i < n_vec) epi_one(src, bias, dst, res, i, pix, cv, dst_pitch, dst_off, res_pitch, res_off, act);
 }
 
 // SPP: x [B, H, W, C] -> dst [B, H, W, 4C] = [x | max5 | max9 | max13] (stride 1, -inf padding).
@@ -126,7 +145,7 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ src, int src_pitch, int src_
 
 inline int grid_for(long long n_vec) {
     long long blocks = (n_vec + 255) / 256;
-    const long long cap = 148LL * 16;   // 16 resident CTAs of 256 threads per SM, grid-stride beyond that
+    const long long cap = 148LL * 8;    // 8 resident CTAs of 256 threads per SM (one full wave), grid-stride beyond that
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 

@@ -163,6 +163,109 @@ letterbox_kernel(const unsigned char* __restrict__ src, size_t frame_stride, int
     }
 }
 
+
+// Focus-unfolded layout (out_layout 2): one CTA per PAIR of output rows, so every thread owns whole 16-channel pixels of
+// the [S/2, S/2, 16] tensor and writes them with full 32-byte stores (the per-row version wrote 2-byte pieces of those
+// pixels; the partial-sector writes made L2 read each sector back from HBM: 2.4x the algorithmic traffic in ncu).
+template <typename OutT>
+__global__ void __launch_bounds__(LB_THREADS)
+letterbox_focus16_kernel(const unsigned char* __restrict__ src, size_t frame_stride, int H, int W, OutT* __restrict__ dst,
+                         int S, int rw, int rh, double scale_x, double scale_y, int area2x, int pad, int swap_rb,
+                         const unsigned char* __restrict__ src_end) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int fy = blockIdx.x, b = blockIdx.y, S2 = S >> 1;
+    OutT* orow = dst + (((size_t)b * S2 + fy) * S2) * 16;
+    const float padf = (float)pad;
+    const size_t row_bytes = (size_t)W * 3;
+    const size_t pitch = (row_bytes + 31 + 15) & ~(size_t)15;
+    const unsigned char* base = src + (size_t)b * frame_stride;
+    Tap ty[2];
+    const unsigned char* g[4];
+    size_t al[4];
+    unsigned nb[4];
+    bool need[4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int y = 2 * fy + r;
+        if (area2x) { ty[r].s0 = 2 * y; ty[r].s1 = 2 * y + 1; ty[r].w0 = 1; ty[r].w1 = 1; }
+        else ty[r] = linear_tap(min(y, rh - 1), H, scale_y);
+        const bool live = y < rh;
+        g[2 * r] = base + (size_t)ty[r].s0 * row_bytes;
+        g[2 * r + 1] = base + (size_t)ty[r].s1 * row_bytes;
+        need[2 * r] = live;
+        need[2 * r + 1] = live && (area2x || ty[r].w1 != 0);
+    }
+    bool tail = false;
+    unsigned total = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        al[k] = (size_t)g[k] & 15;
+        nb[k] = (unsigned)((al[k] + row_bytes + 15) & ~(size_t)15);
+        if (need[k]) { total += nb[k]; tail = tail || (g[k] - al[k] + nb[k] > src_end); }
+    }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    if (total > 0) {
+        if (tail) {
+            for (int k = 0; k < 4; ++k)
+                if (need[k]) for (size_t i = threadIdx.x; i < row_bytes; i += LB_THREADS) smem[k * pitch + al[k] + i] = g[k][i];
+            __syncthreads();
+        } else {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar, total);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (need[k]) bulk_g2s(smem + k * pitch, g[k] - al[k], nb[k], &bar);
+            }
+            mbar_wait(&bar, 0);
+        }
+    }
+    const int c0 = swap_rb ? 2 : 0, c2 = swap_rb ? 0 : 2;
+    for (int fx = threadIdx.x; fx < S2; fx += LB_THREADS) {
+        float px[16];
+#pragma unroll
+        for (int k = 12; k < 16; ++k) px[k] = 0.0f;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const int x = 2 * fx + dx;
+            Tap tx;
+            if (!area2x) tx = linear_tap(min(x, rw - 1), W, scale_x);
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const int y = 2 * fy + dy;
+                const int patch = dx * 2 + dy;   // (tl, bl, tr, br) = (dx,dy) (0,0),(0,1),(1,0),(1,1)
+                float v[3] = {padf, padf, padf};
+                if (x < rw && y < rh) {
+                    const unsigned char* r0 = smem + (2 * dy) * pitch + al[2 * dy];
+                    const unsigned char* r1 = need[2 * dy + 1] ? smem + (2 * dy + 1) * pitch + al[2 * dy + 1] : r0;
+                    if (area2x) {
+                        const unsigned char* p0 = r0 + 6 * x;
+                        const unsigned char* p1 = r1 + 6 * x;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) v[c] = (float)((p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const int h0 = r0[3 * tx.s0 + c] * tx.w0 + r0[3 * tx.s1 + c] * tx.w1;
+                            const int h1 = r1[3 * tx.s0 + c] * tx.w0 + r1[3 * tx.s1 + c] * tx.w1;
+                            const int o = (((ty[dy].w0 * (h0 >> 4)) >> 16) + ((ty[dy].w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                            v[c] = (float)min(max(o, 0), 255);
+                        }
+                    }
+                }
+                px[patch * 3 + 0] = v[c0]; px[patch * 3 + 1] = v[1]; px[patch * 3 + 2] = v[c2];
+            }
+        }
+        OutT o16[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) o16[k] = cvt_out<OutT>(px[k]);
+        uint4* d4 = reinterpret_cast<uint4*>(orow + (size_t)fx * 16);
+        const uint4* s4 = reinterpret_cast<const uint4*>(o16);
+#pragma unroll
+        for (int k = 0; k < (int)(16 * sizeof(OutT) / 16); ++k) d4[k] = s4[k];
+    }
+}
+
 }  // namespace
 
 extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, int W, long long frame_stride_bytes,
@@ -183,8 +286,25 @@ extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, in
     if (smem > 200 * 1024) return TK_ERR_CAPACITY;
     if (((size_t)src & 15) != 0) return TK_ERR_ARG;  // bulk copies round spans down to 16 B
     const unsigned char* src_end = src + (size_t)(n_frames - 1) * (size_t)frame_stride_bytes + (size_t)H * W * 3;
-    dim3 grid(S, n_frames);
     cudaStream_t st = (cudaStream_t)stream;
+    if (out_layout == 2) {
+        const size_t smem4 = 4 * pitch + 16;
+        if (smem4 > 200 * 1024) return TK_ERR_CAPACITY;
+        dim3 grid2(S / 2, n_frames);
+        if (out_dtype == TK_DTYPE_F32) {
+            TK_CUDA_TRY(cudaFuncSetAttribute(letterbox_focus16_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            letterbox_focus16_kernel<float><<<grid2, LB_THREADS, smem4, st>>>(src, (size_t)frame_stride_bytes, H, W, (float*)dst, S, rw, rh,
+                                                                              scale_x, scale_y, area2x, pad_value, swap_rb, src_end);
+        } else {
+            TK_CUDA_TRY(cudaFuncSetAttribute(letterbox_focus16_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+            letterbox_focus16_kernel<__nv_bfloat16><<<grid2, LB_THREADS, smem4, st>>>(src, (size_t)frame_stride_bytes, H, W,
+                                                                                      (__nv_bfloat16*)dst, S, rw, rh, scale_x, scale_y,
+                                                                                      area2x, pad_value, swap_rb, src_end);
+        }
+        TK_CUDA_TRY(cudaGetLastError());
+        return TK_OK;
+    }
+    dim3 grid(S, n_frames);
     if (out_dtype == TK_DTYPE_F32) {
         TK_CUDA_TRY(cudaFuncSetAttribute(letterbox_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         letterbox_kernel<float><<<grid, LB_THREADS, smem, st>>>(src, (size_t)frame_stride_bytes, H, W, (float*)dst, S, rw, rh,
