@@ -52,6 +52,7 @@ class YoloxDetectorDevice:
         self.pred = None
         self.nms_out = None
         self.time_kernels = False
+        self.launches_per_batch = 0
         self.kernel_events = []
         self.variant = variant
         torch.backends.cudnn.benchmark = True
@@ -100,6 +101,11 @@ class YoloxDetectorDevice:
         return self.fused(x) if self.use_fused else self.model(x)
 
     def _forward_post(self, W, H):
+        n0 = kernels.LAUNCHES
+        self._forward_post_impl(W, H)
+        self.launches_per_batch = kernels.LAUNCHES - n0   # libtrackkern launches of one batch (replayed by the CUDA graph)
+
+    def _forward_post_impl(self, W, H):
         self.pred = self._net(self.x)
         self.nms_out = kernels.yolox_nms(self.pred, self.ratio, self.size, logits=True, score_thr=self.score_thr,
                                          nms_thr=self.nms_thr, max_out=self.max_per_image, status=self.status)

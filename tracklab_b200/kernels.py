@@ -9,6 +9,13 @@ from . import _lib
 
 F32, BF16 = 0, 1
 
+LAUNCHES = 0   # number of libtrackkern kernel launches issued through this module (bench.py reports it)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -47,7 +54,7 @@ def letterbox(frames: torch.Tensor, size: int = 640, out_dtype=torch.bfloat16, p
     ratio = ctypes.c_double()
     with torch.cuda.device(frames.device):
         _lib.check(lib.tk_letterbox_u8(frames.data_ptr(), B, H, W, frames.stride(0), out.data_ptr(), _dtype_code(out.dtype),
-                                       int(nhwc), size, pad, int(swap_rb), ctypes.byref(ratio), _stream()), "tk_letterbox_u8")
+                                       int(nhwc), size, pad, int(swap_rb), ctypes.byref(ratio), _stream()), "tk_letterbox_u8"); _count()
     return out, ratio.value
 
 
@@ -68,7 +75,7 @@ def yolox_nms(pred: torch.Tensor, ratio: float, input_size: int = 640, logits: b
         _lib.check(lib.tk_yolox_nms(pred.data_ptr(), _dtype_code(pred.dtype), B, A, C - 5, input_size, int(logits),
                                     float(ratio), float(score_thr), float(nms_thr), max_out, boxes.data_ptr(),
                                     scores.data_ptr(), cls.data_ptr(), count.data_ptr(), status.data_ptr(), _stream()),
-                   "tk_yolox_nms")
+                   "tk_yolox_nms"); _count()
     return boxes, scores, cls, count, status
 
 
@@ -84,7 +91,7 @@ def pack_detections(boxes, scores, cls, count, width: int, height: int, cursor: 
                                           keep_class, width, height, float(fixed_conf), float(category_id),
                                           cursor.data_ptr(), dets_out.data_ptr(), offsets_out.data_ptr(),
                                           dets_out.shape[0], offsets_out.shape[0] - 1, status.data_ptr(), _stream()),
-                   "tk_pack_detections")
+                   "tk_pack_detections"); _count()
     return dets_out, offsets_out
 
 
@@ -99,7 +106,7 @@ def bias_act(src: torch.Tensor, bias: torch.Tensor, dst: torch.Tensor, dst_offse
     rp, r = (residual.shape[1], residual.data_ptr()) if residual is not None else (0, None)
     with torch.cuda.device(src.device):
         _lib.check(lib.tk_bias_act_nhwc(src.data_ptr(), bias.data_ptr(), dst.data_ptr(), r, B * H * W, C, dst.shape[1], dst_offset,
-                                        rp, res_offset, act, _stream()), "tk_bias_act_nhwc")
+                                        rp, res_offset, act, _stream()), "tk_bias_act_nhwc"); _count()
     return dst
 
 
@@ -108,7 +115,7 @@ def spp_pool(x: torch.Tensor, dst: torch.Tensor, dst_offset: int = 0):
     lib = _lib.load()
     B, C, H, W = x.shape
     with torch.cuda.device(x.device):
-        _lib.check(lib.tk_spp_nhwc(x.data_ptr(), dst.data_ptr(), B, H, W, C, dst.shape[1], dst_offset, _stream()), "tk_spp_nhwc")
+        _lib.check(lib.tk_spp_nhwc(x.data_ptr(), dst.data_ptr(), B, H, W, C, dst.shape[1], dst_offset, _stream()), "tk_spp_nhwc"); _count()
     return dst
 
 
@@ -119,7 +126,7 @@ def upsample2x(src: torch.Tensor, dst: torch.Tensor, dst_offset: int = 0, src_of
     C = channels or Cs
     with torch.cuda.device(src.device):
         _lib.check(lib.tk_upsample2x_nhwc(src.data_ptr(), Cs, src_offset, dst.data_ptr(), B, h, w, C, dst.shape[1], dst_offset,
-                                          _stream()), "tk_upsample2x_nhwc")
+                                          _stream()), "tk_upsample2x_nhwc"); _count()
     return dst
 
 
@@ -132,7 +139,7 @@ def iou_matrix(a: torch.Tensor, b: torch.Tensor, variant: str = "iou"):
     out = torch.empty((B, N, M), dtype=torch.float64, device=a.device)
     with torch.cuda.device(a.device):
         _lib.check(lib.tk_iou_matrix(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, N, M, _lib.ASSO_CODES[variant], _stream()),
-                   "tk_iou_matrix")
+                   "tk_iou_matrix"); _count()
     return out
 
 
@@ -144,7 +151,7 @@ def iou_p1_dist(a: torch.Tensor, b: torch.Tensor):
     M = b.shape[1]
     out = torch.empty((B, N, M), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
-        _lib.check(lib.tk_iou_p1_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, N, M, _stream()), "tk_iou_p1_f32")
+        _lib.check(lib.tk_iou_p1_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), B, N, M, _stream()), "tk_iou_p1_f32"); _count()
     return out
 
 
@@ -158,7 +165,7 @@ def cosine_dist(a: torch.Tensor, b: torch.Tensor):
     scratch = torch.empty((B * (N + M),), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         _lib.check(lib.tk_cosine_dist(a.data_ptr(), b.data_ptr(), out.data_ptr(), scratch.data_ptr(), B, N, M, E, _stream()),
-                   "tk_cosine_dist")
+                   "tk_cosine_dist"); _count(3)
     return out
 
 
@@ -173,7 +180,7 @@ def lap_batched(cost: torch.Tensor, cost_limit: float | None = None, status: tor
         status = torch.zeros((1,), dtype=torch.int32, device=cost.device)
     with torch.cuda.device(cost.device):
         _lib.check(lib.tk_lap_batched(cost.data_ptr(), B, N, M, float(cost_limit or 0.0), int(cost_limit is not None),
-                                      x.data_ptr(), y.data_ptr(), status.data_ptr(), _stream()), "tk_lap_batched")
+                                      x.data_ptr(), y.data_ptr(), status.data_ptr(), _stream()), "tk_lap_batched"); _count()
     return x, y, status
 
 
@@ -201,5 +208,5 @@ def crop_resize_norm(frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.
     with torch.cuda.device(frames.device):
         _lib.check(lib.tk_crop_resize_norm(frames.data_ptr(), H, W, frames.stride(0), dets.data_ptr(), det_frame.data_ptr(), N,
                                            out.data_ptr(), _dtype_code(out_dtype), (pad_channels_to if channels_last else 0), out_hw[0], out_hw[1], m, sd,
-                                           _stream()), "tk_crop_resize_norm")
+                                           _stream()), "tk_crop_resize_norm"); _count()
     return out

@@ -90,7 +90,7 @@ class DetectTrackPipeline:
                 done.record(self.s_det)
                 if host:
                     free_ev[i & 1] = done
-            self.launches += 3  # letterbox, yolox_nms, pack_detections (the network itself is cuDNN/PyTorch)
+            self.launches += 1 + det.launches_per_batch   # letterbox + epilogues/nms/pack of the (graph-replayed) batch; convolutions are cuDNN
             self.s_trk.wait_event(done)   # tracker batch k depends on detector batch k (true data dependency when own=True)
             with torch.cuda.stream(self.s_trk):
                 offs = t_offs[f0:f1 + 1].unsqueeze(0)
