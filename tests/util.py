@@ -13,6 +13,39 @@ def load_golden(name):
                 tracker=str(g["tracker"]), dets_sha=bytes(g["dets_sha"].tobytes()))
 
 
+def load_bpbreid_golden(name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    return dict(rows=g["rows"], frames=g["frames"], gen=ast.literal_eval(str(g["gen"])), hyper=ast.literal_eval(str(g["hyper"])))
+
+
+BPB_KEYS = ("ema_alpha", "mc_lambda", "max_dist", "max_iou_distance", "max_age", "n_init", "min_bbox_confidence",
+            "max_kalman_prediction_without_update")
+
+
+def assert_bpbreid_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1e-6, dist_tol=1e-5, allow_relabel=False):
+    """BPBReID rows [track_id, kf_ltwh(4), pred_kf_ltwh(4), matched code, matched dist, hits, age, det_id]: integer columns
+    bit-exact (track ids up to a consistent relabelling when allow_relabel, see assert_rows_match), boxes / distances within
+    tolerance, NaN pattern (births have no predicted box and no match) identical."""
+    assert rows.shape == ref_rows.shape, (rows.shape, ref_rows.shape)
+    ka, kb = np.lexsort((rows[:, 13], frames)), np.lexsort((ref_rows[:, 13], ref_frames))
+    a, b = rows[ka], ref_rows[kb]
+    assert np.array_equal(frames[ka], ref_frames[kb])
+    for c, what in ((13, "det ids"), (9, "matched_with stage"), (11, "hits"), (12, "age")):
+        assert np.array_equal(a[:, c], b[:, c]), what + " differ"
+    if allow_relabel and not np.array_equal(a[:, 0], b[:, 0]):
+        fwd, bwd = {}, {}
+        for x, y in zip(a[:, 0], b[:, 0]):
+            assert fwd.setdefault(x, y) == y and bwd.setdefault(y, x) == x, "tracks differ beyond a relabelling"
+    else:
+        assert np.array_equal(a[:, 0], b[:, 0]), "track ids differ"
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    err = np.nanmax(np.abs(a[:, 1:9] - b[:, 1:9])) if len(a) else 0.0
+    derr = np.nanmax(np.abs(a[:, 10] - b[:, 10])) if np.isfinite(a[:, 10]).any() else 0.0
+    assert err <= box_tol, f"box error {err}"
+    assert derr <= dist_tol, f"matched distance error {derr}"
+    return err, derr
+
+
 def assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1e-6, allow_relabel=False):
     """Integer outputs (frame, track id, det id, class) bit-exact; boxes/scores within tolerance.
     Rows are compared as sets per frame keyed by det id (the wrappers index results by det id).
