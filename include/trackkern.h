@@ -198,6 +198,42 @@ int tk_strongsort_run(void* handle, const double* dets, const float* features, c
 int tk_strongsort_status(void* handle, int* status_host, void* stream);
 int tk_strongsort_destroy(void* handle);
 
+/* ---- BPBReID-StrongSORT: part-based appearance, visibility-aware EMA ------------------------------------------
+ * Replaces bpbreid_strong_sort.StrongSORT.update driven once per frame by
+ * /root/reference/tracklab/wrappers/track/bpbreid_strong_sort_api.py:73-118
+ * (/root/reference/plugins/track/bpbreid_strong_sort/strong_sort.py:53-141, sort/tracker.py:123-167,242-333) for
+ * matching_strategy "strong_sort_matching" + motion_criterium "iou".
+ *   dets        float64 [N,7] rows [l, t, w, h, bbox_conf, class, det id]   (ltwh, as the wrapper stacks bbox_ltwh)
+ *   features    float32 [N, n_parts, feature_dim] (feature_dim a multiple of 4, base 16-byte aligned);
+ *   visibility  float32 [N, n_parts] (booleans as 0/1)
+ *   cap_tracks  may be far larger than cap_dets (<= 256): with n_init 0 / max_age 300 every false positive is a
+ *               confirmed track for 300 frames; only tracks that pass the Mahalanobis gate enter the assignment.
+ *   out_rows    float64 [.,14] = [track_id, track_bbox_kf_ltwh(4), track_bbox_pred_kf_ltwh(4) (NaN at birth),
+ *               matched_with stage (0 none, 1 'R', 2 'S'), matched distance (NaN when none), hits, age, det id];
+ *               only confirmed tracks updated in the frame are emitted (time_since_update 0, state 'c').
+ * The per-detection `costs` visualisation dictionaries (sort/tracker.py:365-407) are not produced.
+ */
+typedef struct tk_bpbreid_params {
+    double max_dist;            /* 0.5   */
+    double max_iou_distance;    /* 0.8   */
+    double mc_lambda;           /* 0.995 */
+    double ema_alpha;           /* 0.9   */
+    double min_bbox_confidence; /* 0.0   */
+    int max_age;                /* 300   */
+    int n_init;                 /* 0     */
+    int max_kalman_prediction_without_update; /* 7 */
+    int n_parts;
+    int feature_dim;
+    int ctas_per_video;         /* 0 = default */
+} tk_bpbreid_params;
+
+int tk_bpbreid_create(const tk_bpbreid_params* p, int n_seq, int cap_tracks, int cap_dets, void** handle);
+int tk_bpbreid_reset(void* handle, int keep_id_counter, void* stream);
+int tk_bpbreid_run(void* handle, const double* dets, const float* features, const float* visibility, const int* offsets, int n_frames,
+                   double* out_rows, const int* out_start, int* out_frame_count, int* out_count, int out_capacity_rows, void* stream);
+int tk_bpbreid_status(void* handle, int* status_host, void* stream);
+int tk_bpbreid_destroy(void* handle);
+
 /* ---- Stateless batched cost matrices + assignment (building blocks; stress sweep of BASELINE configs[4]) ------
  * All tensors device, row-major, `n_problems` independent problems stacked on the leading axis.
  *   tk_iou_matrix   a [B,N,4], b [B,M,4] float64 x1y1x2y2 -> out [B,N,M]; variant TK_ASSO_*

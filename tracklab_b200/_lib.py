@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libtrackkern.so")
 
 TK_ERRORS = {-1: "TK_ERR_ARG", -2: "TK_ERR_CUDA", -3: "TK_ERR_CAPACITY", -4: "TK_ERR_INFEASIBLE"}
 DEV_STATUS = {1: "track capacity overflow", 2: "detections-per-frame capacity overflow",
-              4: "assignment infeasible", 8: "output capacity overflow", 16: "non-PD innovation covariance"}
+              4: "assignment infeasible", 8: "output capacity overflow", 16: "non-PD innovation covariance",
+              32: "assignment-side capacity overflow", 64: "undefined appearance cost (no commonly visible part)"}
 
 
 class TrackKernError(RuntimeError):
@@ -38,6 +39,13 @@ class StrongsortParams(ctypes.Structure):
                 ("n_init", ctypes.c_int), ("nn_budget", ctypes.c_int), ("max_unmatched_preds", ctypes.c_int),
                 ("feature_dim", ctypes.c_int), ("image_width", ctypes.c_int), ("image_height", ctypes.c_int),
                 ("ctas_per_video", ctypes.c_int)]
+
+
+class BpbreidParams(ctypes.Structure):
+    _fields_ = [("max_dist", ctypes.c_double), ("max_iou_distance", ctypes.c_double), ("mc_lambda", ctypes.c_double),
+                ("ema_alpha", ctypes.c_double), ("min_bbox_confidence", ctypes.c_double), ("max_age", ctypes.c_int),
+                ("n_init", ctypes.c_int), ("max_kalman_prediction_without_update", ctypes.c_int), ("n_parts", ctypes.c_int),
+                ("feature_dim", ctypes.c_int), ("ctas_per_video", ctypes.c_int)]
 
 
 ASSO_CODES = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3}
@@ -77,6 +85,11 @@ def _declare(lib):
         "tk_strongsort_run": ([vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp], ci),
         "tk_strongsort_status": ([vp, P(ci), vp], ci),
         "tk_strongsort_destroy": ([vp], ci),
+        "tk_bpbreid_create": ([P(BpbreidParams), ci, ci, ci, P(vp)], ci),
+        "tk_bpbreid_reset": ([vp, ci, vp], ci),
+        "tk_bpbreid_run": ([vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp], ci),
+        "tk_bpbreid_status": ([vp, P(ci), vp], ci),
+        "tk_bpbreid_destroy": ([vp], ci),
     }
     for name, (args, res) in sig.items():
         fn = getattr(lib, name)

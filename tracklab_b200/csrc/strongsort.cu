@@ -81,25 +81,6 @@ __host__ __device__ inline SsDev ss_carve(char* base, int cap, int capd, int bud
     return d;
 }
 
-// sense-reversing barrier over the CTAs of one video group (all co-resident: cooperative launch)
-__device__ void group_barrier(unsigned* bar, int n) {
-    __syncthreads();
-    if (n > 1 && threadIdx.x == 0) {
-        volatile unsigned* gen = bar + 1;
-        const unsigned g = *gen;
-        __threadfence();
-        if (atomicAdd(bar, 1u) == (unsigned)(n - 1)) {
-            bar[0] = 0;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            while (*gen == g) { __nanosleep(64); }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
 // float32 L2 norm of a length-E vector by one warp (np.linalg.norm on float32), result in every lane
 __device__ __forceinline__ float warp_norm(const float* x, int E) {
     float s = 0.0f;

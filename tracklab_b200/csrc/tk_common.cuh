@@ -23,6 +23,8 @@ void tk_set_last_cuda_error(int e);
 #define TK_DEV_LAP_INFEASIBLE 4
 #define TK_DEV_OVERFLOW_OUT 8
 #define TK_DEV_BAD_CHOLESKY 16
+#define TK_DEV_OVERFLOW_ASSIGN 32   /* more live rows / candidates than the assignment side capacity */
+#define TK_DEV_NAN_COST 64          /* appearance cost undefined (no commonly visible part) */
 
 namespace tk {
 
@@ -75,6 +77,25 @@ __device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
+}
+
+// sense-reversing barrier over the CTAs of one video group (all co-resident: cooperative launch)
+__device__ __forceinline__ void group_barrier(unsigned* bar, int n) {
+    __syncthreads();
+    if (n > 1 && threadIdx.x == 0) {
+        volatile unsigned* gen = bar + 1;
+        const unsigned g = *gen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == (unsigned)(n - 1)) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == g) { __nanosleep(64); }
+        }
+        __threadfence();
+    }
+    __syncthreads();
 }
 
 }  // namespace tk

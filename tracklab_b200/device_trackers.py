@@ -165,6 +165,53 @@ class StrongSortDevice(_VideoTrackerDevice):
         return out_rows, out_fc, out_count
 
 
+class BpbreidStrongSortDevice(_VideoTrackerDevice):
+    """BPBReID-StrongSORT association for ``n_seq`` videos (C ABI: tk_bpbreid_*): part-based features + visibility scores.
+
+    Mirrors bpbreid_strong_sort.StrongSORT(**cfg).update for ``matching_strategy="strong_sort_matching"``,
+    ``motion_criterium="iou"`` (/root/reference/plugins/track/bpbreid_strong_sort/strong_sort.py:11-141,
+    /root/reference/tracklab/configs/modules/track/bpbreid_strong_sort.yaml)."""
+
+    _prefix = "bpbreid"
+    COLS = 14
+
+    def __init__(self, n_parts, feature_dim, ema_alpha=0.9, mc_lambda=0.995, max_dist=0.5, max_iou_distance=0.8, max_age=300,
+                 n_init=0, min_bbox_confidence=0.0, max_kalman_prediction_without_update=7, ctas_per_video=8, n_seq=1,
+                 cap_tracks=1024, cap_dets=128, device="cuda:0"):
+        self.n_parts, self.feature_dim = n_parts, feature_dim
+        self._create(_lib.BpbreidParams(max_dist, max_iou_distance, mc_lambda, ema_alpha, min_bbox_confidence, max_age, n_init,
+                                        max_kalman_prediction_without_update, n_parts, feature_dim, ctas_per_video),
+                     n_seq, cap_tracks, cap_dets, device)
+
+    def run(self, dets: torch.Tensor, offsets: torch.Tensor, features: torch.Tensor, visibility: torch.Tensor,
+            out_rows: torch.Tensor | None = None, out_start: torch.Tensor | None = None, out_count: torch.Tensor | None = None):
+        """dets float64 [N,7] = [l,t,w,h,conf,cls,det id]; features float32 [N,K,E]; visibility float32 [N,K].
+        At most one row per detection is produced."""
+        for t, n in ((dets, "dets"), (offsets, "offsets"), (features, "features"), (visibility, "visibility")):
+            _require_cuda(t, n)
+            assert t.is_contiguous(), n
+        assert dets.dtype == torch.float64 and features.dtype == torch.float32 and visibility.dtype == torch.float32
+        assert features.shape == (dets.shape[0], self.n_parts, self.feature_dim) and visibility.shape == (dets.shape[0], self.n_parts)
+        assert offsets.dtype == torch.int32 and offsets.shape[0] == self.n_seq
+        n_frames = offsets.shape[1] - 1
+        cap_rows = max(1, dets.shape[0])
+        if out_rows is None:
+            assert self.n_seq == 1, "pass out_rows/out_start for several videos"
+            out_rows = torch.empty((cap_rows, self.COLS), dtype=torch.float64, device=dets.device)
+        else:
+            cap_rows = out_rows.shape[0] // self.n_seq
+        if out_start is None:
+            out_start = torch.zeros(self.n_seq, dtype=torch.int32, device=dets.device)
+        if out_count is None:
+            out_count = torch.zeros(self.n_seq, dtype=torch.int32, device=dets.device)
+        out_fc = torch.empty((self.n_seq, n_frames), dtype=torch.int32, device=dets.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._fn["run"](self.handle, dets.data_ptr(), features.data_ptr(), visibility.data_ptr(), offsets.data_ptr(),
+                                       n_frames, out_rows.data_ptr(), out_start.data_ptr(), out_fc.data_ptr(), out_count.data_ptr(),
+                                       cap_rows, _stream_ptr()), "tk_bpbreid_run")
+        return out_rows, out_fc, out_count
+
+
 def rows_to_frames(out_rows: torch.Tensor, out_fc: torch.Tensor, out_start: torch.Tensor, seq: int = 0):
     """Host helper: split the rows of video ``seq`` per frame -> (rows float64[R,8], frame int32[R])."""
     fc = out_fc[seq].cpu().numpy()
