@@ -52,3 +52,37 @@ def test_modules_through_engine_match_reference_engine(name, frames_per_batch):
     got = np.stack([np.asarray(x, dtype=np.float64) for x in out["track_bbox_ltwh"][has]])
     assert np.abs(got - g["track_bbox_ltwh"][ref_has]).max() < 1e-6
     assert np.array_equal(out["track_bbox_conf"].to_numpy(dtype=float, na_value=np.nan)[has], g["track_bbox_conf"][ref_has])
+
+
+def test_bpbreid_module_through_engine_matches_reference_plugin():
+    """BPBReIDStrongSORT drop-in (visibility as booleans, like the BPBReID ReID module emits) vs the golden of the
+    unmodified reference plugin: same detection -> track partition, stages, hits and ages; float64 boxes within 1e-6."""
+    from tests.util import load_bpbreid_golden
+    from tracklab_b200 import modules
+    from tracklab_b200.engine_mirror import OfflineEngineMirror
+    g = load_bpbreid_golden("bpbreid_yaml_s6000")
+    video = make_video(**g["gen"])
+    vmd, imd, det = _tracking_frames([video])
+    det["embeddings"] = list(video.embeddings)
+    det["visibility_scores"] = list(video.visibility.astype(bool))
+    cfg = types.SimpleNamespace(ecc=False, **g["hyper"])
+    mod = modules.BPBReIDStrongSORT(cfg, "cuda:0")
+    assert mod.level == "image" and mod.name == "BPBReIDStrongSORT"
+    out = OfflineEngineMirror([mod], vmd, imd, det).track_dataset().sort_index()
+    ref = g["rows"]
+    ref = ref[np.argsort(ref[:, 13])]
+    has = out["track_id"].notna().to_numpy()
+    assert np.array_equal(out.index.to_numpy()[has], ref[:, 13].astype(int))
+    tid = out["track_id"].to_numpy(dtype=float, na_value=np.nan)[has]
+    fwd, bwd = {}, {}
+    for x, y in zip(tid, ref[:, 0]):   # one consistent relabelling (solver-tie caveat, tests/util.py)
+        assert fwd.setdefault(x, y) == y and bwd.setdefault(y, x) == x
+    sel = out[has]
+    assert np.array_equal(sel["hits"].to_numpy(dtype=float), ref[:, 11]) and np.array_equal(sel["age"].to_numpy(dtype=float), ref[:, 12])
+    assert (sel["state"] == "c").all() and (sel["time_since_update"] == 0).all()
+    code = np.array([(1 if m[0] == "R" else 2) if isinstance(m, tuple) else 0 for m in sel["matched_with"]])   # None -> NaN after the merge
+    assert np.array_equal(code, ref[:, 9].astype(int))
+    box = np.stack([np.asarray(b, dtype=np.float64) for b in sel["track_bbox_kf_ltwh"]])
+    assert np.abs(box - ref[:, 1:5]).max() < 1e-6
+    born = np.isnan(ref[:, 5])
+    assert all((not isinstance(p, np.ndarray)) == b for p, b in zip(sel["track_bbox_pred_kf_ltwh"], born))

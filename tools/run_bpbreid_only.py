@@ -19,3 +19,14 @@ for _ in range(3):
     e0.record(); rows, fc, cnt = trk.run(dets, offs, feats, vis); e1.record(); torch.cuda.synchronize()
     print(f"bpbreid F={F} E={E} K={K} ctas={ncta}: {e0.elapsed_time(e1) * 1e3 / F:.1f} us/frame, rows {int(cnt.item())}")
 trk.check_status()
+import ctypes
+lib = trk.lib
+if hasattr(lib, "tk_debug_bpbreid_phases"):
+    buf = (ctypes.c_ulonglong * 64)()
+    lib.tk_debug_bpbreid_phases(buf, 1)
+    trk.reset(); trk.run(dets, offs, feats, vis); torch.cuda.synchronize()
+    lib.tk_debug_bpbreid_phases(buf, 0)
+    names = ["compact", "predict+xyah", "cache", "rect", "B1", "P1", "B2", "fuse+live", "costA", "lapA", "pairsA+cand", "costB", "lapB",
+             "kf_update", "miss+birth", "prune+out", "B3"]
+    tot = sum(buf[:17])
+    print("master phases (cycles/frame):", ", ".join(f"{n} {buf[i] / F:.0f}" for i, n in enumerate(names)), f"| total {tot / F:.0f}")

@@ -35,11 +35,19 @@ namespace {
 
 using namespace tk;
 
+// Optional per-phase cycle accounting of the master CTA (build with -DTK_PHASE_PROF), read with tk_debug_bpbreid_phases().
+#ifdef TK_PHASE_PROF
+__device__ unsigned long long g_bp_prof[64];
+#define PH(k) do { if (master && threadIdx.x == 0) { const long long _t = clock64(); g_bp_prof[k] += (unsigned long long)(_t - ph_t0); ph_t0 = _t; } } while (0)
+#else
+#define PH(k) do { } while (0)
+#endif
+
 constexpr int BP_THREADS = 256;
 enum : unsigned char { BP_FREE = 0, BP_TENTATIVE = 1, BP_CONFIRMED = 2, BP_DELETED = 3 };
-constexpr double W_POS = 1.0 / 20, W_VEL = 1.0 / 160, INFTY_COST = 1e5, CHI2_4 = 9.4877;
+constexpr double W_POS = 1.0 / 20, W_VEL = 1.0 / 160, CHI2_4 = 9.4877;
 constexpr int BP_COLS = 14;
-constexpr int BP_NARR = 35;
+constexpr int BP_NARR = 36;
 
 struct BpParams {
     double max_dist, max_iou_dist, mc_lambda, min_conf;
@@ -54,7 +62,7 @@ struct BpDev {
     int *hits, *birth, *last, *track_id, *list, *list_tmp, *free_list, *conf_list, *det_rows, *ppack, *cpack;
     int *ema_slot, *ema_row, *born_slot, *born_row;   // feature updates of the frame, published for the worker CTAs
     unsigned char *state, *has_pred, *m_code;
-    float *feat, *featn, *dfeatn, *vis, *pa;   // featn / dfeatn: L2-normalised parts of the tracks / of the frame's detections
+    float *feat, *featn, *dfeatn, *vis, *dvis, *pa;   // featn / dfeatn: L2-normalised parts of the tracks / of the frame's detections
 };
 
 __host__ __device__ inline size_t bp_al(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -70,7 +78,7 @@ __host__ __device__ inline void bp_layout(int cap, int capd, int K, int E, F&& f
     for (int k = 0; k < 8; ++k) f(i++, (size_t)cap * 4);                                               // hits .. conf_list
     f(i++, (size_t)capd * 4); f(i++, np * 4); f(i++, np * 4);                                          // det_rows ppack cpack
     for (int k = 0; k < 3; ++k) f(i++, (size_t)cap);                                                   // state has_pred m_code
-    f(i++, (size_t)cap * K * E * 4); f(i++, (size_t)cap * K * E * 4); f(i++, (size_t)capd * K * E * 4); f(i++, (size_t)cap * K * 4);   // feat featn dfeatn vis
+    f(i++, (size_t)cap * K * E * 4); f(i++, (size_t)cap * K * E * 4); f(i++, (size_t)capd * K * E * 4); f(i++, (size_t)cap * K * 4); f(i++, (size_t)capd * K * 4);   // feat featn dfeatn vis dvis
     f(i++, np * 4);                                                                                    // pa
     for (int k = 0; k < 4; ++k) f(i++, (size_t)capd * 4);                                              // ema_slot ema_row born_slot born_row
 }
@@ -88,10 +96,16 @@ __host__ __device__ inline BpDev bp_carve(char* base, int cap, int capd, int K, 
         (void**)&d.pred, (void**)&d.pg, (void**)&d.pf, (void**)&d.hits, (void**)&d.birth, (void**)&d.last, (void**)&d.track_id,
         (void**)&d.list, (void**)&d.list_tmp, (void**)&d.free_list, (void**)&d.conf_list, (void**)&d.det_rows, (void**)&d.ppack,
         (void**)&d.cpack, (void**)&d.state, (void**)&d.has_pred, (void**)&d.m_code, (void**)&d.feat, (void**)&d.featn,
-        (void**)&d.dfeatn, (void**)&d.vis, (void**)&d.pa, (void**)&d.ema_slot, (void**)&d.ema_row, (void**)&d.born_slot, (void**)&d.born_row};
+        (void**)&d.dfeatn, (void**)&d.vis, (void**)&d.dvis, (void**)&d.pa, (void**)&d.ema_slot, (void**)&d.ema_row, (void**)&d.born_slot, (void**)&d.born_row};
     char* p = base;
     bp_layout(cap, capd, K, E, [&](int i, size_t b) { *slots[i] = (void*)p; p += bp_al(b); });
     return d;
+}
+
+// float32 copy of a gate rectangle, widened so that the float test can only pass more pairs than the double one
+// (coordinates up to 16k pixels: three roundings of at most 2^-9 each)
+__device__ __forceinline__ float4 bp_gate_f32(const double* g) {
+    return make_float4((float)g[0], (float)g[1], __double2float_ru(g[2]) + 0.01f, __double2float_ru(g[3]) + 0.01f);
 }
 
 __device__ __forceinline__ float warp_sum(float s) {
@@ -198,7 +212,7 @@ __device__ void bp_feature_updates(const BpDev& S, const BpParams& prm, const fl
 // F.normalize of the frame's detections (nn_matching.py:121-122) into S.dfeatn. The calling CTA filters the frame itself
 // (filter_detections, strong_sort.py:139-143) into `rows` (shared memory) so that it does not depend on the master.
 __device__ void bp_det_normalise(const BpDev& S, const BpParams& prm, const double* __restrict__ D, int nraw, const float* __restrict__ feats,
-                                 int r0, int* rows, int* nd_smem, int wg, int wn) {
+                                 const float* __restrict__ viss, int r0, int* rows, int* nd_smem, int wg, int wn) {
     if (warp_id() == 0) {
         const int nd_ = warp_compact(nraw, 0, [&](int i) { return D[i * 7 + 4] > prm.min_conf; }, [&](int i, int p) { rows[p] = i; });
         if (lane_id() == 0) *nd_smem = nd_;
@@ -210,6 +224,7 @@ __device__ void bp_det_normalise(const BpDev& S, const BpParams& prm, const doub
         const float4* fv = reinterpret_cast<const float4*>(feats + (size_t)(r0 + rows[d]) * KE + (size_t)k * prm.E);
         float4* dn = reinterpret_cast<float4*>(S.dfeatn + (size_t)d * KE + (size_t)k * prm.E);
         const float nf = warp_part_norm(fv, E4);
+        if (lane_id() == 0) S.dvis[d * K + k] = viss[(size_t)(r0 + rows[d]) * K + k];
 #pragma unroll 4
         for (int e = lane_id(); e < E4; e += 32) {
             const float4 v = fv[e];
@@ -238,10 +253,12 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
     double* lap_u = (double*)take(sizeof(double) * side);
     double* d_z = (double*)take(sizeof(double) * 4 * capd);
     double* d_ltwh = (double*)take(sizeof(double) * 4 * capd);
-    double* gate_m = (double*)take(sizeof(double) * 4 * cap);    // mirror of S.gate
+    float4* gate_f = (float4*)take(sizeof(float4) * cap);        // conservative float32 gate rectangles (cx, cy, rx, ry) per slot
+    float2* dz_f = (float2*)take(sizeof(float2) * capd);         // float32 centres of the frame's detections
     int* list_m = (int*)take(sizeof(int) * cap);                  // mirror of S.list
     int* last_m = (int*)take(sizeof(int) * cap);                  // mirror of S.last (tick of the last update)
     int* scr = (int*)take(sizeof(int) * cap);                     // filters to predict / row of a confirmed position
+    int* conf_m = (int*)take(sizeof(int) * cap);                  // mirror of S.conf_list (slots of the confirmed tracks, track order)
     int* match_a = (int*)take(sizeof(int) * side);
     int* match_b = (int*)take(sizeof(int) * side);
     int* col4row = (int*)take(sizeof(int) * side);
@@ -270,7 +287,7 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
         for (int k = tid; k < nt; k += BP_THREADS) list_m[k] = S.list[k];
         for (int s = tid; s < cap; s += BP_THREADS) {
             last_m[s] = S.last[s]; state_m[s] = S.state[s];
-            for (int i = 0; i < 4; ++i) gate_m[4 * s + i] = S.gate[4 * s + i];
+            gate_f[s] = bp_gate_f32(S.gate + 4 * s);
         }
         __syncthreads();
     }
@@ -279,6 +296,9 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
     const bool worker = !master || ncta == 1;
     const int wg = (ncta == 1 ? 0 : cta - 1) * (BP_THREADS / 32) + warp_id(), wn = (ncta == 1 ? 1 : ncta - 1) * (BP_THREADS / 32);
     bool pending = false;   // feature updates of the last processed frame still to be applied
+#ifdef TK_PHASE_PROF
+    long long ph_t0 = clock64();
+#endif
 
     for (int f = 0; f < n_frames; ++f) {
         const int r0 = offsets[seq * F1 + f], r1 = offsets[seq * F1 + f + 1];
@@ -290,7 +310,7 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
 
         if (!master) {   // workers: previous frame's feature updates, this frame's detection norms (overlaps the master's predict + gate)
             if (pending) bp_feature_updates(S, prm, feats, viss, wg, wn);
-            bp_det_normalise(S, prm, D, nraw, feats, r0, tmp_d, &sh->nd_w, wg, wn);
+            bp_det_normalise(S, prm, D, nraw, feats, viss, r0, tmp_d, &sh->nd_w, wg, wn);
             __threadfence();
         }
 
@@ -306,11 +326,12 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
                 if (lane_id() == 0) { sh->nd = nd_; S.hdr[6] = nd_; sh->ncp = 0; sh->nap = 0; }
             } else if (warp_id() == 2) {
                 const int nc = warp_compact(nt, 0, [&](int k) { return state_m[list_m[k]] == BP_CONFIRMED; },
-                                            [&](int k, int p) { S.conf_list[p] = list_m[k]; });
+                                            [&](int k, int p) { S.conf_list[p] = list_m[k]; conf_m[p] = list_m[k]; });
                 if (lane_id() == 0) sh->nconf = nc;
             }
             __syncthreads();
             const int nkf = sh->nkf, nd = sh->nd, nconf = sh->nconf;
+            PH(0);
             for (int base = 0; base < nkf; base += BP_THREADS / 8) {   // kalman_filter.py:74-104
                 const int k = base + (tid >> 3), j = tid & 7;
                 const bool act = k < nkf;
@@ -327,88 +348,147 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
                 double* z = d_z + 4 * i;
                 z[0] = dr[0] + dr[2] / 2; z[1] = dr[1] + dr[3] / 2; z[2] = dr[2] / dr[3]; z[3] = dr[3];
                 for (int c = 0; c < 4; ++c) S.dz[4 * i + c] = z[c];
+                dz_f[i] = make_float2((float)z[0], (float)z[1]);
             }
             if (ncta == 1) {
                 if (pending) bp_feature_updates(S, prm, feats, viss, wg, wn);
-                bp_det_normalise(S, prm, D, nraw, feats, r0, tmp_d, &sh->nd_w, wg, wn);
+                bp_det_normalise(S, prm, D, nraw, feats, viss, r0, tmp_d, &sh->nd_w, wg, wn);
             }
             __syncthreads();
+            PH(1);
             for (int k = tid; k < nkf; k += BP_THREADS) {   // gating cache of the filters that moved
                 const int s = scr[k];
                 double g[4];
                 if (!bp_track_cache(S.mean + (size_t)s * 8, S.cov + (size_t)s * 64, g, S.chol + (size_t)s * 24)) atomicOr(status, TK_DEV_BAD_CHOLESKY);
-                for (int i = 0; i < 4; ++i) { gate_m[4 * s + i] = g[i]; S.gate[4 * s + i] = g[i]; }
+                for (int i = 0; i < 4; ++i) S.gate[4 * s + i] = g[i];
+                gate_f[s] = bp_gate_f32(g);
             }
             for (int k = tid; k < cap; k += BP_THREADS) { t_flag[k] = 0; t_live[k] = 0; }
             __syncthreads();
-            // rectangle test for every (confirmed track, detection): candidates of the exact gate
-            if (nd > 0)
-                for (int r = tid; r < nconf; r += BP_THREADS) {
-                    const double* g = gate_m + 4 * S.conf_list[r];
-                    const double cx = g[0], cy = g[1], rx = g[2], ry = g[3];
-                    for (int d = 0; d < nd; ++d) {
-                        if (fabs(d_z[4 * d] - cx) <= rx && fabs(d_z[4 * d + 1] - cy) <= ry) S.cpack[atomicAdd(&sh->ncp, 1)] = (r << 8) | d;
-                    }
-                }
+            PH(2);
+            // Gate (linear_assignment.py:166-175), first step: rectangle test of every (confirmed track, detection) in float32
+            // with a conservative margin, flattened over the CTA. Count, block scan, write: no atomics, deterministic order.
+            // The exact test of the hits is done by all CTAs after the barrier.
+            {
+                const int total = nd > 0 ? nconf * nd : 0;
+                auto hit_at = [&](int r, int d, int& pk) {
+                    const int slot = conf_m[r];
+                    const float4 g = gate_f[slot];
+                    const float2 z = dz_f[d];
+                    pk = (slot << 8) | d;
+                    return fabsf(z.x - g.x) <= g.z && fabsf(z.y - g.y) <= g.w;
+                };
+                const int per = (total + BP_THREADS - 1) / BP_THREADS, e_lo = min(total, tid * per), e_hi = min(total, e_lo + per);
+                const int r_lo = nd > 0 ? e_lo / nd : 0, d_lo = e_lo - r_lo * nd;
+                int cnt = 0, pk;
+                for (int e = e_lo, r = r_lo, d = d_lo; e < e_hi; ++e) { cnt += hit_at(r, d, pk) ? 1 : 0; if (++d == nd) { d = 0; ++r; } }
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane_id() >= o) incl += v; }
+                if (lane_id() == 31) match_a[warp_id()] = incl;
+                __syncthreads();
+                int base = incl - cnt;
+                for (int w = 0; w < warp_id(); ++w) base += match_a[w];
+                if (tid == BP_THREADS - 1) sh->ncp = base + cnt;
+                for (int e = e_lo, r = r_lo, d = d_lo; e < e_hi; ++e) { if (hit_at(r, d, pk)) S.cpack[base++] = pk; if (++d == nd) { d = 0; ++r; } }
+            }
             __syncthreads();
-            if (tid == 0) S.hdr[7] = sh->ncp;
+            if (tid == 0) { S.hdr[7] = sh->ncp; S.hdr[10] = 0; }
             __threadfence();
         }
+        PH(3);
         group_barrier(S.bar, ncta);
+        PH(4);
 
-        // ================= all CTAs: exact gate + part distance of the candidates =================
-        // A warp takes 8 candidates at a time: lanes 0-7 evaluate the Mahalanobis gate from the cached factor
-        // (linear_assignment.py:166-175, kalman_filter.py:168-227), then the whole warp walks the survivors' K x E normalised
-        // part embeddings (nn_matching.py:99-135): pg = gate distance (-1 when gated), pa = appearance distance.
+        // ================= all CTAs: exact gate of the hits + part distance of the survivors =================
+        // A warp takes 4 hits at a time (static interleave): lanes 0-3 evaluate the Mahalanobis distance from the cached
+        // factor (kalman_filter.py:168-227); survivors get a slot in the pair list (ppack, pg) and the whole warp walks their
+        // K x E L2-normalised part embeddings (nn_matching.py:99-135). The part loop is software-pipelined: the next part's
+        // 2 x 4 float4 per lane are in flight while the current one is reduced (one warp on L2-resident rows is latency-bound).
         {
             const int ncp = S.hdr[7];
-            const int gw = cta * (BP_THREADS / 32) + warp_id(), nw = ncta * (BP_THREADS / 32), lane = lane_id();
-            const int E4 = E >> 2;
-            for (int ch = gw; ch * 8 < ncp; ch += nw) {
-                const int i = ch * 8 + lane;
-                int pk = 0;
+            const int gw = cta * (BP_THREADS / 32) + warp_id(), nw = ncta * (BP_THREADS / 32), lane = lane_id(), E4 = E >> 2;
+            for (int ch = gw; ch * 4 < ncp; ch += nw) {
+                const int hi = ch * 4 + lane;
+                int pk_l = 0;
+                double g_l = 0.0;
                 bool pass = false;
-                if (lane < 8 && i < ncp) {
-                    pk = S.cpack[i];
-                    const double* c = S.chol + (size_t)S.conf_list[pk >> 8] * 24;
-                    const double g = kf8_maha(c, c + 4, c + 20, S.dz + 4 * (pk & 255));
-                    pass = !(g > CHI2_4);
-                    S.pg[i] = pass ? g : -1.0;
+                if (lane < 4 && hi < ncp) {
+                    pk_l = S.cpack[hi];
+                    const double* c = S.chol + (size_t)(pk_l >> 8) * 24;
+                    g_l = kf8_maha(c, c + 4, c + 20, S.dz + 4 * (pk_l & 255));
+                    pass = !(g_l > CHI2_4);
                 }
                 unsigned todo = __ballot_sync(0xffffffffu, pass);
-                while (todo) {
+                if (todo == 0u) continue;
+                int q0 = 0;
+                if (lane == 0) q0 = atomicAdd(&S.hdr[10], __popc(todo));
+                q0 = __shfl_sync(0xffffffffu, q0, 0);
+                if (pass) { const int q = q0 + __popc(todo & ((1u << lane) - 1u)); S.ppack[q] = pk_l; S.pg[q] = g_l; }
+                for (int i = q0; todo; ++i) {
                     const int j = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const int q = __shfl_sync(0xffffffffu, pk, j);
-                    const int s = S.conf_list[q >> 8], d = q & 255;
-                    const size_t drow = (size_t)(r0 + S.det_rows[d]);
+                    const int pk = __shfl_sync(0xffffffffu, pk_l, j), s = pk >> 8, d = pk & 255;
+                    const float w_l = lane < K ? __fmul_rn(S.vis[s * K + lane], S.dvis[d * K + lane]) : 0.0f;   // lane k: weight of part k
+                    const float4* a = reinterpret_cast<const float4*>(S.featn + (size_t)s * KE);
+                    const float4* b = reinterpret_cast<const float4*>(S.dfeatn + (size_t)d * KE);
                     float num = 0.0f, den = 0.0f;
-                    for (int k = 0; k < K; ++k) {
-                        const float4* a = reinterpret_cast<const float4*>(S.featn + (size_t)s * KE + (size_t)k * E);
-                        const float4* b = reinterpret_cast<const float4*>(S.dfeatn + (size_t)d * KE + (size_t)k * E);
-                        float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
-#pragma unroll 4
-                        for (int e = lane; e < E4; e += 32) {
-                            const float4 av = a[e], bv = b[e];
-                            const float x0 = av.x - bv.x, x1 = av.y - bv.y, x2 = av.z - bv.z, x3 = av.w - bv.w;
-                            c0 = fmaf(x0, x0, c0); c1 = fmaf(x1, x1, c1); c2 = fmaf(x2, x2, c2); c3 = fmaf(x3, x3, c3);
-                        }
-                        const float acc = warp_sum((c0 + c1) + (c2 + c3));
-                        const float w = __fmul_rn(S.vis[s * K + k], viss[drow * K + k]);   // visibility-weighted mean over the parts
-                        num = __fadd_rn(num, __fmul_rn(sqrtf(acc), w));
+                    auto finish = [&](int k, float sq) {   // visibility-weighted mean over the parts, in part order
+                        const float w = __shfl_sync(0xffffffffu, w_l, k);
+                        num = __fadd_rn(num, __fmul_rn(sqrtf(warp_sum(sq)), w));
                         den = __fadd_rn(den, w);
+                    };
+                    if (E4 <= 128 && K <= 32) {
+                        float4 A0[4], B0[4], A1[4], B1[4];
+                        auto load = [&](int k, float4 (&A)[4], float4 (&B)[4]) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const int e = lane + 32 * t;
+                                if (e < E4) { A[t] = a[k * E4 + e]; B[t] = b[k * E4 + e]; }
+                                else { A[t] = make_float4(0.f, 0.f, 0.f, 0.f); B[t] = A[t]; }
+                            }
+                        };
+                        auto square = [&](const float4 (&A)[4], const float4 (&B)[4]) {
+                            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float x0 = A[t].x - B[t].x, x1 = A[t].y - B[t].y, x2 = A[t].z - B[t].z, x3 = A[t].w - B[t].w;
+                                c0 = fmaf(x0, x0, c0); c1 = fmaf(x1, x1, c1); c2 = fmaf(x2, x2, c2); c3 = fmaf(x3, x3, c3);
+                            }
+                            return (c0 + c1) + (c2 + c3);
+                        };
+                        load(0, A0, B0);
+                        for (int k = 0; k < K; k += 2) {
+                            if (k + 1 < K) load(k + 1, A1, B1);
+                            finish(k, square(A0, B0));
+                            if (k + 2 < K) load(k + 2, A0, B0);
+                            if (k + 1 < K) finish(k + 1, square(A1, B1));
+                        }
+                    } else {
+                        for (int k = 0; k < K; ++k) {
+                            float c0 = 0.0f, c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;
+#pragma unroll 4
+                            for (int e = lane; e < E4; e += 32) {
+                                const float4 av = a[k * E4 + e], bv = b[k * E4 + e];
+                                const float x0 = av.x - bv.x, x1 = av.y - bv.y, x2 = av.z - bv.z, x3 = av.w - bv.w;
+                                c0 = fmaf(x0, x0, c0); c1 = fmaf(x1, x1, c1); c2 = fmaf(x2, x2, c2); c3 = fmaf(x3, x3, c3);
+                            }
+                            finish(k, (c0 + c1) + (c2 + c3));
+                        }
                     }
-                    if (lane == 0) S.pa[ch * 8 + j] = __fdiv_rn(__fdiv_rn(num, den), 2.0f);   // nn_matching.py:133
+                    if (lane == 0) S.pa[i] = __fdiv_rn(__fdiv_rn(num, den), 2.0f);   // nn_matching.py:133
                 }
             }
             __threadfence();
         }
+        PH(5);
         group_barrier(S.bar, ncta);
+        PH(6);
         pending = true;
         if (!master) { group_barrier(S.bar, ncta); continue; }   // third barrier: the master has published the frame's feature updates
 
         // ================= master: fusion, assignments, updates =================
-        const int nd = sh->nd, nconf = sh->nconf, nt = S.hdr[1], nap = sh->ncp;   // candidate list; pg < 0 marks the gated ones
+        const int nd = sh->nd, nconf = sh->nconf, nt = S.hdr[1], nap = S.hdr[10];   // pairs that passed the gate
         if (nd == 0) {   // every detection filtered out: predict only, tracker.update is not called (strong_sort.py:88-89)
             if (tid == 0) { out_frame_count[seq * n_frames + f] = 0; S.hdr[8] = 0; S.hdr[9] = 0; }
             __threadfence();
@@ -417,20 +497,20 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
         }
         // ---- stage A: confirmed tracks x all detections (tracker.py:264-301, linear_assignment.py:132-175)
         for (int i = tid; i < nap; i += BP_THREADS) {
-            if (S.pg[i] < 0.0) { S.pf[i] = INFTY_COST; continue; }   // cost_matrix[row, gating_distance > threshold] = gated_cost
             const double a = (double)S.pa[i];
             if (!(a == a)) atomicOr(status, TK_DEV_NAN_COST);   // no commonly visible part: the reference's solver raises on NaN
             const double fused = __dadd_rn(__dmul_rn(prm.mc_lambda, a), __dmul_rn(1.0 - prm.mc_lambda, S.pg[i]));
             S.pf[i] = fused;
-            if (!(fused > prm.max_dist)) t_live[S.cpack[i] >> 8] = 1;
+            if (!(fused > prm.max_dist)) t_live[S.ppack[i] >> 8] = 1;   // by slot
         }
         __syncthreads();
         if (warp_id() == 0) {   // rows with at least one feasible entry; the others cannot be matched (cost max_dist + 1e-5 everywhere)
-            const int nl = warp_compact(nconf, 0, [&](int r) { return t_live[r] != 0; }, [&](int r, int p) { scr[r] = p; if (p < capl) live_rows[p] = r; });
+            const int nl = warp_compact(nconf, 0, [&](int r) { return t_live[conf_m[r]] != 0; }, [&](int r, int p) { const int s = conf_m[r]; scr[s] = p; if (p < capl) live_rows[p] = s; });
             if (lane_id() == 0) { sh->nlive = nl; if (nl > capl) atomicOr(status, TK_DEV_OVERFLOW_ASSIGN); }
         }
         __syncthreads();
         const int nlive = sh->nlive <= capl ? sh->nlive : 0;
+        PH(7);
         {
             const bool a_rows = nlive <= nd;
             const int ld = lap_pitch(a_rows ? nd : nlive);
@@ -442,10 +522,11 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
                 for (int i = tid; i < nap; i += BP_THREADS) {
                     const double fused = S.pf[i];
                     if (fused > prm.max_dist) continue;
-                    const int pk = S.cpack[i], r = scr[pk >> 8], d = pk & 255;
+                    const int pk = S.ppack[i], r = scr[pk >> 8], d = pk & 255;
                     if (a_rows) cost[(size_t)r * ld + d] = fused - L_app; else cost[(size_t)d * ld + r] = fused - L_app;
                 }
             __syncthreads();
+            PH(8);
             if (nlive > 0) {
                 const int nr = a_rows ? nlive : nd, nc = a_rows ? nd : nlive;
                 if (!lap_solve_cta(cost, ld, nr, nc, true, lap_u, col4row, row4col, path, &sh->lap_ok)) { if (tid == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); }
@@ -458,24 +539,26 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
         }
         if (warp_id() == 0) {
             const int np_ = warp_compact(nlive, 0, [&](int i) { return match_a[i] >= 0; },
-                                         [&](int i, int p) { const int s = S.conf_list[live_rows[i]]; pair_t[p] = s; pair_d[p] = match_a[i]; t_flag[s] = 1; S.m_code[s] = 1; });
+                                         [&](int i, int p) { const int s = live_rows[i]; pair_t[p] = s; pair_d[p] = match_a[i]; t_flag[s] = 1; S.m_code[s] = 1; });
             if (lane_id() == 0) sh->npairs = np_;
         }
         if (nlive > 0)
             for (int i = tid; i < nap; i += BP_THREADS) {   // ("R", gated distance of the matched pair) tracker.py:409-421
-                const int pk = S.cpack[i], r = pk >> 8;
-                if (t_live[r] && !(S.pf[i] > prm.max_dist) && match_a[scr[r]] == (pk & 255)) S.m_dist[S.conf_list[r]] = S.pf[i];
+                const int pk = S.ppack[i], sl = pk >> 8;
+                if (t_live[sl] && !(S.pf[i] > prm.max_dist) && match_a[scr[sl]] == (pk & 255)) S.m_dist[sl] = S.pf[i];
             }
         __syncthreads();
+        PH(9);
         // stage-B candidates: unconfirmed + unmatched confirmed with tsu == 1 (tracker.py:303-309)
         if (warp_id() == 0) {
             int nc = warp_compact(nt, 0, [&](int k) { return state_m[list_m[k]] != BP_CONFIRMED; }, [&](int k, int p) { if (p < capl) cand[p] = list_m[k]; });
-            nc = warp_compact(nconf, nc, [&](int r) { const int s = S.conf_list[r]; return !t_flag[s] && tick - last_m[s] == 1; },
-                              [&](int r, int p) { if (p < capl) cand[p] = S.conf_list[r]; });
+            nc = warp_compact(nconf, nc, [&](int r) { const int s = conf_m[r]; return !t_flag[s] && tick - last_m[s] == 1; },
+                              [&](int r, int p) { if (p < capl) cand[p] = conf_m[r]; });
             const int nu = warp_compact(nd, 0, [&](int d) { return match_b[d] < 0; }, [&](int d, int p) { un_d[p] = d; });
             if (lane_id() == 0) { if (nc > capl) { atomicOr(status, TK_DEV_OVERFLOW_ASSIGN); nc = 0; } sh->ncand = nc; sh->nud = nu; }
         }
         __syncthreads();
+        PH(10);
         // ---- stage B: IoU cost on the candidates (iou_matching.py:7-78, linear_assignment.py:11-73)
         {
             const int ncand = sh->ncand, nud = sh->nud;
@@ -501,6 +584,7 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
             for (int i = tid; i < ncand; i += BP_THREADS) match_a[i] = -1;
             for (int i = tid; i < nud; i += BP_THREADS) match_b[i] = -1;
             __syncthreads();
+            PH(11);
             if (ncand > 0 && nud > 0) {
                 const int nr = a_rows ? ncand : nud, nc = a_rows ? nud : ncand;
                 if (!lap_solve_cta(cost, ld, nr, nc, true, lap_u, col4row, row4col, path, &sh->lap_ok)) { if (tid == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); }
@@ -522,6 +606,7 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
             }
             __syncthreads();
         }
+        PH(12);
         // ---- Track.update for every pair (track.py:137-174, kalman_filter.py:106-166)
         {
             const int np_ = sh->npairs;
@@ -559,6 +644,7 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
             }
             __syncthreads();
         }
+        PH(13);
         // ---- mark_missed (track.py:181-187), births (tracker.py:423-441)
         for (int k = tid; k < nt; k += BP_THREADS) {
             const int s = list_m[k];
@@ -603,10 +689,12 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
                 const int s = k < np_ ? pair_t[k] : un_d[k - np_];
                 double g[4];
                 if (!bp_track_cache(S.mean + (size_t)s * 8, S.cov + (size_t)s * 64, g, S.chol + (size_t)s * 24)) atomicOr(status, TK_DEV_BAD_CHOLESKY);
-                for (int i = 0; i < 4; ++i) { gate_m[4 * s + i] = g[i]; S.gate[4 * s + i] = g[i]; }
+                for (int i = 0; i < 4; ++i) S.gate[4 * s + i] = g[i];
+                gate_f[s] = bp_gate_f32(g);
             }
         }
         __syncthreads();
+        PH(14);
         if (warp_id() == 0) {   // tracks = [t for t in tracks if not deleted]; free the deleted slots; emit (strong_sort.py:96-120)
             const int n0 = nt + sh->n_born;
             int nfree = S.hdr[5];
@@ -643,8 +731,10 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
             }
             out_n += cnt;
         }
+        PH(15);
         __threadfence();
         group_barrier(S.bar, ncta);   // third barrier of the frame: ema_slot / born_slot lists are visible to the workers
+        PH(16);
     }
     if (worker && pending) bp_feature_updates(S, prm, feats, viss, wg, wn);   // updates of the last frame of the launch
     if (master) {   // write the mirrors back
@@ -675,8 +765,8 @@ __global__ void bpbreid_reset_kernel(char* base, size_t stride, int cap, int cap
 size_t bp_smem(int cap, int capd, int capl) {
     const int side = capl > capd ? capl : capd;
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    size_t s = al(8 * (size_t)(capl + 1) * (capd + 1)) + al(8 * side) + 2 * al(8 * 4 * capd) + al(8 * 4 * cap);
-    s += 3 * al(4 * cap) + 5 * al(4 * side) + 2 * al(4 * capl) + 4 * al(4 * capd) + 3 * al(cap) + al(sizeof(BpShared));
+    size_t s = al(8 * (size_t)(capl + 1) * (capd + 1)) + al(8 * side) + 2 * al(8 * 4 * capd) + al(16 * cap) + al(8 * capd);
+    s += 4 * al(4 * cap) + 5 * al(4 * side) + 2 * al(4 * capl) + 4 * al(4 * capd) + 3 * al(cap) + al(sizeof(BpShared));
     return s;
 }
 
@@ -739,6 +829,15 @@ int tk_bpbreid_status(void* handle, int* status_host, void* stream) {
     TK_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return TK_OK;
 }
+
+#ifdef TK_PHASE_PROF
+int tk_debug_bpbreid_phases(unsigned long long* host_out64, int reset) {
+    cudaDeviceSynchronize();
+    if (host_out64) cudaMemcpyFromSymbol(host_out64, g_bp_prof, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_bp_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int tk_bpbreid_destroy(void* handle) {
     if (!handle) return TK_ERR_ARG;

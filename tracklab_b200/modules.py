@@ -326,3 +326,118 @@ class StrongSORT(ImageLevelModule):
 
 
 _bind_from(StrongSORT, _StrongSortImpl)
+
+
+# ---- BPBReID-StrongSORT: part-based embeddings + visibility scores come from the upstream ReID module ---------------
+class _BpbreidImpl:
+    """Shared implementation bound into ``BPBReIDStrongSORT``. Replaces
+    /root/reference/tracklab/wrappers/track/bpbreid_strong_sort_api.py:13-118: the video's ``bbox_ltwh`` / ``embeddings``
+    [K,E] / ``visibility_scores`` [K] columns go to the device once and tk_bpbreid_run associates the whole video.
+    Only ``matching_strategy: strong_sort_matching`` + ``motion_criterium: iou`` with ``ecc: false`` (the reference YAML) are
+    implemented; the ``costs`` column (per-detection visualisation dictionaries, sort/tracker.py:365-407) is left empty."""
+
+    def __init__(self, cfg, device, batch_size=None, **kwargs):
+        ImageLevelModule.__init__(self, batch_size=1)
+        if not torch.cuda.is_available():
+            raise _lib.TrackKernError(f"{type(self).__name__} needs a CUDA device: tracklab_b200 has no CPU path")
+        if bool(_cfg_get(cfg, "ecc", False)):
+            raise _lib.TrackKernError("ecc=True (cv2.findTransformECC camera compensation) is not implemented on device")
+        if _cfg_get(cfg, "matching_strategy", "strong_sort_matching") != "strong_sort_matching" or \
+                _cfg_get(cfg, "motion_criterium", "iou") != "iou":
+            raise _lib.TrackKernError("only matching_strategy=strong_sort_matching with motion_criterium=iou is implemented on device")
+        self.cfg = cfg
+        self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
+        self.cap_tracks = int(_cfg_get(cfg, "cap_tracks", 1024))
+        self.cap_dets = int(_cfg_get(cfg, "cap_dets", 128))
+        self.ctas_per_video = int(_cfg_get(cfg, "ctas_per_video", 24))
+        self.frames_per_batch = _cfg_get(cfg, "frames_per_batch", None)
+        self.hyper = dict(ema_alpha=float(_cfg_get(cfg, "ema_alpha", 0.9)), mc_lambda=float(_cfg_get(cfg, "mc_lambda", 0.995)),
+                          max_dist=float(_cfg_get(cfg, "max_dist", 0.5)), max_iou_distance=float(_cfg_get(cfg, "max_iou_distance", 0.8)),
+                          max_age=int(_cfg_get(cfg, "max_age", 300)), n_init=int(_cfg_get(cfg, "n_init", 0)),
+                          min_bbox_confidence=float(_cfg_get(cfg, "min_bbox_confidence", 0.0)),
+                          max_kalman_prediction_without_update=int(_cfg_get(cfg, "max_kalman_prediction_without_update", 7)))
+        self.tracker = None
+        self._pipe = _TrackerDatapipe(self, self.frames_per_batch)
+        self._result = None
+
+    def reset(self):
+        self._result = None
+        if self.tracker is not None:
+            self.tracker.reset()
+
+    def datapipe(self):
+        return self._pipe
+
+    def dataloader(self, engine=None):
+        return _VideoBatches(self._pipe)
+
+    def preprocess(self, image, detections, metadata):   # never called: the datapipe is overridden
+        return {"input": []}
+
+    def _track_video(self, img_metadatas, detections):
+        from .device_trackers import BpbreidStrongSortDevice
+        image_ids = np.asarray(img_metadatas.index)
+        if detections is None or len(detections) == 0:
+            self._result = pd.DataFrame(columns=["image_id"] + self.output_columns)
+            return
+        pos = {int(i): k for k, i in enumerate(image_ids)}
+        img = detections["image_id"].to_numpy()
+        keep = np.fromiter((int(i) in pos for i in img), dtype=bool, count=len(img))
+        det = detections[keep]
+        frame = np.fromiter((pos[int(i)] for i in det["image_id"].to_numpy()), dtype=np.int64, count=len(det))
+        order = np.argsort(frame, kind="stable")
+        rows = np.zeros((len(det), 7), dtype=np.float64)
+        rows[:, :4] = np.stack(det["bbox_ltwh"].to_numpy()).astype(np.float64).reshape(-1, 4)[order]   # np.asarray(..., dtype=float) strong_sort.py:69
+        conf_col = "bbox_conf" if "bbox_conf" in det.columns else "keypoints_conf"                     # bpbreid_strong_sort_api.py:85-88
+        rows[:, 4] = det[conf_col].to_numpy(dtype=np.float64)[order]
+        rows[:, 6] = np.asarray(det.index, dtype=np.float64)[order]
+        feats = np.ascontiguousarray(np.stack(det["embeddings"].to_numpy()).astype(np.float32)[order])
+        vis = np.ascontiguousarray(np.stack(det["visibility_scores"].to_numpy()).astype(np.float32)[order])
+        counts = np.bincount(frame, minlength=len(image_ids))
+        offsets = np.zeros(len(image_ids) + 1, dtype=np.int32)
+        np.cumsum(counts, out=offsets[1:])
+        if counts.max() > self.cap_dets:
+            raise _lib.TrackKernError(f"{counts.max()} detections in one frame exceed cap_dets={self.cap_dets}")
+        K, E = feats.shape[1:]
+        if self.tracker is None or (self.tracker.n_parts, self.tracker.feature_dim) != (K, E):
+            self.tracker = BpbreidStrongSortDevice(K, E, **self.hyper, ctas_per_video=self.ctas_per_video, cap_tracks=self.cap_tracks,
+                                                   cap_dets=self.cap_dets, device=self.device)
+        out_rows, out_fc, out_cnt = self.tracker.run(torch.from_numpy(rows).to(self.device), torch.from_numpy(offsets)[None].to(self.device),
+                                                     torch.from_numpy(feats).to(self.device), torch.from_numpy(vis).to(self.device))
+        self.tracker.check_status()
+        n = int(out_cnt[0].item())
+        res = out_rows[:n].cpu().numpy()
+        fc = out_fc[0].cpu().numpy()
+        frame_of_row = np.repeat(np.arange(len(fc)), fc)
+        code = res[:, 9].astype(int)
+        self._result = pd.DataFrame({
+            "track_id": res[:, 0].astype(int),
+            "track_bbox_kf_ltwh": list(res[:, 1:5]),
+            "track_bbox_pred_kf_ltwh": [None if np.isnan(r[0]) else r for r in res[:, 5:9]],
+            "matched_with": [None if c == 0 else ("R" if c == 1 else "S", float(d)) for c, d in zip(code, res[:, 10])],
+            "costs": [{} for _ in range(n)],
+            "hits": res[:, 11].astype(int), "age": res[:, 12].astype(int),
+            "time_since_update": np.zeros(n, dtype=int), "state": ["c"] * n,
+            "image_id": image_ids[frame_of_row],
+        }, index=pd.Index(res[:, 13].astype(int)))
+
+    def process(self, batch, detections, metadatas):
+        if len(detections) == 0 or self._result is None or len(self._result) == 0:
+            return []
+        sel = self._result[self._result["image_id"].isin(list(metadatas.index))]
+        if len(sel) == 0:
+            return []
+        assert set(sel.index).issubset(detections.index), \
+            "Mismatch of indexes during the tracking. The results should match the detections."
+        return sel[list(self.output_columns)]
+
+
+class BPBReIDStrongSORT(ImageLevelModule):
+    """Drop-in for tracklab.wrappers.track.bpbreid_strong_sort_api.BPBReIDStrongSORT."""
+    input_columns = ["bbox_ltwh", "embeddings", "visibility_scores"]
+    output_columns = ["track_id", "track_bbox_kf_ltwh", "track_bbox_pred_kf_ltwh", "matched_with", "costs", "hits", "age",
+                      "time_since_update", "state"]
+    collate_fn = None
+
+
+_bind_from(BPBReIDStrongSORT, _BpbreidImpl)
