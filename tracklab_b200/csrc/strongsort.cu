@@ -11,11 +11,14 @@
 // and of the wrapper filter /root/reference/tracklab/wrappers/track/strong_sort_api.py:66-93 (ecc off, max_unmatched_preds 0).
 //
 // Execution shape. The appearance term is min over a gallery of up to `budget` (100) EMA features per confirmed track:
-// T x budget x D x E multiply-adds per frame (164 MFLOP at 40 x 100 x 40 x 512) inside the per-frame dependency chain —
-// too much for one SM, so each video gets a GROUP of CTAs launched cooperatively: per frame the master CTA predicts
-// and lists, all CTAs of the group compute gallery-vs-detections cosine tiles (fp32 FMA out of shared memory), a
-// group barrier, then the master gates (Mahalanobis), fuses, solves both assignments (lap.cuh), updates filters
-// (octets), EMA features and galleries, and emits rows. Still one launch per chunk of frames, no host round trips.
+// T x budget x D x E multiply-adds per frame (164 MFLOP at 40 x 100 x 40 x 512, 4x that with ResNet-50's 2048-d features)
+// inside the per-frame dependency chain, of which the Mahalanobis gate (linear_assignment.py:166-174) then overwrites all
+// but a few entries per detection with 1e5. So the gate goes first and each video gets a GROUP of CTAs launched
+// cooperatively: per frame the master CTA predicts, lists and gates (pairs that survive are published); meanwhile the
+// other CTAs L2-normalise the frame's detection features; after a group barrier ALL CTAs evaluate the cosine distance of
+// the surviving pairs only, one warp per (pair, 8 gallery rows), min-reduced with ordered-int atomics; a second barrier,
+// then the master fuses, solves both assignments (lap.cuh), updates filters (octets), EMA features and galleries, and
+// emits rows. Still one launch per chunk of frames, no host round trips.
 #include <cooperative_groups.h>
 #include "kf_xyah.cuh"
 #include "lap.cuh"
@@ -42,8 +45,9 @@ struct SsDev {
     unsigned char *state, *fresh;
     float *smooth, *gallery;   // [cap][E], [cap][budget][E] (gallery rows are stored re-normalised)
     int* app_key;              // [cap][capd] appearance cost of the current frame as ordered-int float keys (row = position in conf_list)
-    int *row_trk, *row_start;  // stacked gallery rows of the frame -> confirmed-track position; first row of each track
-    float* dnorm_g;            // [capd] norms of the frame's detection features
+    int* ppack;                // [cap][capd] (confirmed-track position << 8 | detection) of the pairs inside the gate
+    float* dfeatn;             // [capd][E] L2-normalised detection features of the frame
+    int *task_slot, *task_row, *task_flag;   // feature work of the frame published for the worker CTAs (hdr[8] = count)
     unsigned* bar;             // group barrier: count, generation
 };
 
@@ -54,7 +58,7 @@ __host__ __device__ inline size_t ss_state_bytes(int cap, int capd, int budget, 
     s += ss_al((size_t)cap * 8 * 8) + ss_al((size_t)cap * 64 * 8) + 2 * ss_al((size_t)cap * 8);
     s += 10 * ss_al((size_t)cap * 4) + ss_al((size_t)capd * 4) + 2 * ss_al((size_t)cap);
     s += ss_al((size_t)cap * E * 4) + ss_al((size_t)cap * budget * E * 4) + ss_al((size_t)cap * capd * 8);
-    s += ss_al((size_t)cap * budget * 4) + ss_al((size_t)(cap + 1) * 4) + ss_al((size_t)capd * 4);
+    s += ss_al((size_t)cap * capd * 4) + ss_al((size_t)capd * E * 4) + 3 * ss_al((size_t)cap * 4);
     return s;
 }
 
@@ -75,9 +79,11 @@ __host__ __device__ inline SsDev ss_carve(char* base, int cap, int capd, int bud
     d.smooth = (float*)p; p += ss_al((size_t)cap * E * 4);
     d.gallery = (float*)p; p += ss_al((size_t)cap * budget * E * 4);
     d.app_key = (int*)p; p += ss_al((size_t)cap * capd * 8);
-    d.row_trk = (int*)p; p += ss_al((size_t)cap * budget * 4);
-    d.row_start = (int*)p; p += ss_al((size_t)(cap + 1) * 4);
-    d.dnorm_g = (float*)p;
+    d.ppack = (int*)p; p += ss_al((size_t)cap * capd * 4);
+    d.dfeatn = (float*)p; p += ss_al((size_t)capd * E * 4);
+    d.task_slot = (int*)p; p += ss_al((size_t)cap * 4);
+    d.task_row = (int*)p; p += ss_al((size_t)cap * 4);
+    d.task_flag = (int*)p;
     return d;
 }
 
@@ -88,6 +94,79 @@ __device__ __forceinline__ float warp_norm(const float* x, int E) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return sqrtf(s);
+}
+
+// float32 dot product of two length-E vectors by one warp (result in every lane); float4 path when E % 4 == 0
+__device__ __forceinline__ float warp_dot(const float* __restrict__ a, const float* __restrict__ b, int E) {
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    if ((E & 3) == 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll 4
+        for (int k = lane_id(); k < (E >> 2); k += 32) {
+            const float4 x = a4[k], y = b4[k];
+            s0 = fmaf(x.x, y.x, s0); s1 = fmaf(x.y, y.y, s1); s2 = fmaf(x.z, y.z, s2); s3 = fmaf(x.w, y.w, s3);
+        }
+    } else {
+#pragma unroll 4
+        for (int k = lane_id(); k < E; k += 32) s0 = fmaf(a[k], b[k], s0);
+    }
+    float s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+// b = features / ||features|| (nn_matching.py:46-48) for the frame's detections into S.dfeatn. The calling CTA filters the
+// frame itself (strong_sort_api.py:69) into `rows` (shared memory) so that it does not wait for the master.
+__device__ void ss_det_normalise(const SsDev& S, const SsParams& prm, const double* __restrict__ D, int nraw, const float* __restrict__ feats,
+                                 int r0, int* rows, int* nd_smem, int wg, int wn) {
+    if (warp_id() == 0) {
+        const int nd_ = warp_compact(nraw, 0, [&](int i) { return D[i * 7 + 4] > prm.min_conf; }, [&](int i, int p) { rows[p] = i; });
+        if (lane_id() == 0) *nd_smem = nd_;
+    }
+    __syncthreads();
+    const int nd = *nd_smem, E = prm.E;
+    for (int d = wg; d < nd; d += wn) {
+        const float* fv = feats + (size_t)(r0 + rows[d]) * E;
+        float* dn = S.dfeatn + (size_t)d * E;
+        const float nf = sqrtf(warp_dot(fv, fv, E));
+#pragma unroll 4
+        for (int k = lane_id(); k < E; k += 32) dn[k] = __fdiv_rn(fv[k], nf);
+    }
+}
+
+// Feature side of the frame, one warp per track: birth feature (track.py:84), EMA update (track.py:284-288) and, for
+// confirmed tracks, the gallery append of the re-normalised EMA feature (nn_matching.py:127-142, what _cosine_distance
+// normalises again on every call). Runs on the worker CTAs while the master already predicts the next frame.
+constexpr int SS_TASK_BIRTH = 1, SS_TASK_EMA = 2, SS_TASK_APPEND = 4;
+__device__ void ss_feature_tasks(const SsDev& S, const SsParams& prm, const float* __restrict__ feats, int wg, int wn) {
+    const int n = S.hdr[8], E = prm.E, lane = lane_id();
+    for (int t = wg; t < n; t += wn) {
+        const int s = S.task_slot[t], fl = S.task_flag[t];
+        float* sm = S.smooth + (size_t)s * E;
+        if (fl & (SS_TASK_BIRTH | SS_TASK_EMA)) {
+            const float* fv = feats + (size_t)S.task_row[t] * E;
+            const float nf = warp_norm(fv, E);
+            if (fl & SS_TASK_BIRTH) {
+                for (int k = lane; k < E; k += 32) sm[k] = __fdiv_rn(fv[k], nf);
+            } else {
+                for (int k = lane; k < E; k += 32)
+                    sm[k] = __fadd_rn(__fmul_rn(prm.ema_alpha, sm[k]), __fmul_rn(prm.ema_beta, __fdiv_rn(fv[k], nf)));
+                __syncwarp();
+                const float ns = warp_norm(sm, E);
+                for (int k = lane; k < E; k += 32) sm[k] = __fdiv_rn(sm[k], ns);
+            }
+            __syncwarp();
+        }
+        if (fl & SS_TASK_APPEND) {
+            const int h = S.g_head[s];
+            float* dst = S.gallery + ((size_t)s * prm.budget + h) * E;
+            const float ns = warp_norm(sm, E);
+            for (int e = lane; e < E; e += 32) dst[e] = __fdiv_rn(sm[e], ns);
+            if (lane == 0) { S.g_head[s] = (h + 1) % prm.budget; if (S.g_count[s] < prm.budget) S.g_count[s] += 1; }
+        }
+    }
 }
 
 // Detection.to_xyah (sort/detection.py:45-52) from the float64 wrapper row: tlwh float32, then float32 ops
@@ -102,7 +181,7 @@ __device__ __forceinline__ void det_boxes(const double* d, float* tlwh, double* 
     }
 }
 
-struct SsShared { int lap_ok, nd, nconf, ncand, nud, npairs, n_out, n_ut; };
+struct SsShared { int lap_ok, nd, nconf, ncand, nud, npairs, n_out, n_ut, nap, nd_w; };
 
 __global__ void __launch_bounds__(SS_THREADS)
 strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int cap, int capd, int ncta,
@@ -117,12 +196,7 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
     unsigned char* sp = smem_raw;
     auto take = [&](size_t bytes) { unsigned char* p = sp; sp += (bytes + 15) & ~(size_t)15; return p; };
     const int side = cap > capd ? cap : capd;
-    // appearance tiles (all CTAs)
-    float* tb = (float*)take(sizeof(float) * 16 * 68);             // [16 k][64 d (+4 pad)] detections chunk
-    float* ta = (float*)take(sizeof(float) * 16 * 68);             // [16 k][64 rows (+4 pad)] gallery chunk
-    float* bmin = (float*)take(sizeof(float) * 64 * 64);           // per-tile min keys [track in tile][d]
-    float* dnorm = (float*)take(sizeof(float) * capd);             // |feature| of the frame's detections
-    // master only
+    // master only (workers: tmp_d for their own copy of the filtered detection list)
     double* cost = (double*)take(sizeof(double) * (size_t)(cap + 1) * (capd + 1));
     double* lap_u = (double*)take(sizeof(double) * side);
     double* d_z = (double*)take(sizeof(double) * 4 * capd);
@@ -139,6 +213,7 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
     int* pair_t = (int*)take(sizeof(int) * cap);
     int* pair_d = (int*)take(sizeof(int) * cap);
     int* out_pos = (int*)take(sizeof(int) * cap);
+    int* upd_row = (int*)take(sizeof(int) * cap);                   // absolute detection row that updated / created the slot this frame
     unsigned char* t_flag = (unsigned char*)take(cap);
     unsigned char* d_flag = (unsigned char*)take(capd);
     SsShared* sh = (SsShared*)take(sizeof(SsShared));
@@ -149,6 +224,10 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
     int out_n = out_count[seq];
     const double L_app = prm.max_dist + 1e-5, L_iou = prm.max_iou_dist + 1e-5;
 
+    const bool worker = !master || ncta == 1;
+    const int wg = (ncta == 1 ? 0 : cta - 1) * (SS_THREADS / 32) + warp_id(), wn = (ncta == 1 ? 1 : ncta - 1) * (SS_THREADS / 32);
+    bool pending = false;   // feature tasks of the last processed frame still to be applied
+
     for (int f = 0; f < n_frames; ++f) {
         const int r0 = offsets[seq * F1 + f], r1 = offsets[seq * F1 + f + 1];
         const int nraw = r1 - r0;
@@ -156,7 +235,12 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
         if (nraw > capd) { if (master && tid == 0) atomicOr(status, TK_DEV_OVERFLOW_DETS); break; }
         const double* D = dets + (size_t)r0 * 7;
 
-        // ================= master: predict, detections, lists =================
+        if (!master) {   // workers: last frame's feature tasks, this frame's normalised detection features (overlaps the master's predict + gate)
+            if (pending) ss_feature_tasks(S, prm, feats, wg, wn);
+            ss_det_normalise(S, prm, D, nraw, feats, r0, tmp_d, &sh->nd_w, wg, wn);
+            __threadfence();
+        }
+        // ================= master: predict, detections, lists, gate =================
         if (master) {
             const int nt = S.hdr[1];
             for (int base = 0; base < nt; base += SS_THREADS / 8) {   // Track.predict (track.py:245-249, kalman_filter.py:80-112)
@@ -191,136 +275,89 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
             if (warp_id() == 0) {
                 const int nc = warp_compact(nt, 0, [&](int k) { return S.state[S.list[k]] == SS_CONFIRMED; },
                                             [&](int k, int p) { S.conf_list[p] = S.list[k]; });
-                if (lane_id() == 0) { sh->nconf = nc; S.hdr[7] = nc; }
-                // first stacked row of every confirmed track (exclusive scan of the gallery sizes)
-                int run = 0;
-                for (int c0 = 0; c0 < nc; c0 += 32) {
-                    const int c = c0 + lane_id();
-                    const int g = c < nc ? S.g_count[S.conf_list[c]] : 0;
-                    int incl = g;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane_id() >= o) incl += v; }
-                    if (c < nc) S.row_start[c] = run + incl - g;
-                    run += __shfl_sync(0xffffffffu, incl, 31);
-                }
-                if (lane_id() == 0) { S.row_start[nc] = run; S.hdr[2] = run; }
+                if (lane_id() == 0) { sh->nconf = nc; S.hdr[7] = nc; sh->nap = 0; }
+            }
+            if (ncta == 1) {
+                if (pending) ss_feature_tasks(S, prm, feats, wg, wn);
+                ss_det_normalise(S, prm, D, nraw, feats, r0, tmp_d, &sh->nd_w, wg, wn);
             }
             __syncthreads();
             {
                 const int nc = sh->nconf, nd2 = sh->nd;
-                for (int c = warp_id(); c < nc; c += SS_THREADS / 32) {
-                    const int r_lo = S.row_start[c], r_hi = S.row_start[c + 1];
-                    for (int r = r_lo + lane_id(); r < r_hi; r += 32) S.row_trk[r] = c;
+                for (int r = tid; r < nc; r += SS_THREADS) {   // projected distribution of each confirmed track (confidence 0)
+                    const int s = S.conf_list[r];
+                    const double* m = S.mean + (size_t)s * 8;
+                    const double* P = S.cov + (size_t)s * 64;
+                    const double sp_ = W_POS * m[3];
+                    const double rr[4] = {sp_ * sp_, sp_ * sp_, 1e-1 * 1e-1, sp_ * sp_};
+                    double Pl[64];
+                    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Pl[i * 8 + j] = P[i * 8 + j];
+                    double L[16], Sm[16], invd[4];
+                    if (!kf8_chol4(Pl, rr, L, Sm, invd)) atomicOr(status, TK_DEV_BAD_CHOLESKY);
+                    double* c = chol + 24 * r;
+                    for (int i = 0; i < 4; ++i) c[i] = m[i];
+                    for (int i = 0; i < 16; ++i) c[4 + i] = L[i];
+                    for (int i = 0; i < 4; ++i) c[20 + i] = invd[i];
                 }
-                for (int e = tid; e < nc * nd2; e += SS_THREADS) S.app_key[(size_t)(e / nd2) * capd + (e % nd2)] = 0x7fffffff;
-                for (int d = warp_id(); d < nd2; d += SS_THREADS / 32) {   // b = features / ||features|| (nn_matching.py:46-48)
-                    const float nf = warp_norm(feats + (size_t)(r0 + S.det_rows[d]) * E, E);
-                    if (lane_id() == 0) S.dnorm_g[d] = nf;
+                __syncthreads();
+                // Mahalanobis gate first (linear_assignment.py:166-174): only pairs inside it need an appearance distance
+                for (int e0 = 0; e0 < nc * nd2; e0 += SS_THREADS) {
+                    const int e = e0 + tid;
+                    bool in = false;
+                    int r = 0, d = 0;
+                    if (e < nc * nd2) {
+                        r = e / nd2; d = e - r * nd2;
+                        const double* c = chol + 24 * r;
+                        in = !(kf8_maha(c, c + 4, c + 20, d_z + 4 * d) > CHI2_4);
+                        S.app_key[(size_t)r * capd + d] = 0x7fffffff;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (m) {
+                        int base = 0;
+                        if (lane_id() == 0) base = atomicAdd(&sh->nap, __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (in) S.ppack[base + __popc(m & ((1u << lane_id()) - 1u))] = (r << 8) | d;
+                    }
                 }
+                __syncthreads();
+                if (tid == 0) S.hdr[2] = sh->nap;
             }
             __threadfence();
         }
         group_barrier(S.bar, ncta);
 
-        // ================= all CTAs: appearance cost (nn_matching.py:30-49,73-91,144-161) =================
-        // One stacked fp32 GEMM per frame: rows = every gallery sample of every confirmed track (row_trk maps a row to its
-        // track), columns = the frame's detections (normalised on load). 64x64 output tiles, 4x4 register micro-tiles,
-        // k walked in chunks of 16 through shared memory; the min over a track's samples is taken with ordered-int
-        // atomics, first in shared memory per tile, then once per (track, detection) in global memory.
+        // ================= all CTAs: appearance cost of the gated-in pairs (nn_matching.py:30-49,73-91,144-161) =================
+        // item = (pair, 8 gallery rows of its track): 1 - <gallery row, normalised detection>, min over the rows with an
+        // ordered-int atomic per item (the gallery rows are stored re-normalised, as _cosine_distance does on every call).
         {
-            const int nd = S.hdr[6], nconf = S.hdr[7], nrows = S.hdr[2];
-            for (int d = tid; d < nd; d += SS_THREADS) dnorm[d] = S.dnorm_g[d];
-            __syncthreads();
-            const int tx = tid & 15, ty = tid >> 4;
-            const int ntile_r = (nrows + 63) >> 6, ntile_c = (nd + 63) >> 6;
-            for (int tile = cta; tile < ntile_r * ntile_c && nconf > 0; tile += ncta) {
-                const int tr0 = (tile / ntile_c) * 64, tc0 = (tile % ntile_c) * 64;
-                const int c_first = S.row_trk[tr0];
-                for (int e = tid; e < 64 * 64; e += SS_THREADS) ((int*)bmin)[e] = 0x7fffffff;
-                float acc[4][4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
-                // per-thread load coordinates: 64 rows x 16 k per chunk = 1024 floats of A and of B, 4 each
-                const int lr = tid >> 2, lk = (tid & 3) * 4;
-                const int arow = tr0 + lr;
-                const float* ap = nullptr;
-                if (arow < nrows) {
-                    const int c = S.row_trk[arow];
-                    const int slot = S.conf_list[c];
-                    ap = S.gallery + ((size_t)slot * prm.budget + (arow - S.row_start[c])) * E;
+            const int nap = S.hdr[2], budget = prm.budget;
+            const int nchunk = (budget + 7) >> 3;
+            const int gw = cta * (SS_THREADS / 32) + warp_id(), nw = ncta * (SS_THREADS / 32);
+            for (int it = gw; it < nap * nchunk; it += nw) {
+                const int p = it / nchunk, ch = it - p * nchunk;
+                const int pk = S.ppack[p], r = pk >> 8, d = pk & 255;
+                const int slot = S.conf_list[r];
+                const int j0 = ch * 8, j1 = min(S.g_count[slot], j0 + 8);
+                if (j0 >= j1) continue;
+                const float* dn = S.dfeatn + (size_t)d * E;
+                const float* g = S.gallery + ((size_t)slot * budget + j0) * E;
+                float best = __int_as_float(0x7f800000);
+                for (int j = j0; j < j1; ++j, g += E) best = fminf(best, __fsub_rn(1.0f, warp_dot(g, dn, E)));
+                if (lane_id() == 0) {
+                    int key = __float_as_int(best);
+                    key = key >= 0 ? key : key ^ 0x7fffffff;
+                    atomicMin(&S.app_key[(size_t)r * capd + d], key);
                 }
-                const int bd = tc0 + lr;
-                const float* bp = bd < nd ? feats + (size_t)(r0 + S.det_rows[bd]) * E : nullptr;
-                const float bnorm = bd < nd ? dnorm[bd] : 1.0f;
-                __syncthreads();
-                for (int k0 = 0; k0 < E; k0 += 16) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int k = k0 + lk + q;
-                        ta[(lk + q) * 68 + lr] = (ap && k < E) ? ap[k] : 0.0f;
-                        tb[(lk + q) * 68 + lr] = (bp && k < E) ? __fdiv_rn(bp[k], bnorm) : 0.0f;
-                    }
-                    __syncthreads();
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const float4 av = *reinterpret_cast<const float4*>(ta + k * 68 + ty * 4);
-                        const float4 bv = *reinterpret_cast<const float4*>(tb + k * 68 + tx * 4);
-                        const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-                        for (int a = 0; a < 4; ++a)
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
-                    }
-                    __syncthreads();
-                }
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const int r = tr0 + ty * 4 + a;
-                    if (r >= nrows) continue;
-                    const int lt = S.row_trk[r] - c_first;          // < 64: a 64-row tile spans at most 64 tracks
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int d = tx * 4 + b;
-                        if (tc0 + d >= nd) continue;
-                        int key = __float_as_int(__fsub_rn(1.0f, acc[a][b]));
-                        key = key >= 0 ? key : key ^ 0x7fffffff;
-                        atomicMin(&((int*)bmin)[lt * 64 + d], key);
-                    }
-                }
-                __syncthreads();
-                const int c_last = S.row_trk[min(tr0 + 63, nrows - 1)];
-                for (int e = tid; e < (c_last - c_first + 1) * 64; e += SS_THREADS) {
-                    const int lt = e >> 6, d = e & 63;
-                    if (tc0 + d < nd) atomicMin(&S.app_key[(size_t)(c_first + lt) * capd + tc0 + d], ((int*)bmin)[e]);
-                }
-                __syncthreads();
             }
             __threadfence();
         }
         group_barrier(S.bar, ncta);
-        if (!master) continue;
+        pending = true;
+        if (!master) { group_barrier(S.bar, ncta); continue; }   // third barrier: the master has published the frame's feature tasks
 
         // ================= master: gating, fusion, assignments, updates =================
         const int nd = sh->nd, nconf = sh->nconf, nt = S.hdr[1];
         // ---- stage A: confirmed tracks x all detections (tracker.py:152-170, linear_assignment.py:131-174)
-        for (int r = tid; r < nconf; r += SS_THREADS) {   // projected distribution of each confirmed track (confidence 0)
-            const int s = S.conf_list[r];
-            const double* m = S.mean + (size_t)s * 8;
-            const double* P = S.cov + (size_t)s * 64;
-            const double sp_ = W_POS * m[3];
-            const double rr[4] = {sp_ * sp_, sp_ * sp_, 1e-1 * 1e-1, sp_ * sp_};
-            double Pl[64];
-            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Pl[i * 8 + j] = P[i * 8 + j];
-            double L[16], Sm[16], invd[4];
-            if (!kf8_chol4(Pl, rr, L, Sm, invd)) atomicOr(status, TK_DEV_BAD_CHOLESKY);
-            double* c = chol + 24 * r;
-            for (int i = 0; i < 4; ++i) c[i] = m[i];
-            for (int i = 0; i < 16; ++i) c[4 + i] = L[i];
-            for (int i = 0; i < 4; ++i) c[20 + i] = invd[i];
-        }
-        __syncthreads();
         {
             const bool a_rows = nconf <= nd;
             const int ld = lap_pitch(a_rows ? nd : nconf);
@@ -430,21 +467,9 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
                 if (act && (tid & 7) == 0) {
                     const double* dr = D + (size_t)S.det_rows[d] * 7;
                     S.conf[s] = dr[4]; S.cls[s] = (int)dr[5]; S.det_id[s] = dr[6];
-                    S.hits[s] += 1; S.tsu[s] = 0;
+                    S.hits[s] += 1; S.tsu[s] = 0; upd_row[s] = r0 + S.det_rows[d];
                     if (S.state[s] == SS_TENTATIVE && S.hits[s] >= prm.n_init) S.state[s] = SS_CONFIRMED;
                 }
-            }
-            // EMA appearance (track.py:284-288): one warp per pair, float32
-            for (int p = warp_id(); p < np_; p += SS_THREADS / 32) {
-                const int s = pair_t[p];
-                const float* fv = feats + (size_t)(r0 + S.det_rows[pair_d[p]]) * E;
-                float* sm = S.smooth + (size_t)s * E;
-                const float nf = warp_norm(fv, E);
-                for (int k = lane_id(); k < E; k += 32)
-                    sm[k] = __fadd_rn(__fmul_rn(prm.ema_alpha, sm[k]), __fmul_rn(prm.ema_beta, __fdiv_rn(fv[k], nf)));
-                __syncwarp();
-                const float ns = warp_norm(sm, E);
-                for (int k = lane_id(); k < E; k += 32) sm[k] = __fdiv_rn(sm[k], ns);
             }
             __syncthreads();
         }
@@ -471,7 +496,7 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
                 S.list[nt + k] = s;
                 S.track_id[s] = id0 + k; S.cls[s] = (int)dr[5]; S.conf[s] = dr[4]; S.det_id[s] = dr[6];
                 S.hits[s] = 1; S.age[s] = 1; S.tsu[s] = 0; S.state[s] = SS_TENTATIVE; S.fresh[s] = 1;
-                S.g_count[s] = 0; S.g_head[s] = 0;
+                S.g_count[s] = 0; S.g_head[s] = 0; t_flag[s] = 2; upd_row[s] = r0 + S.det_rows[d];
                 pair_t[k] = s; pair_d[k] = d;     // reuse as the birth list for the parallel initialisation below
             }
             n += nb;
@@ -493,12 +518,6 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
                                      __fmul_rn((float)(10 * W_VEL), zf[3])};
                 for (int i = 0; i < 8; ++i) P[i * 9] = (double)__fmul_rn(sd[i], sd[i]);
             }
-            for (int k = warp_id(); k < nb; k += SS_THREADS / 32) {   // feature /= norm (track.py:84)
-                const int s = pair_t[k];
-                const float* fv = feats + (size_t)(r0 + S.det_rows[pair_d[k]]) * E;
-                const float nf = warp_norm(fv, E);
-                for (int e = lane_id(); e < E; e += 32) S.smooth[(size_t)s * E + e] = __fdiv_rn(fv[e], nf);
-            }
         }
         __syncthreads();
         if (warp_id() == 0) {   // tracks = [t for t in tracks if not deleted] (order kept); free the deleted slots
@@ -514,7 +533,14 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
             __syncwarp();
             const int cnt = warp_compact(n, 0, [&](int k) { const int s = S.list[k]; return S.state[s] == SS_CONFIRMED && S.tsu[s] <= 1; },
                                          [&](int k, int p) { out_pos[k] = p; });
+            const int ntask = warp_compact(n, 0, [&](int k) { const int s = S.list[k]; return t_flag[s] != 0 || S.state[s] == SS_CONFIRMED; },
+                                           [&](int k, int p) {
+                                               const int s = S.list[k];
+                                               S.task_slot[p] = s; S.task_row[p] = upd_row[s];
+                                               S.task_flag[p] = (t_flag[s] == 2 ? SS_TASK_BIRTH : (t_flag[s] == 1 ? SS_TASK_EMA : 0)) | (S.state[s] == SS_CONFIRMED ? SS_TASK_APPEND : 0);
+                                           });
             if (lane_id() == 0) {
+                S.hdr[8] = ntask;
                 S.hdr[1] = n; S.hdr[5] = nfree; sh->n_out = cnt;
                 out_frame_count[seq * n_frames + f] = cnt;
                 if (out_n + cnt > out_cap) atomicOr(status, TK_DEV_OVERFLOW_OUT);
@@ -523,17 +549,6 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
         __syncthreads();
         {
             const int n = S.hdr[1];
-            // gallery append for confirmed tracks: re-normalised copy of the EMA feature (what _cosine_distance uses)
-            for (int k = warp_id(); k < n; k += SS_THREADS / 32) {
-                const int s = S.list[k];
-                if (S.state[s] != SS_CONFIRMED) continue;
-                const float* sm = S.smooth + (size_t)s * E;
-                const int h = S.g_head[s];
-                float* dst = S.gallery + ((size_t)s * prm.budget + h) * E;
-                const float ns = warp_norm(sm, E);
-                for (int e = lane_id(); e < E; e += 32) dst[e] = __fdiv_rn(sm[e], ns);
-                if (lane_id() == 0) { S.g_head[s] = (h + 1) % prm.budget; if (S.g_count[s] < prm.budget) S.g_count[s] += 1; }
-            }
             // output rows (strong_sort.py:70-82,110-121)
             if (out_n + sh->n_out <= out_cap)
                 for (int k = tid; k < n; k += SS_THREADS) {
@@ -551,7 +566,9 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
         }
         __syncthreads();
         __threadfence();
+        group_barrier(S.bar, ncta);   // third barrier of the frame: the task list is visible to the workers
     }
+    if (worker && pending) ss_feature_tasks(S, prm, feats, wg, wn);   // tasks of the last frame of the launch
     if (master && tid == 0) out_count[seq] = out_n;
 }
 
@@ -571,9 +588,9 @@ __global__ void strongsort_reset_kernel(char* base, size_t stride, int cap, int 
 size_t ss_smem(int cap, int capd) {
     const int side = cap > capd ? cap : capd;
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
-    size_t s = 2 * al(4 * 16 * 68) + al(4 * 64 * 64) + al(4 * capd);
+    size_t s = 0;
     s += al(8 * (size_t)(cap + 1) * (capd + 1)) + al(8 * side) + al(8 * 4 * capd) + al(4 * 4 * capd) + al(8 * 24 * cap);
-    s += 5 * al(4 * side) + al(4 * cap) + 2 * al(4 * capd) + 3 * al(4 * cap) + al(cap) + al(capd) + al(sizeof(SsShared));
+    s += 5 * al(4 * side) + al(4 * cap) + 2 * al(4 * capd) + 4 * al(4 * cap) + al(cap) + al(capd) + al(sizeof(SsShared));
     return s;
 }
 
