@@ -61,10 +61,24 @@ int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, int W, long l
  * device int[N] frame index of each row; out: device [N,3,out_h,out_w] (out_nhwc=P>0: channels-last [N,out_h,out_w,P], P = channel pitch 3 or
  * e.g. 8 with caller-zeroed padding channels) of out_dtype.
  * mean3/std3: HOST float[3]. Pixel values are integer-exact vs Pillow's resampler.
+ * out_nhwc = TK_CROP_LAYOUT_S2D16: the ResNet stem layout. out is [N, out_h/2 + 3, out_w/2 + 3, 16] (caller-zeroed once):
+ * pixel (y, x, c) goes to row y/2 + 2, column x/2 + 2, channel ((y&1)*2 + (x&1))*3 + c, so that the 7x7 stride-2 pad-3
+ * stem convolution (/root/reference/plugins/track/strong_sort/deep/models/resnet.py:342-348) becomes a 4x4 stride-1
+ * convolution on 16 channels without padding (same sums, 5x faster in cuDNN than 7x7/2 on a 3->8 channel input).
  */
+#define TK_CROP_LAYOUT_S2D16 (-16)
 int tk_crop_resize_norm(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,
                         const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,
                         const float* mean3, const float* std3, void* stream);
+
+/* ---- Pooling passes of the ReID backbone (channels-last bf16) ----------------------------------------------
+ * tk_maxpool3x3s2_nhwc: src [N,H,W,C] -> dst [N,(H+1)/2,(W+1)/2,C], 3x3 window, stride 2, padding 1 (-inf), i.e.
+ *                       nn.MaxPool2d(3, 2, 1) after the stem (/root/reference/plugins/track/strong_sort/deep/models/resnet.py:349)
+ * tk_avgpool_nhwc:      src [N,HW,C] bf16 -> dst [N,C] float32, mean over the HW positions accumulated in float32
+ *                       (global average pool + flatten, resnet.py:355-356).  C must be a multiple of 8.
+ */
+int tk_maxpool3x3s2_nhwc(const void* src, int n, int H, int W, int C, void* dst, void* stream);
+int tk_avgpool_nhwc(const void* src, int n, int HW, int C, float* dst, void* stream);
 
 /* ---- Detector post-processing: YOLOX decode + threshold + class-aware NMS --------------------------
  * Replaces rtmlib YOLOX.postprocess / multiclass_nms behind rtmlib_api.py:30 (score_thr 0.7, nms_thr 0.45).

@@ -149,6 +149,64 @@ inline int grid_for(long long n_vec) {
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+// 3x3 / stride 2 / pad 1 max pooling, NHWC: one thread per (output pixel, 8-channel vector); the nine 16-byte loads of
+// neighbouring outputs overlap in L1/L2, HBM sees the input once.
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int H, int W, int C, int Ho, int Wo, long long n_vec) {
+    const int cv_n = C >> 3;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % cv_n);
+        long long pix = i / cv_n;
+        const int xo = (int)(pix % Wo); pix /= Wo;
+        const int yo = (int)(pix % Ho);
+        const long long img = pix / Ho;
+        const __nv_bfloat16* base = src + (size_t)img * H * W * C + cv * 8;
+        bf16x8 m;
+        bool first = true;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int y = 2 * yo + dy;
+            if (y < 0 || y >= H) continue;
+#pragma unroll
+            for (int dx = -1; dx <= 1; ++dx) {
+                const int x = 2 * xo + dx;
+                if (x < 0 || x >= W) continue;
+                const bf16x8 t = *reinterpret_cast<const bf16x8*>(base + ((size_t)y * W + x) * C);
+                if (first) { m = t; first = false; }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) m.v[k] = __hmax2(m.v[k], t.v[k]);
+                }
+            }
+        }
+        *reinterpret_cast<bf16x8*>(dst + (((size_t)img * Ho + yo) * Wo + xo) * C + cv * 8) = m;
+    }
+}
+
+// global average pool: one warp per (image, 8-channel vector pair): lanes stride over the positions, float32 accumulation
+__global__ void __launch_bounds__(256)
+avgpool_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int n, int HW, int C) {
+    const int cv_n = C >> 3;
+    const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= n * cv_n) return;
+    const int img = w / cv_n, cv = w - img * cv_n;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = lane; p < HW; p += 32) {
+        const bf16x8 t = *reinterpret_cast<const bf16x8*>(src + ((size_t)img * HW + p) * C + cv * 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(t.v[k]); acc[2 * k] += f.x; acc[2 * k + 1] += f.y; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[(size_t)img * C + cv * 8 + k] = acc[k] / (float)HW;
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -186,6 +244,23 @@ int tk_upsample2x_nhwc(const void* src, int src_pitch, int src_offset, void* dst
     upsample2x_kernel<<<grid_for(n_vec), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_pitch, src_offset,
                                                                        (__nv_bfloat16*)dst, n_vec, h, w, channels / 8,
                                                                        dst_pitch, dst_offset);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_maxpool3x3s2_nhwc(const void* src, int n, int H, int W, int C, void* dst, void* stream) {
+    if (!src || !dst || n <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7)) return TK_ERR_ARG;
+    const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+    const long long n_vec = (long long)n * Ho * Wo * (C / 8);
+    maxpool3x3s2_kernel<<<grid_for(n_vec), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, H, W, C, Ho, Wo, n_vec);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_avgpool_nhwc(const void* src, int n, int HW, int C, float* dst, void* stream) {
+    if (!src || !dst || n <= 0 || HW <= 0 || C <= 0 || (C & 7)) return TK_ERR_ARG;
+    const long long warps = (long long)n * (C / 8);
+    avgpool_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, dst, n, HW, C);
     TK_CUDA_TRY(cudaGetLastError());
     return TK_OK;
 }

@@ -403,8 +403,12 @@ crop_resize_norm_kernel(const unsigned char* __restrict__ frames, size_t frame_s
         for (int c = 0; c < 3; ++c) {
             const float t = __fdiv_rn((float)v[c], 255.0f);                 // ToTensor
             const float o = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);      // Normalize
-            const size_t idx = nhwc ? (((size_t)n * out_h + yy) * out_w + xx) * nhwc + c   // nhwc = channel pitch (3, or 8 with zero padding)
-                                    : (((size_t)n * 3 + c) * out_h + yy) * out_w + xx;
+            size_t idx;
+            if (nhwc == TK_CROP_LAYOUT_S2D16)   // 2x2 space-to-depth, 16-channel pitch, zero border of 2 before / 1 after (see trackkern.h)
+                idx = ((((size_t)n * (out_h / 2 + 3) + (yy >> 1) + 2) * (out_w / 2 + 3) + (xx >> 1) + 2) << 4) + (((yy & 1) * 2 + (xx & 1)) * 3 + c);
+            else
+                idx = nhwc ? (((size_t)n * out_h + yy) * out_w + xx) * nhwc + c   // nhwc = channel pitch (3, or 8 with zero padding)
+                           : (((size_t)n * 3 + c) * out_h + yy) * out_w + xx;
             out[idx] = cvt_out<OutT>(o);
         }
     }
@@ -417,6 +421,7 @@ extern "C" int tk_crop_resize_norm(const unsigned char* frames, int H, int W, lo
                                    const float* mean3, const float* std3, void* stream) {
     if (!frames || !dets || !det_frame || !out || !mean3 || !std3 || n_dets < 0 || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0) return TK_ERR_ARG;
     if (out_dtype != TK_DTYPE_F32 && out_dtype != TK_DTYPE_BF16) return TK_ERR_ARG;
+    if (out_nhwc == TK_CROP_LAYOUT_S2D16 && ((out_h | out_w) & 1)) return TK_ERR_ARG;
     if (n_dets == 0) return TK_OK;
     if (2 * ((W + out_w - 1) / out_w) + 1 > CR_KMAX || 2 * ((H + out_h - 1) / out_h) + 1 > CR_KMAX) return TK_ERR_CAPACITY;
     dim3 grid(out_h, n_dets);

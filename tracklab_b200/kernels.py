@@ -110,6 +110,28 @@ def bias_act(src: torch.Tensor, bias: torch.Tensor, dst: torch.Tensor, dst_offse
     return dst
 
 
+def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
+    """nn.MaxPool2d(3, 2, 1) on a bf16 channels-last [N,C,H,W] tensor (C ABI: tk_maxpool3x3s2_nhwc)."""
+    lib = _lib.load()
+    N, C, H, W = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((N, C, (H + 1) // 2, (W + 1) // 2), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tk_maxpool3x3s2_nhwc(x.data_ptr(), N, H, W, C, out.data_ptr(), _stream()), "tk_maxpool3x3s2_nhwc"); _count()
+    return out
+
+
+def avgpool(x: torch.Tensor) -> torch.Tensor:
+    """Global average pool of a bf16 channels-last [N,C,H,W] tensor -> float32 [N,C] (C ABI: tk_avgpool_nhwc)."""
+    lib = _lib.load()
+    N, C, H, W = x.shape
+    assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    out = torch.empty((N, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tk_avgpool_nhwc(x.data_ptr(), N, H * W, C, out.data_ptr(), _stream()), "tk_avgpool_nhwc"); _count()
+    return out
+
+
 def spp_pool(x: torch.Tensor, dst: torch.Tensor, dst_offset: int = 0):
     """dst[:, off:off+4C] = [x, maxpool5(x), maxpool9(x), maxpool13(x)] (C ABI: tk_spp_nhwc)."""
     lib = _lib.load()
@@ -189,13 +211,25 @@ REID_STD = (0.229, 0.224, 0.225)
 
 
 def crop_resize_norm(frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.Tensor, out_hw=(256, 128),
-                     out_dtype=torch.float32, channels_last: bool = False, mean=REID_MEAN, std=REID_STD, pad_channels_to: int = 3):
+                     out_dtype=torch.float32, channels_last: bool = False, mean=REID_MEAN, std=REID_STD, pad_channels_to: int = 3,
+                     s2d16_out: torch.Tensor | None = None):
     """frames uint8 [F,H,W,3], dets float64 [N,7], det_frame int32 [N] -> ReID input [N,3,h,w] (C ABI: tk_crop_resize_norm).
     pad_channels_to=8 (channels-last only) returns [N,8,h,w] with zero channels 3..7 for the fused backbone."""
     lib = _lib.load()
     _cuda(frames, "frames"); _cuda(dets, "dets"); _cuda(det_frame, "det_frame")
     F, H, W, _ = frames.shape
     N = dets.shape[0]
+    if s2d16_out is not None:
+        # stem layout (TK_CROP_LAYOUT_S2D16): s2d16_out is a zero-initialised channels-last [>=N, 16, h/2+3, w/2+3] buffer
+        assert s2d16_out.shape[0] >= N and tuple(s2d16_out.shape[1:]) == (16, out_hw[0] // 2 + 3, out_hw[1] // 2 + 3)
+        assert s2d16_out.is_contiguous(memory_format=torch.channels_last)
+        m = (ctypes.c_float * 3)(*mean)
+        sd = (ctypes.c_float * 3)(*std)
+        with torch.cuda.device(frames.device):
+            _lib.check(lib.tk_crop_resize_norm(frames.data_ptr(), H, W, frames.stride(0), dets.data_ptr(), det_frame.data_ptr(), N,
+                                               s2d16_out.data_ptr(), _dtype_code(s2d16_out.dtype), -16, out_hw[0], out_hw[1], m, sd,
+                                               _stream()), "tk_crop_resize_norm"); _count()
+        return s2d16_out
     if pad_channels_to != 3:
         assert channels_last
         out = torch.zeros((N, pad_channels_to, out_hw[0], out_hw[1]), dtype=out_dtype,

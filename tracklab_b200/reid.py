@@ -1,7 +1,7 @@
 """Device-resident ReID stage: frames + detection rows (HBM) -> appearance features float32 [N, E] (HBM).
 
-crop gather (tk_crop_resize_norm, PIL-exact) -> ResNet-50 in bf16 channels-last (cuDNN convolutions + libtrackkern
-epilogues). Stands in for the in-tracker ReID forward of the StrongSORT plugin
+crop gather (tk_crop_resize_norm, PIL-exact, written in the stem's space-to-depth layout) -> ResNet-50 in bf16 channels-last
+(cuDNN convolutions with fused bias/ReLU/residual, libtrackkern pooling kernels, one CUDA graph per crop-count bucket). Stands in for the in-tracker ReID forward of the StrongSORT plugin
 (/root/reference/plugins/track/strong_sort/strong_sort.py:135-145, reid_multibackend.py:184-237) for all detections of a
 batch of frames at once; the features feed tk_strongsort_run.
 """
@@ -14,7 +14,8 @@ from .nets.resnet_reid import build_resnet50_reid
 
 
 class ReidStageDevice:
-    def __init__(self, device="cuda:0", max_crops=2048, seed=1234, model=None, fused=True, precision="bf16"):
+    def __init__(self, device="cuda:0", max_crops=2048, seed=1234, model=None, fused=True, precision="bf16", legacy=False,
+                 use_graphs=True):
         if not torch.cuda.is_available():
             raise _lib.TrackKernError("ReidStageDevice needs a CUDA device (no CPU path)")
         _lib.load()
@@ -28,7 +29,7 @@ class ReidStageDevice:
             self.model = self.model.float()
         elif fused:
             from .nets.resnet_fused import ResNet50Fused
-            self.fused = ResNet50Fused(self.model, self.device)
+            self.fused = ResNet50Fused(self.model, self.device, legacy=legacy, use_graphs=use_graphs)
         else:
             self.model = self.model.to(torch.bfloat16).to(memory_format=torch.channels_last)
         torch.backends.cudnn.benchmark = True
@@ -48,6 +49,10 @@ class ReidStageDevice:
                     out[i:j] = self.model(x)
                 finally:
                     torch.backends.cudnn.allow_tf32 = tf32
+            elif self.fused is not None and not self.fused.legacy:
+                buf = self.fused.input_buffer(j - i)   # s2d16 stem layout, crop count rounded up to the bucket
+                kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], s2d16_out=buf)
+                out[i:j] = self.fused(buf, n_valid=j - i)
             elif self.fused is not None:
                 x = kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.bfloat16, channels_last=True,
                                              pad_channels_to=8)
