@@ -25,6 +25,7 @@ int tk_last_cuda_error(void);
 #define TK_ASSO_GIOU 1
 #define TK_ASSO_DIOU 2
 #define TK_ASSO_CIOU 3
+#define TK_ASSO_CT_DIST 4   /* centre distance rescaled by the matrix maximum (association.py:150-171) */
 
 /* element types for tensor arguments */
 #define TK_DTYPE_F32 0

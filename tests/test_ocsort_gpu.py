@@ -30,7 +30,9 @@ def test_ocsort_matches_reference_golden(name, cap):
     print(name, "max box err", err)
 
 
-# diou/ciou are not exercised through the whole tracker: against the [-1,-1,-1,-1] placeholder "last observation" of a
+# diou/ciou/ct_dist are not exercised through the whole tracker (ct_dist: all placeholder columns are identical, the same
+# pure tie; the oracle is pinned to the reference on tests/golden/ocsort_ctdist_byte_s1003.npz where both sides share the
+# solver stand-in, and the device arithmetic is pinned per element in tests/test_pairwise_gpu.py + the smoke test below): against the [-1,-1,-1,-1] placeholder "last observation" of a
 # track born in the previous frame they give every track the SAME positive score (association.py:58-147 on a point box),
 # so the reference's OCR round (ocsort.py:284-306) is a pure solver tie there. Their arithmetic is pinned per element in
 # tests/test_pairwise_gpu.py instead.
@@ -44,3 +46,14 @@ def test_ocsort_matches_oracle_fresh_seed(asso):
     rows, frames = _run_device(video, hyper, 0.4)
     # fresh seed with births next to unmatched tracks: id numbering may hit the solver tie described in tests/util.py
     assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1e-6, allow_relabel=True)
+
+
+def test_ocsort_ct_dist_runs_and_keeps_identities_on_clean_video():
+    """ct_dist end to end on a video without births after frame 0 and without misses: no placeholder observation ever
+    enters the OCR round, so the result is solver-independent and must equal the oracle exactly."""
+    from oracle.ocsort_np import OCSortOracle
+    video = make_video(seed=23, n_frames=80, n_ids=25, p_detect=1.0, fp_rate=0.0, occlusion=False, conf_range=(0.6, 1.0))
+    hyper = dict(det_thresh=0.5, max_age=20, min_hits=2, iou_threshold=0.25, delta_t=2, asso_func="ct_dist", inertia=0.3, use_byte=True)
+    ref_rows, ref_frames = OCSortOracle(**hyper, min_confidence=0.4).run_video(video.dets, video.offsets)
+    rows, frames = _run_device(video, hyper, 0.4)
+    assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1e-6)

@@ -12,7 +12,7 @@ def _boxes(rng, B, N, W=1920, H=1080):
     return np.concatenate([xy, xy + wh], axis=2)
 
 
-@pytest.mark.parametrize("variant", ["iou", "giou", "diou", "ciou"])
+@pytest.mark.parametrize("variant", ["iou", "giou", "diou", "ciou", "ct_dist"])
 @pytest.mark.parametrize("shape", [(1, 20, 20), (3, 40, 37), (2, 150, 150), (1, 1, 9)])
 def test_iou_family_matches_oracle(variant, shape):
     from oracle.ocsort_np import ASSO

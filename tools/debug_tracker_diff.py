@@ -35,3 +35,18 @@ for k, v in [("base", {}), ("nobyte", dict(use_byte=False))]:
             break
     else:
         print(asso, k, "equal up to relabelling")
+if asso == "ct_dist":
+    from tests.util import load_golden
+    g = load_golden("ocsort_ctdist_byte_s1003")
+    video = make_video(**g["gen"])
+    ref, rf = g["rows"], g["frames"]
+    trk = OCSortDevice(**g["hyper"], min_confidence=g["min_conf"])
+    rows, fc, cnt = trk.run(torch.from_numpy(video.dets).cuda(), torch.from_numpy(video.offsets.astype(np.int32))[None].cuda())
+    print("status", trk.status())
+    got, gf = rows_to_frames(rows, fc, torch.zeros(1, dtype=torch.int32))
+    print("rows", got.shape, ref.shape)
+    for f in range(video.n_frames):
+        a = got[gf == f]; b = ref[rf == f]
+        a = a[np.argsort(a[:, 7])]; b = b[np.argsort(b[:, 7])]
+        if a.shape != b.shape or not np.array_equal(a[:, [4, 7]], b[:, [4, 7]]):
+            print("golden: first differing frame", f); print(a[:, [4, 6, 7]]); print(b[:, [4, 6, 7]]); break

@@ -48,7 +48,7 @@ class BpbreidParams(ctypes.Structure):
                 ("feature_dim", ctypes.c_int), ("ctas_per_video", ctypes.c_int)]
 
 
-ASSO_CODES = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3}
+ASSO_CODES = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3, "ct_dist": 4}
 
 _lib = None
 

@@ -284,7 +284,15 @@ struct OcShared {
     int lap_ok;
     int nd, nlo, nt, shortcut, n_ud, n_ut, n_pairs, sorted_ud, n_births, n_out;
     int rowmax, colmax, maxflag;
+    unsigned long long dmax_bits;   // ct_dist: largest centre distance of the current matrix (non-negative double bits are ordered)
 };
+
+// ct_dist (association.py:150-171): centre distance d, then (d / d.max()).max() - d / d.max() = 1 - d / d.max()
+// (NaN everywhere when all centres coincide, exactly like the 0/0 of the reference). Two passes over the matrix.
+__device__ __forceinline__ double centre_dist(const double* a, const double* b) {
+    const double dx = (a[0] + a[2]) / 2.0 - (b[0] + b[2]) / 2.0, dy = (a[1] + a[3]) / 2.0 - (b[1] + b[3]) / 2.0;
+    return sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+}
 
 // Solve the min-cost full assignment of the smaller side (no limit). match_d[d] = t or -1.
 // C is stored with the smaller side as rows and leading dimension lap_pitch(cols).
@@ -500,13 +508,23 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
         // ---- BYTE round on low-score detections (ocsort.py:264-282) -----------------------------------
         if (prm.use_byte && nlo > 0 && sh->n_ut > 0) {
             const int nut = sh->n_ut;
-            if (tid == 0) sh->maxflag = 0;
+            if (tid == 0) { sh->maxflag = 0; sh->dmax_bits = 0ull; }
             __syncthreads();
             const bool dr = nlo <= nut;
             const int l2 = lap_pitch(dr ? nut : nlo);
+            if (prm.asso == TK_ASSO_CT_DIST) {
+                for (int e = tid; e < nlo * nut; e += OC_THREADS) {
+                    const double dd = centre_dist(D + (size_t)d_lo[e / nut] * 7, trk_box + 4 * un_t[e % nut]);
+                    iou_m[e] = dd;
+                    atomicMax(&sh->dmax_bits, (unsigned long long)__double_as_longlong(dd));
+                }
+                __syncthreads();
+            }
+            const double dmax = __longlong_as_double((long long)sh->dmax_bits);
             for (int e = tid; e < nlo * nut; e += OC_THREADS) {
                 const int d = e / nut, t = e % nut;
-                const double v = asso_value(prm.asso, D + (size_t)d_lo[d] * 7, trk_box + 4 * un_t[t]);
+                const double v = prm.asso == TK_ASSO_CT_DIST ? 1.0 - iou_m[e] / dmax
+                                                             : asso_value(prm.asso, D + (size_t)d_lo[d] * 7, trk_box + 4 * un_t[t]);
                 iou_m[(size_t)d * nut + t] = v;
                 if (dr) cost[(size_t)d * l2 + t] = -v; else cost[(size_t)t * l2 + d] = -v;
                 if (v > prm.iou_threshold) sh->maxflag = 1;
@@ -538,13 +556,23 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
         // ---- OCR round on the last observations (ocsort.py:284-306) -----------------------------------
         if (sh->n_ud > 0 && sh->n_ut > 0) {
             const int nud = sh->n_ud, nut = sh->n_ut;
-            if (tid == 0) sh->maxflag = 0;
+            if (tid == 0) { sh->maxflag = 0; sh->dmax_bits = 0ull; }
             __syncthreads();
             const bool dr = nud <= nut;
             const int l2 = lap_pitch(dr ? nut : nud);
+            if (prm.asso == TK_ASSO_CT_DIST) {
+                for (int e = tid; e < nud * nut; e += OC_THREADS) {
+                    const double dd = centre_dist(D + (size_t)d_hi[un_d[e / nut]] * 7, S.last_obs + (size_t)S.list[un_t[e % nut]] * 5);
+                    iou_m[e] = dd;
+                    atomicMax(&sh->dmax_bits, (unsigned long long)__double_as_longlong(dd));
+                }
+                __syncthreads();
+            }
+            const double dmax = __longlong_as_double((long long)sh->dmax_bits);
             for (int e = tid; e < nud * nut; e += OC_THREADS) {
                 const int d = e / nut, t = e % nut;
-                const double v = asso_value(prm.asso, D + (size_t)d_hi[un_d[d]] * 7, S.last_obs + (size_t)S.list[un_t[t]] * 5);
+                const double v = prm.asso == TK_ASSO_CT_DIST ? 1.0 - iou_m[e] / dmax
+                                                             : asso_value(prm.asso, D + (size_t)d_hi[un_d[d]] * 7, S.last_obs + (size_t)S.list[un_t[t]] * 5);
                 iou_m[(size_t)d * nut + t] = v;
                 if (dr) cost[(size_t)d * l2 + t] = -v; else cost[(size_t)t * l2 + d] = -v;
                 if (v > prm.iou_threshold) sh->maxflag = 1;
@@ -697,7 +725,7 @@ extern "C" {
 int tk_ocsort_create(const tk_ocsort_params* p, int n_seq, int cap_tracks, int cap_dets, void** handle) {
     if (!p || !handle || n_seq <= 0 || cap_tracks <= 0 || cap_dets <= 0) return TK_ERR_ARG;
     if (cap_tracks > tk::LAP_MAX_COLS || cap_dets > tk::LAP_MAX_COLS) return TK_ERR_CAPACITY;
-    if (p->delta_t < 1 || p->delta_t > RING || p->asso_func < 0 || p->asso_func > 3) return TK_ERR_ARG;
+    if (p->delta_t < 1 || p->delta_t > RING || p->asso_func < 0 || p->asso_func > TK_ASSO_CT_DIST) return TK_ERR_ARG;
     OcHandle* h = new OcHandle();
     h->prm.det_thresh = p->det_thresh; h->prm.iou_threshold = p->iou_threshold; h->prm.inertia = p->inertia;
     h->prm.min_conf = p->min_confidence; h->prm.max_age = p->max_age; h->prm.min_hits = p->min_hits;

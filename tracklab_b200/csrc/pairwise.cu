@@ -185,13 +185,44 @@ lap_batched_kernel(const double* __restrict__ cost, int N, int M, double cost_li
     }
 }
 
+// ct_dist (association.py:150-171): one CTA per problem — centre distances, block maximum, 1 - d / d.max()
+__global__ void __launch_bounds__(256)
+ct_dist_matrix_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int N, int M) {
+    __shared__ unsigned long long s_max;
+    const int p = blockIdx.x;
+    const double* ap = a + (size_t)p * N * 4;
+    const double* bp = b + (size_t)p * M * 4;
+    double* op = out + (size_t)p * N * M;
+    if (threadIdx.x == 0) s_max = 0ull;
+    __syncthreads();
+    unsigned long long lm = 0ull;
+    for (int e = threadIdx.x; e < N * M; e += blockDim.x) {
+        const int i = e / M, j = e - i * M;
+        const double dx = (ap[4 * i] + ap[4 * i + 2]) / 2.0 - (bp[4 * j] + bp[4 * j + 2]) / 2.0;
+        const double dy = (ap[4 * i + 1] + ap[4 * i + 3]) / 2.0 - (bp[4 * j + 1] + bp[4 * j + 3]) / 2.0;
+        const double d = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        op[e] = d;
+        const unsigned long long k = (unsigned long long)__double_as_longlong(d);   // d >= 0: bit order = value order
+        lm = k > lm ? k : lm;
+    }
+    atomicMax(&s_max, lm);
+    __syncthreads();
+    const double dmax = __longlong_as_double((long long)s_max);
+    for (int e = threadIdx.x; e < N * M; e += blockDim.x) op[e] = 1.0 - op[e] / dmax;
+}
+
 }  // namespace
 
 extern "C" {
 
 int tk_iou_matrix(const double* a, const double* b, double* out, int n_problems, int N, int M, int variant, void* stream) {
-    if (!a || !b || !out || n_problems <= 0 || N < 0 || M < 0 || variant < 0 || variant > 3) return TK_ERR_ARG;
+    if (!a || !b || !out || n_problems <= 0 || N < 0 || M < 0 || variant < 0 || variant > TK_ASSO_CT_DIST) return TK_ERR_ARG;
     if (N == 0 || M == 0) return TK_OK;
+    if (variant == TK_ASSO_CT_DIST) {
+        ct_dist_matrix_kernel<<<n_problems, 256, 0, (cudaStream_t)stream>>>(a, b, out, N, M);
+        TK_CUDA_TRY(cudaGetLastError());
+        return TK_OK;
+    }
     const size_t smem = sizeof(double) * 4 * ((size_t)M + 32);
     if (smem > 200 * 1024) return TK_ERR_CAPACITY;
     TK_CUDA_TRY(cudaFuncSetAttribute(iou_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -117,7 +117,7 @@ class OCSortDevice(_VideoTrackerDevice):
                  asso_func="giou", inertia=0.3941737016672115, use_byte=False, min_confidence=0.4,
                  n_seq=1, cap_tracks=128, cap_dets=128, device="cuda:0"):
         if asso_func not in _lib.ASSO_CODES:
-            raise _lib.TrackKernError(f"asso_func {asso_func!r} not supported on device (iou/giou/diou/ciou)")
+            raise _lib.TrackKernError(f"asso_func {asso_func!r} not supported on device (iou/giou/diou/ciou/ct_dist)")
         self._create(_lib.OcsortParams(det_thresh, iou_threshold, inertia, min_confidence, max_age, min_hits, delta_t,
                                        _lib.ASSO_CODES[asso_func], int(bool(use_byte))), n_seq, cap_tracks, cap_dets, device)
 
