@@ -72,6 +72,23 @@ int tk_crop_resize_norm(const unsigned char* frames, int H, int W, long long fra
                         const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,
                         const float* mean3, const float* std3, void* stream);
 
+/* ---- RT-DETR detector pre/post-processing ---------------------------------------------------------------------
+ * Replace transformers' RTDetrImageProcessor around the model call of
+ * /root/reference/tracklab/wrappers/bbox_detector/transformers_api.py:31-54.
+ *   tk_resize_frames_u8  frames uint8 [n,H,W,3] -> out [n,3,out_h,out_w] (float32 / bf16) = resize(frame) * scale:
+ *                        Pillow's antialiased bilinear resampler evaluated exactly (the processor of the pinned
+ *                        transformers 4.52; the torchvision backend of 5.x differs from Pillow by at most one 8-bit step).
+ *   tk_rtdetr_decode     post_process_object_detection (sigmoid focal scores, top-Q over Q*C, cxcywh -> absolute xyxy in
+ *                        float32, score > threshold) + the wrapper's class filter and sanitize/ltwh conversion
+ *                        (utils/coordinates.py:270-328): logits [n,Q,C] float32, boxes [n,Q,4] float32 ->
+ *                        rows float64 [n, Q, 6] = [l, t, w, h, score, query index] in descending score order and
+ *                        counts int32 [n]. keep_label < 0 keeps every class (the 6th column then holds label * Q + query).
+ */
+int tk_resize_frames_u8(const unsigned char* frames, int n_frames, int H, int W, long long frame_stride_bytes, void* out,
+                        int out_dtype, int out_h, int out_w, float scale, void* stream);
+int tk_rtdetr_decode(const float* logits, const float* boxes, int n_images, int n_queries, int n_classes, int img_w, int img_h,
+                     float threshold, int keep_label, double* rows_out, int* counts_out, void* stream);
+
 /* ---- Pooling passes of the ReID backbone (channels-last bf16) ----------------------------------------------
  * tk_maxpool3x3s2_nhwc: src [N,H,W,C] -> dst [N,(H+1)/2,(W+1)/2,C], 3x3 window, stride 2, padding 1 (-inf), i.e.
  *                       nn.MaxPool2d(3, 2, 1) after the stem (/root/reference/plugins/track/strong_sort/deep/models/resnet.py:349)

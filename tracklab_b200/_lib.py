@@ -66,6 +66,8 @@ def _declare(lib):
         "tk_bias_act_nhwc": ([vp, vp, vp, vp, ctypes.c_longlong, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_spp_nhwc": ([vp, vp, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_upsample2x_nhwc": ([vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, vp], ci),
+        "tk_resize_frames_u8": ([vp, ci, ci, ci, ctypes.c_longlong, vp, ci, ci, ci, ctypes.c_float, vp], ci),
+        "tk_rtdetr_decode": ([vp, vp, ci, ci, ci, ci, ci, ctypes.c_float, ci, vp, vp, vp], ci),
         "tk_maxpool3x3s2_nhwc": ([vp, ci, ci, ci, ci, vp, vp], ci),
         "tk_avgpool_nhwc": ([vp, ci, ci, ci, vp, vp], ci),
         "tk_iou_matrix": ([vp, vp, vp, ci, ci, ci, ci, vp], ci),

@@ -414,7 +414,55 @@ crop_resize_norm_kernel(const unsigned char* __restrict__ frames, size_t frame_s
     }
 }
 
+// Whole-frame Pillow-exact antialiased bilinear resize (no aspect preservation) + rescale: the RT-DETR image processor
+// (transformers RTDetrImageProcessor: resize to 640x640, x 1/255, no normalisation) behind
+// /root/reference/tracklab/wrappers/bbox_detector/transformers_api.py:32. One CTA per (output row, frame); planar output.
+template <typename OutT>
+__global__ void __launch_bounds__(128)
+resize_frames_kernel(const unsigned char* __restrict__ frames, size_t frame_stride, int H, int W, OutT* __restrict__ out,
+                     int out_h, int out_w, float scale) {
+    __shared__ int kv[CR_KMAX];
+    __shared__ int s_ymin, s_ny;
+    const int n = blockIdx.y, yy = blockIdx.x;
+    const unsigned char* img = frames + (size_t)n * frame_stride;
+    if (threadIdx.x == 0) { int ym; s_ny = pil_taps(H, out_h, yy, kv, ym); s_ymin = ym; }
+    __syncthreads();
+    for (int xx = threadIdx.x; xx < out_w; xx += blockDim.x) {
+        int kh[CR_KMAX], xmin;
+        const int nx = pil_taps(W, out_w, xx, kh, xmin);
+        int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+        for (int ky = 0; ky < s_ny; ++ky) {
+            const unsigned char* row = img + ((size_t)(s_ymin + ky) * W + xmin) * 3;
+            int h[3] = {1 << 21, 1 << 21, 1 << 21};
+            for (int kx = 0; kx < nx; ++kx) {
+                h[0] += row[kx * 3 + 0] * kh[kx]; h[1] += row[kx * 3 + 1] * kh[kx]; h[2] += row[kx * 3 + 2] * kh[kx];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[c] += clip8(h[c]) * kv[ky];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            out[(((size_t)n * 3 + c) * out_h + yy) * out_w + xx] = cvt_out<OutT>(__fmul_rn((float)clip8(acc[c]), scale));
+    }
+}
+
 }  // namespace
+
+extern "C" int tk_resize_frames_u8(const unsigned char* frames, int n_frames, int H, int W, long long frame_stride_bytes, void* out,
+                                   int out_dtype, int out_h, int out_w, float scale, void* stream) {
+    if (!frames || !out || n_frames < 0 || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0) return TK_ERR_ARG;
+    if (out_dtype != TK_DTYPE_F32 && out_dtype != TK_DTYPE_BF16) return TK_ERR_ARG;
+    if (n_frames == 0) return TK_OK;
+    if (2 * ((W + out_w - 1) / out_w) + 1 > CR_KMAX || 2 * ((H + out_h - 1) / out_h) + 1 > CR_KMAX) return TK_ERR_CAPACITY;
+    dim3 grid(out_h, n_frames);
+    if (out_dtype == TK_DTYPE_F32)
+        resize_frames_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(frames, (size_t)frame_stride_bytes, H, W, (float*)out, out_h, out_w, scale);
+    else
+        resize_frames_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)stream>>>(frames, (size_t)frame_stride_bytes, H, W, (__nv_bfloat16*)out, out_h,
+                                                                                  out_w, scale);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
 
 extern "C" int tk_crop_resize_norm(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,
                                    const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,

@@ -110,6 +110,33 @@ def bias_act(src: torch.Tensor, bias: torch.Tensor, dst: torch.Tensor, dst_offse
     return dst
 
 
+def resize_frames(frames: torch.Tensor, out_hw=(640, 640), out_dtype=torch.float32, scale: float = 1.0 / 255.0) -> torch.Tensor:
+    """frames uint8 [n,H,W,3] -> [n,3,h,w] = PIL-bilinear(frame) * scale (RTDetrImageProcessor; C ABI: tk_resize_frames_u8)."""
+    lib = _lib.load()
+    _cuda(frames, "frames")
+    n, H, W, _ = frames.shape
+    out = torch.empty((n, 3, out_hw[0], out_hw[1]), dtype=out_dtype, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _lib.check(lib.tk_resize_frames_u8(frames.data_ptr(), n, H, W, frames.stride(0), out.data_ptr(), _dtype_code(out_dtype), out_hw[0],
+                                           out_hw[1], scale, _stream()), "tk_resize_frames_u8"); _count()
+    return out
+
+
+def rtdetr_decode(logits: torch.Tensor, boxes: torch.Tensor, image_wh, threshold: float, keep_label: int = 0):
+    """logits float32 [n,Q,C], boxes float32 [n,Q,4] (cxcywh, relative) -> (rows float64 [n,Q,6] = [l,t,w,h,score,query],
+    counts int32 [n]) in descending score order (C ABI: tk_rtdetr_decode)."""
+    lib = _lib.load()
+    _cuda(logits, "logits"); _cuda(boxes, "boxes")
+    assert logits.dtype == torch.float32 and boxes.dtype == torch.float32 and logits.is_contiguous() and boxes.is_contiguous()
+    n, Q, C = logits.shape
+    rows = torch.empty((n, Q, 6), dtype=torch.float64, device=logits.device)
+    counts = torch.empty((n,), dtype=torch.int32, device=logits.device)
+    with torch.cuda.device(logits.device):
+        _lib.check(lib.tk_rtdetr_decode(logits.data_ptr(), boxes.data_ptr(), n, Q, C, int(image_wh[0]), int(image_wh[1]), float(threshold),
+                                        int(keep_label), rows.data_ptr(), counts.data_ptr(), _stream()), "tk_rtdetr_decode"); _count()
+    return rows, counts
+
+
 def maxpool3x3s2(x: torch.Tensor) -> torch.Tensor:
     """nn.MaxPool2d(3, 2, 1) on a bf16 channels-last [N,C,H,W] tensor (C ABI: tk_maxpool3x3s2_nhwc)."""
     lib = _lib.load()

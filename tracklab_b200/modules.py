@@ -441,3 +441,52 @@ class BPBReIDStrongSORT(ImageLevelModule):
 
 
 _bind_from(BPBReIDStrongSORT, _BpbreidImpl)
+
+
+# ---- RT-DETR detector (transformers flavour of the bbox_detector step) -------------------------------------------------
+class RTDetr(ImageLevelModule):
+    """Drop-in for tracklab.wrappers.bbox_detector.transformers_api.RTDetr: same constructor, columns, running detection id and
+    row contents; resize, model and post-processing run on the device for the whole batch (tk_resize_frames_u8 ->
+    RTDetrForObjectDetection -> tk_rtdetr_decode). ``model_name`` selects the architecture; weights come from ``weights``
+    (a state_dict file) or are seeded (there is no network for ``from_pretrained``)."""
+    input_columns = []
+    output_columns = ["image_id", "video_id", "category_id", "bbox_ltwh", "bbox_conf"]
+
+    def __init__(self, device, batch_size, model_name="rtdetr_r50vd_coco_o365", min_confidence=0.4, weights=None, precision="bf16",
+                 seed=1234, **kwargs):
+        super().__init__(batch_size)
+        if not torch.cuda.is_available():
+            raise _lib.TrackKernError("RTDetr needs a CUDA device: tracklab_b200 has no CPU path")
+        if "r50vd" not in model_name or "v2" in model_name:
+            raise _lib.TrackKernError(f"{model_name}: only the r50vd RT-DETR architecture is built (configs/modules/bbox_detector/rtdetr_transformers.yaml)")
+        from .nets.rtdetr import build_rtdetr
+        from .rtdetr_detector import RTDetrDetectorDevice
+        self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
+        sd = torch.load(str(weights), map_location="cpu") if weights is not None and os.path.isfile(str(weights)) else None
+        self.detector = RTDetrDetectorDevice(self.device, min_confidence, precision, model=build_rtdetr(seed, state_dict=sd))
+        self._calibrate = sd is None     # seeded weights: the person bias is set on the first batch (nets/rtdetr.py)
+        self.min_confidence = min_confidence
+        self.id = 0
+
+    @torch.no_grad()
+    def preprocess(self, image, detections: pd.DataFrame, metadata: pd.Series):
+        return image
+
+    @torch.no_grad()
+    def process(self, batch, detections: pd.DataFrame, metadatas: pd.DataFrame):
+        frames = torch.as_tensor(batch)
+        if frames.dim() == 3:
+            frames = frames[None]
+        frames = frames.to(self.device, non_blocking=True).contiguous()
+        if self._calibrate:
+            self.detector.calibrate(frames[:1])
+            self._calibrate = False
+        rows, counts = self.detector.detect_batch(frames)
+        rows, counts = rows.cpu().numpy(), counts.cpu().numpy()        # one read per batch
+        out = []
+        for i in range(len(counts)):
+            for r in rows[i, :counts[i]]:
+                out.append(pd.Series(dict(image_id=metadatas["id"].values[i], bbox_ltwh=r[:4].astype(np.float32), bbox_conf=float(r[4]),
+                                          video_id=metadatas["video_id"].values[i], category_id=1), name=self.id))
+                self.id += 1
+        return out
