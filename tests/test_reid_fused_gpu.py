@@ -65,3 +65,21 @@ def test_fused_resnet_matches_fp32_module(use_graphs):
     assert got.shape == ref.shape and float(cos.min()) > 0.999, float(cos.min())
     rel = (got - ref).norm(dim=1) / ref.norm(dim=1)
     assert float(rel.max()) < 0.05, float(rel.max())
+
+
+@pytest.mark.parametrize("arch", ["osnet_x1_0", "osnet_ibn_x1_0"])
+def test_osnet_stage_bf16_matches_fp32_module(arch):
+    """OSNet flavours (the StrongSORT YAML default is osnet_ibn_x1_0): bf16 channels-last under a CUDA graph vs the fp32 module."""
+    from tracklab_b200.reid import ReidStageDevice
+    from tracklab_b200.synth import make_frames, make_video
+    v = make_video(seed=79, n_frames=4, n_ids=25)
+    frames = make_frames(v, 0, 4, device="cuda")
+    dets = torch.from_numpy(v.dets).cuda()
+    det_frame = torch.from_numpy(np.repeat(np.arange(4), np.diff(v.offsets)).astype(np.int32)).cuda()
+    ref = ReidStageDevice(precision="fp32", arch=arch).features(frames, dets, det_frame)
+    stage = ReidStageDevice(precision="bf16", arch=arch)
+    for _ in range(2):
+        got = stage.features(frames, dets, det_frame)
+    assert got.shape == ref.shape == (dets.shape[0], 512)
+    cos = torch.nn.functional.cosine_similarity(got, ref, dim=1)
+    assert float(cos.min()) > 0.995, float(cos.min())

@@ -10,11 +10,12 @@ from tracklab_b200.synth import make_frames, make_video
 n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 precision = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 legacy = len(sys.argv) > 3 and sys.argv[3] == "legacy"
+arch = sys.argv[4] if len(sys.argv) > 4 else "resnet50"
 video = make_video(seed=3000, n_frames=n_frames, n_ids=44)
 frames = make_frames(video, 0, n_frames, device="cuda")
 dets = torch.from_numpy(video.dets).cuda()
 det_frame = torch.from_numpy(np.repeat(np.arange(n_frames), np.diff(video.offsets)).astype(np.int32)).cuda()
-reid = ReidStageDevice(precision=precision, legacy=legacy)
+reid = ReidStageDevice(precision=precision, legacy=legacy, arch=arch)
 for _ in range(3): reid.features(frames, dets, det_frame)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

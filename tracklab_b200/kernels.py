@@ -239,7 +239,7 @@ REID_STD = (0.229, 0.224, 0.225)
 
 def crop_resize_norm(frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.Tensor, out_hw=(256, 128),
                      out_dtype=torch.float32, channels_last: bool = False, mean=REID_MEAN, std=REID_STD, pad_channels_to: int = 3,
-                     s2d16_out: torch.Tensor | None = None):
+                     s2d16_out: torch.Tensor | None = None, out: torch.Tensor | None = None):
     """frames uint8 [F,H,W,3], dets float64 [N,7], det_frame int32 [N] -> ReID input [N,3,h,w] (C ABI: tk_crop_resize_norm).
     pad_channels_to=8 (channels-last only) returns [N,8,h,w] with zero channels 3..7 for the fused backbone."""
     lib = _lib.load()
@@ -257,7 +257,10 @@ def crop_resize_norm(frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.
                                                s2d16_out.data_ptr(), _dtype_code(s2d16_out.dtype), -16, out_hw[0], out_hw[1], m, sd,
                                                _stream()), "tk_crop_resize_norm"); _count()
         return s2d16_out
-    if pad_channels_to != 3:
+    if out is not None:   # caller-owned (bucket-sized) buffer: the first N crops are written
+        assert out.shape[0] >= N and out.dtype == out_dtype and pad_channels_to == 3
+        assert out.is_contiguous(memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+    elif pad_channels_to != 3:
         assert channels_last
         out = torch.zeros((N, pad_channels_to, out_hw[0], out_hw[1]), dtype=out_dtype,
                           device=frames.device).contiguous(memory_format=torch.channels_last)

@@ -213,13 +213,16 @@ class _StrongSortImpl:
         self.decode_batch = int(_cfg_get(cfg, "decode_batch", 16))
         self.hyper = dict(_cfg_get(cfg, "hyperparams", {}) or {})
         self.min_confidence = float(_cfg_get(cfg, "min_confidence", 0.4))
-        model = None
+        # the plugin's factory reads the architecture from the weights file name (deep/reid_model_factory.py:122-127)
         weights = _cfg_get(cfg, "model_weights", None)
-        if weights is not None and os.path.isfile(str(weights)):   # a reference-format ResNet-50 state_dict (conv + BN)
-            from .nets.resnet_reid import ResNet50ReID
+        name = os.path.basename(str(weights)) if weights is not None else ""
+        arch = _cfg_get(cfg, "reid_arch", None) or next((a for a in ("osnet_ibn_x1_0", "osnet_x1_0", "resnet50") if a in name), "resnet50")
+        model = None
+        if weights is not None and os.path.isfile(str(weights)):   # a reference-format state_dict (conv + BN), folded on load
+            from .reid import build_reid_model
             sd = torch.load(str(weights), map_location="cpu")
-            model = ResNet50ReID().eval().from_reference_state_dict(sd.get("state_dict", sd))
-        self.reid = ReidStageDevice(device=self.device, model=model, precision=_cfg_get(cfg, "reid_precision", "bf16"))
+            model = build_reid_model(arch).from_reference_state_dict(sd.get("state_dict", sd))
+        self.reid = ReidStageDevice(device=self.device, model=model, precision=_cfg_get(cfg, "reid_precision", "bf16"), arch=arch)
         self._trk_cls = StrongSortDevice
         self.tracker = None
         self._pipe = _TrackerDatapipe(self, self.frames_per_batch)
