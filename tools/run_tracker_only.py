@@ -33,3 +33,12 @@ if hasattr(lib, "tk_debug_bytetrack_phases") and kind == "bytetrack":
     lib.tk_debug_bytetrack_phases(buf, 0)
     tot = sum(buf)
     print("phase cycles/frame:", {k: int(v / F) for k, v in enumerate(buf) if v}, "total", int(tot / F))
+if hasattr(lib, "tk_debug_ocsort_phases") and kind == "ocsort":
+    buf = (ctypes.c_ulonglong * 64)()
+    lib.tk_debug_ocsort_phases(buf, 1)
+    trk.reset(); trk.run(dets, offs); torch.cuda.synchronize()
+    lib.tk_debug_ocsort_phases(buf, 0)
+    names = ["split", "predict", "drop", "kobs", "cost1", "lap1", "rnd1_lists(4->6)", "byte", "ocr", "miss+birth", "update1", "out+death"]
+    order = [0, 1, 2, 3, 4, 5, 10, 6, 7, 8, 9, 11]
+    print("ocsort phase cycles/frame:", ", ".join(f"{names[k]} {buf[k] / F:.0f}" for k in order), "| total", int(sum(buf) / F),
+          "| cost1 split: init+precompute", int(buf[12] / F), "main loop (thread 0)", int(buf[13] / F), "wait", int(buf[4] / F))

@@ -20,6 +20,14 @@ namespace {
 
 using namespace tk;
 
+// Optional per-phase cycle accounting (build with -DTK_PHASE_PROF), read with tk_debug_ocsort_phases().
+#ifdef TK_PHASE_PROF
+__device__ unsigned long long g_oc_prof[64];
+#define PH(k) do { if (threadIdx.x == 0) { const long long _t = clock64(); g_oc_prof[k] += (unsigned long long)(_t - ph_t0); ph_t0 = _t; } } while (0)
+#else
+#define PH(k) do { } while (0)
+#endif
+
 constexpr int OC_THREADS = 128;
 constexpr int RING = 8;  // observations kept per track: ages age-1 .. age-RING (delta_t <= RING)
 
@@ -110,70 +118,132 @@ __device__ void kf7_predict(double* x, double* P) {
     for (int i = 0; i < 7; ++i) P[i * 8] = P[i * 8] + q[i];
 }
 
-__device__ bool kf7_correct(double* x, double* P, const double* z) {
+// ---- group-cooperative measurement update: 8 consecutive lanes own one track, lane j < 7 holds row j of P and x[j] ----
+// KalmanFilterNew.update (kalmanfilter.py:488-526): S = H P H^T + R, K = P H^T S^-1 (S^-1 through its Cholesky factor),
+// x += K y, P = (I-KH) P (I-KH)^T + K R K^T. A single thread doing the two 7x7x7 products of the Joseph form keeps ~150
+// doubles live and spills to local memory (~55 us per frame incl. the ORU replays); row-per-lane keeps everything in registers.
+__device__ __forceinline__ double grp_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src, 8); }
+
+// row[7] / xj: this lane's row of P and element of x (identity rows on idle lanes); the result is committed when `on`.
+__device__ __forceinline__ bool kf7_group_correct(double (&row_io)[7], double& xj_io, bool on, const double* z) {
+    const int j = threadIdx.x & 7;
+    double row[7], xj = xj_io;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) row[c] = row_io[c];
     const double R[4] = {1.0, 1.0, 10.0, 10.0};
     double S[16], L[16], Li[16], SI[16];
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) S[i * 4 + j] = (i == j) ? P[i * 7 + j] + R[i] : P[i * 7 + j];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { const double v = grp_bcast(row[b], a); S[a * 4 + b] = (a == b) ? v + R[a] : v; }
+    // S^-1 through the Cholesky factor with reciprocal pivots: one rsqrt per column is the only long-latency operation on the
+    // dependency chain (the reference inverts S with LAPACK's LU, so no operation order can be bit-identical anyway; the
+    // result differs from it by a few ulp either way, tests compare boxes at 1e-6 px).
     bool ok = true;
-    for (int j = 0; j < 4; ++j) {  // Cholesky S = L L^T
-        double d = S[j * 4 + j];
-        for (int k = 0; k < j; ++k) d -= L[j * 4 + k] * L[j * 4 + k];
+    double invd[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double d = S[c * 4 + c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) d -= L[c * 4 + k] * L[c * 4 + k];
         ok = ok && d > 0.0;
-        const double ljj = sqrt(d);
-        L[j * 4 + j] = ljj;
-        for (int i = j + 1; i < 4; ++i) {
-            double s = S[i * 4 + j];
-            for (int k = 0; k < j; ++k) s -= L[i * 4 + k] * L[j * 4 + k];
-            L[i * 4 + j] = s / ljj;
+        invd[c] = rsqrt(d);
+        L[c * 4 + c] = d * invd[c];
+#pragma unroll
+        for (int i = c + 1; i < 4; ++i) {
+            double t = S[i * 4 + c];
+#pragma unroll
+            for (int k = 0; k < c; ++k) t -= L[i * 4 + k] * L[c * 4 + k];
+            L[i * 4 + c] = t * invd[c];
         }
-        for (int i = 0; i < j; ++i) L[i * 4 + j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < c; ++i) L[i * 4 + c] = 0.0;
     }
+#pragma unroll
     for (int c = 0; c < 4; ++c) {  // Li = L^-1 (lower)
+#pragma unroll
         for (int i = 0; i < 4; ++i) {
-            double s = (i == c) ? 1.0 : 0.0;
-            for (int k = c; k < i; ++k) s -= L[i * 4 + k] * Li[k * 4 + c];
-            Li[i * 4 + c] = (i < c) ? 0.0 : s / L[i * 4 + i];
+            double t = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int k = c; k < i; ++k) t -= L[i * 4 + k] * Li[k * 4 + c];
+            Li[i * 4 + c] = (i < c) ? 0.0 : t * invd[i];
         }
     }
+#pragma unroll
     for (int i = 0; i < 4; ++i)   // SI = Li^T Li
-        for (int j = 0; j < 4; ++j) {
-            double s = 0.0;
-            for (int k = (i > j ? i : j); k < 4; ++k) s += Li[k * 4 + i] * Li[k * 4 + j];
-            SI[i * 4 + j] = s;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = (i > b ? i : b); k < 4; ++k) t += Li[k * 4 + i] * Li[k * 4 + b];
+            SI[i * 4 + b] = t;
         }
-    double K[28], y[4];
-    for (int i = 0; i < 4; ++i) y[i] = z[i] - x[i];
-    for (int a = 0; a < 7; ++a)
-        for (int j = 0; j < 4; ++j) {
-            double s = 0.0;
-            for (int k = 0; k < 4; ++k) s += P[a * 7 + k] * SI[k * 4 + j];
-            K[a * 4 + j] = s;
-        }
-    for (int a = 0; a < 7; ++a) {
-        double s = 0.0;
-        for (int k = 0; k < 4; ++k) s += K[a * 4 + k] * y[k];
-        x[a] = x[a] + s;
+    double K[4], y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = z[i] - grp_bcast(xj, i);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t += row[k] * SI[k * 4 + b];
+        K[b] = t;
     }
-    // P = (I-KH) P (I-KH)^T + K R K^T   (Joseph form, kalmanfilter.py:520-521)
-    double A[49], AP[49];
-    for (int a = 0; a < 7; ++a)
-        for (int b = 0; b < 7; ++b) A[a * 7 + b] = ((a == b) ? 1.0 : 0.0) - (b < 4 ? K[a * 4 + b] : 0.0);
-    for (int a = 0; a < 7; ++a)
-        for (int b = 0; b < 7; ++b) {
-            double s = 0.0;
-            for (int k = 0; k < 7; ++k) s += A[a * 7 + k] * P[k * 7 + b];
-            AP[a * 7 + b] = s;
-        }
-    for (int a = 0; a < 7; ++a)
-        for (int b = 0; b < 7; ++b) {
-            double s = 0.0;
-            for (int k = 0; k < 7; ++k) s += AP[a * 7 + k] * A[b * 7 + k];
-            double r = 0.0;
-            for (int k = 0; k < 4; ++k) r += (K[a * 4 + k] * R[k]) * K[b * 4 + k];
-            P[a * 7 + b] = s + r;
-        }
-    return ok;
+    {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t += K[k] * y[k];
+        xj = xj + t;
+    }
+    // P = (I-KH) P (I-KH)^T + K R K^T   (Joseph form, kalmanfilter.py:520-521), row j on lane j
+    double A[7], AP[7];
+#pragma unroll
+    for (int b = 0; b < 7; ++b) A[b] = ((j == b) ? 1.0 : 0.0) - (b < 4 ? K[b] : 0.0);
+#pragma unroll
+    for (int b = 0; b < 7; ++b) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t += A[k] * grp_bcast(row[b], k);
+        AP[b] = t;
+    }
+#pragma unroll
+    for (int b = 0; b < 7; ++b) {   // column b needs row b of A and of K, i.e. K of lane b
+        double Kb[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Kb[k] = grp_bcast(K[k], b);
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) t += AP[k] * (((b == k) ? 1.0 : 0.0) - (k < 4 ? Kb[k] : 0.0));
+        double r = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r += (K[k] * R[k]) * Kb[k];
+        row[b] = t + r;
+    }
+    if (on) {
+        xj_io = xj;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) row_io[c] = row[c];
+    }
+    return ok || !on;
+}
+
+// KalmanFilterNew.predict on the group registers (kf7_predict): rows 0..2 += rows 4..6, columns 0..2 += columns 4..6, + Q
+__device__ __forceinline__ void kf7_group_predict(double (&row)[7], double& xj, bool on) {
+    const int j = threadIdx.x & 7;
+    const double xh = grp_bcast(xj, (j + 4) & 7);
+    double hi[7];
+#pragma unroll
+    for (int c = 0; c < 7; ++c) hi[c] = grp_bcast(row[c], (j + 4) & 7);
+    if (!on) return;
+    if (j < 3) {
+        xj = xj + xh;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) row[c] = row[c] + hi[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) row[c] = row[c] + row[c + 4];
+    const double q[7] = {1.0, 1.0, 1.0, 1.0, 0.01, 0.01, 0.01 * 0.01};
+#pragma unroll
+    for (int c = 0; c < 7; ++c) if (c == j) row[c] = row[c] + q[c];
 }
 
 __device__ __forceinline__ void box_to_z(const double* b, double* z) {  // ocsort.py:21-33
@@ -187,8 +257,19 @@ __device__ __forceinline__ void x_to_box(const double* x, double* b) {  // ocsor
     b[0] = x[0] - w / 2.0; b[1] = x[1] - h / 2.0; b[2] = x[0] + w / 2.0; b[3] = x[1] + h / 2.0;
 }
 
-// KalmanBoxTracker.update(bbox) incl. KalmanFilterNew.update with the ORU replay (ocsort.py:103-148)
-__device__ void oc_track_update(OcDev& S, int s, const double* bbox5, double cls, double det_id, int delta_t, int* status) {
+// KalmanBoxTracker.update(bbox) (ocsort.py:103-148): book-keeping; KalmanFilterNew.update incl. the ORU replay when the track
+// was frozen. Returns the Kalman work left for oc_apply_updates: 1 = plain correction with z_out, 2 = ORU replay (parameters in
+// oru_par / oru_gap) followed by the correction.
+// i-th virtual measurement of the ORU line (kalmanfilter.py:412-421), par = {x1, y1, w1, h1, dx, dy, dw, dh}
+__device__ __forceinline__ void oru_virtual_z(const double* par, int i, double* vz) {
+    const double t = (double)(i + 1);
+    const double ww = __dadd_rn(par[2], __dmul_rn(t, par[6])), hh = __dadd_rn(par[3], __dmul_rn(t, par[7]));
+    vz[0] = __dadd_rn(par[0], __dmul_rn(t, par[4])); vz[1] = __dadd_rn(par[1], __dmul_rn(t, par[5]));
+    vz[2] = __dmul_rn(ww, hh); vz[3] = ww / hh;
+}
+
+__device__ int oc_track_update(OcDev& S, int s, const double* bbox5, double cls, double det_id, int delta_t, double* z_out, double* oru_par,
+                               int* oru_gap) {
     double* lo = S.last_obs + (size_t)s * 5;
     const int age = S.age[s];
     S.conf[s] = bbox5[4];
@@ -221,16 +302,13 @@ __device__ void oc_track_update(OcDev& S, int s, const double* bbox5, double cls
     S.streak[s] += 1;
     S.det_id[s] = det_id;
     // ---- KalmanFilterNew.update(z) (kalmanfilter.py:437-526)
-    double z[4], x[7], P[49];
+    double z[4];
     box_to_z(bbox5, z);
-    double* gx = S.x + (size_t)s * 7;
-    double* gP = S.P + (size_t)s * 49;
+    if (z_out) { for (int k = 0; k < 4; ++k) z_out[k] = z[k]; }
     int hist = S.hist_len[s] + 1;   // history_obs.append(z)
-    bool ok = true;
     if (!S.observed[s] && S.frozen[s]) {
-        // unfreeze (kalmanfilter.py:390-434): restore, interpolate between the last stored observation and z
-        for (int k = 0; k < 7; ++k) x[k] = S.fx[(size_t)s * 7 + k];
-        for (int k = 0; k < 49; ++k) P[k] = S.fP[(size_t)s * 49 + k];
+        // unfreeze (kalmanfilter.py:390-434): the filter is restored to the frozen state and replayed over a straight line of
+        // virtual boxes between the last stored observation and z (ORU); the replay itself runs in oc_apply_updates.
         const int i1 = S.last_z_idx[s], i2 = hist - 1;
         const double* b1 = S.last_z + (size_t)s * 4;
         const double x1 = b1[0], y1 = b1[1], s1 = b1[2], r1 = b1[3];
@@ -239,32 +317,86 @@ __device__ void oc_track_update(OcDev& S, int s, const double* bbox5, double cls
         const int gap = i2 - i1;
         const double dg = (double)gap;
         const double dx = (z[0] - x1) / dg, dy = (z[1] - y1) / dg, dw = (w2 - w1) / dg, dh = (h2 - h1) / dg;
+        oru_par[0] = x1; oru_par[1] = y1; oru_par[2] = w1; oru_par[3] = h1; oru_par[4] = dx; oru_par[5] = dy; oru_par[6] = dw; oru_par[7] = dh;
+        *oru_gap = gap;
         double vz[4];
-        for (int i = 0; i < gap; ++i) {
-            const double t = (double)(i + 1);
-            const double ww = __dadd_rn(w1, __dmul_rn(t, dw)), hh = __dadd_rn(h1, __dmul_rn(t, dh));
-            vz[0] = __dadd_rn(x1, __dmul_rn(t, dx)); vz[1] = __dadd_rn(y1, __dmul_rn(t, dy));
-            vz[2] = __dmul_rn(ww, hh); vz[3] = ww / hh;
-            ok = kf7_correct(x, P, vz) && ok;
-            if (i != gap - 1) kf7_predict(x, P);
-        }
+        oru_virtual_z(oru_par, gap - 1, vz);
         hist = S.frozen_n[s] - 1 + gap;
         S.frozen[s] = 0;
         for (int k = 0; k < 4; ++k) S.last_z[(size_t)s * 4 + k] = vz[k];
         S.last_z_idx[s] = hist - 1;
-        ok = kf7_correct(x, P, z) && ok;   // the real measurement is applied on top (not appended again)
-    } else {
-        for (int k = 0; k < 7; ++k) x[k] = gx[k];
-        for (int k = 0; k < 49; ++k) P[k] = gP[k];
-        ok = kf7_correct(x, P, z);
-        for (int k = 0; k < 4; ++k) S.last_z[(size_t)s * 4 + k] = z[k];
-        S.last_z_idx[s] = hist - 1;
+        S.observed[s] = 1;
+        S.hist_len[s] = hist;
+        return 2;
     }
+    for (int k = 0; k < 4; ++k) S.last_z[(size_t)s * 4 + k] = z[k];
+    S.last_z_idx[s] = hist - 1;
     S.observed[s] = 1;
     S.hist_len[s] = hist;
-    for (int k = 0; k < 7; ++k) gx[k] = x[k];
-    for (int k = 0; k < 49; ++k) gP[k] = P[k];
-    if (!ok) atomicOr(status, TK_DEV_BAD_CHOLESKY);
+    return 1;   // plain correction
+}
+
+// Apply the matched (track, detection) pairs of one association round. Pass A, one thread per pair: book-keeping; pass B,
+// 8 lanes per pair: the Kalman work (ORU replay where the track was frozen, then the correction with the real measurement).
+// slot < 0 skips entry i. Shared scratch: zbuf 4 doubles, oru 8 doubles, gap 1 int, need 1 byte, slot_of 1 int per entry.
+template <class Get>
+__device__ void oc_apply_updates(OcDev& S, int n, Get get, int delta_t, int* status, double* zbuf, double* oru, int* gap_of,
+                                 unsigned char* need, int* slot_of) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int slot; const double* db;
+        get(i, slot, db);
+        slot_of[i] = slot;
+        gap_of[i] = 0;
+        need[i] = slot >= 0 ? (unsigned char)oc_track_update(S, slot, db, db[5], db[6], delta_t, zbuf + 4 * i, oru + 8 * i, gap_of + i) : 0;
+    }
+    __syncthreads();
+    // order the entries: replays first (their latency is gap x (correct + predict); packing them into one pass keeps the
+    // plain corrections from waiting behind them twice), then the plain corrections
+    int* order = slot_of + n;   // scratch behind slot_of (2 * n <= its size, see the caller)
+    if (warp_id() == 0) {
+        int m = warp_compact(n, 0, [&](int i) { return need[i] == 2; }, [&](int i, int p) { order[p] = i; });
+        m = warp_compact(n, m, [&](int i) { return need[i] == 1; }, [&](int i, int p) { order[p] = i; });
+        if (lane_id() == 0) gap_of[n] = m;
+    }
+    __syncthreads();
+    const int m = gap_of[n];
+    for (int base = 0; base < m; base += blockDim.x / 8) {
+        const int e = base + (threadIdx.x >> 3), j = threadIdx.x & 7;
+        const int i = e < m ? order[e] : 0;
+        const int code = e < m ? need[i] : 0;
+        const bool act = code != 0, replay = code == 2;
+        const int slot = act ? slot_of[i] : 0;
+        const bool own = act && j < 7;
+        double* gx = S.x + (size_t)slot * 7;
+        double* gP = S.P + (size_t)slot * 49;
+        const double* sx = replay ? S.fx + (size_t)slot * 7 : gx;        // ORU restarts from the frozen state
+        const double* sP = replay ? S.fP + (size_t)slot * 49 : gP;
+        double row[7], xj = own ? sx[j] : 0.0;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) row[c] = own ? sP[j * 7 + c] : (c == j ? 1.0 : 0.0);
+        bool ok = true;
+        const int gap = replay ? gap_of[i] : 0;
+        int gmax = gap;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+        for (int it = 0; it < gmax; ++it) {
+            const bool on = it < gap;
+            double vz[4] = {0.0, 0.0, 1.0, 1.0};
+            if (on) oru_virtual_z(oru + 8 * i, it, vz);
+            ok = kf7_group_correct(row, xj, on, vz) && ok;
+            kf7_group_predict(row, xj, on && it != gap - 1);
+        }
+        double z[4] = {0.0, 0.0, 0.0, 0.0};
+        if (act) { z[0] = zbuf[4 * i]; z[1] = zbuf[4 * i + 1]; z[2] = zbuf[4 * i + 2]; z[3] = zbuf[4 * i + 3]; }
+        ok = kf7_group_correct(row, xj, act, z) && ok;
+        if (own) {
+            gx[j] = xj;
+#pragma unroll
+            for (int c = 0; c < 7; ++c) gP[j * 7 + c] = row[c];
+        }
+        if (!ok) atomicOr(status, TK_DEV_BAD_CHOLESKY);
+    }
+    __syncthreads();
 }
 
 // KalmanBoxTracker.update(None): freeze on the observed -> unobserved transition (kalmanfilter.py:465-477)
@@ -335,10 +467,14 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
     int* un_t = (int*)take(sizeof(int) * cap);
     int* tmp_d = (int*)take(sizeof(int) * capd);
     int* tmp_t = (int*)take(sizeof(int) * cap);
-    int* rowcnt = (int*)take(sizeof(int) * side);
-    int* colcnt = (int*)take(sizeof(int) * side);
+    int* rowcnt = (int*)take(sizeof(int) * (2 * side + 2));   // also: slot / order scratch of oc_apply_updates
+    int* colcnt = (int*)take(sizeof(int) * (2 * side + 2));   // also: ORU gap scratch of oc_apply_updates
     unsigned char* flag_d = (unsigned char*)take(capd);
     unsigned char* flag_t = (unsigned char*)take(cap);
+    double* zbuf = (double*)take(sizeof(double) * 4 * capd);        // measurements of the pairs being applied (oc_apply_updates)
+    unsigned char* upd_need = (unsigned char*)take(capd);
+    double* oru_buf = (double*)take(sizeof(double) * 8 * capd);     // ORU line parameters of the pairs being applied
+    double* tprm = (double*)take(sizeof(double) * 5 * cap);         // per-track terms of the round-1 direction cost
     OcShared* sh = (OcShared*)take(sizeof(OcShared));
     // per-slot scalars and the small observation records are mirrored in shared memory for the whole launch
     // (the frame loop is a chain of short serial list edits; global round trips there are pure latency)
@@ -365,6 +501,9 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
     const int out_base = out_start[seq];
     int out_n = out_count[seq];
 
+#ifdef TK_PHASE_PROF
+    long long ph_t0 = clock64();
+#endif
     for (int f = 0; f < n_frames; ++f) {
         const int r0 = offsets[seq * F1 + f], r1 = offsets[seq * F1 + f + 1];
         const int nraw = r1 - r0;
@@ -372,21 +511,18 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
         if (nraw > capd) { if (tid == 0) atomicOr(status, TK_DEV_OVERFLOW_DETS); break; }
         const double* D = dets + (size_t)r0 * 7;
 
-        if (tid == 0) {
-            S.hdr[0] += 1;
-            int nh = 0, nl = 0;
-            for (int i = 0; i < nraw; ++i) {
-                const double c = D[i * 7 + 4];
-                if (!(c > prm.min_conf)) continue;                             // oc_sort_api.py:54
-                if (c > prm.det_thresh) d_hi[nh++] = i;                          // ocsort.py:230-231
-                else if (c > 0.1 && c < prm.det_thresh) d_lo[nl++] = i;          // ocsort.py:226-229
-            }
-            sh->nd = nh; sh->nlo = nl; sh->nt = S.hdr[2];
+        if (warp_id() == 0) {   // wrapper filter (oc_sort_api.py:54), high / low score split (ocsort.py:226-231), order kept
+            const int nh = warp_compact(nraw, 0, [&](int i) { const double c = D[i * 7 + 4]; return c > prm.min_conf && c > prm.det_thresh; },
+                                        [&](int i, int p) { d_hi[p] = i; });
+            const int nl = warp_compact(nraw, 0, [&](int i) { const double c = D[i * 7 + 4]; return c > prm.min_conf && !(c > prm.det_thresh) && c > 0.1 && c < prm.det_thresh; },
+                                        [&](int i, int p) { d_lo[p] = i; });
+            if (lane_id() == 0) { S.hdr[0] += 1; sh->nd = nh; sh->nlo = nl; sh->nt = S.hdr[2]; }
         }
         __syncthreads();
         const int frame_count = S.hdr[0];
         int nt = sh->nt;
         const int nd = sh->nd, nlo = sh->nlo;
+        PH(0);
 
         // ---- predict every tracker (ocsort.py:234-244, :150-163) ------------------------------------
         for (int k = tid; k < nt; k += OC_THREADS) {
@@ -406,7 +542,12 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
             flag_t[k] = (isnan(b[0]) || isnan(b[1]) || isnan(b[2]) || isnan(b[3])) ? 1 : 0;
         }
         __syncthreads();
-        if (tid == 0) {   // drop trackers whose prediction is not finite (ocsort.py:241-244)
+        PH(1);
+        if (tid == 0) sh->maxflag = 0;
+        __syncthreads();
+        for (int k = tid; k < nt; k += OC_THREADS) if (flag_t[k]) sh->maxflag = 1;
+        __syncthreads();
+        if (tid == 0 && sh->maxflag) {   // drop trackers whose prediction is not finite (ocsort.py:241-244); practically never taken
             int n = 0, nfree = S.hdr[5];
             for (int k = 0; k < nt; ++k) {
                 const int s = S.list[k];
@@ -419,6 +560,7 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
         __syncthreads();
         nt = sh->nt;
         // k_previous_obs (ocsort.py:10-18)
+        PH(2);
         for (int k = tid; k < nt; k += OC_THREADS) {
             const int s = S.list[k];
             const double* src = nullptr;
@@ -437,6 +579,7 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
         }
         __syncthreads();
 
+        PH(3);
         // ---- first round: associate() (association.py:242-298) -------------------------------------
         if (tid == 0) { sh->rowmax = 0; sh->colmax = 0; sh->n_pairs = 0; }
         for (int i = tid; i < nd; i += OC_THREADS) { rowcnt[i] = 0; match_d[i] = -1; }
@@ -445,32 +588,45 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
         const bool d_rows = nd <= nt;
         const int ld = lap_pitch(d_rows ? nt : nd);
         if (nt > 0) {
-            for (int e = tid; e < nd * nt; e += OC_THREADS) {
-                const int d = e / nt, t = e % nt;
+            // per-detection and per-track terms of the velocity-direction consistency (association.py:175-184,246-266) once per frame
+            for (int d = tid; d < nd; d += OC_THREADS) {
                 const double* db = D + (size_t)d_hi[d] * 7;
+                zbuf[2 * d] = (db[0] + db[2]) / 2.0; zbuf[2 * d + 1] = (db[1] + db[3]) / 2.0;
+            }
+            for (int t = tid; t < nt; t += OC_THREADS) {
                 const int s = S.list[t];
-                const double iou = iou_plain(db, trk_box + 4 * t);
-                // velocity-direction consistency (association.py:175-184,246-266)
                 const double* ko = kobs + 5 * t;
-                const double cx1 = (db[0] + db[2]) / 2.0, cy1 = (db[1] + db[3]) / 2.0;
-                const double cx2 = (ko[0] + ko[2]) / 2.0, cy2 = (ko[1] + ko[3]) / 2.0;
-                double dx = cx1 - cx2, dy = cy1 - cy2;
+                double* tp = tprm + 5 * t;
+                tp[0] = (ko[0] + ko[2]) / 2.0; tp[1] = (ko[1] + ko[3]) / 2.0;
+                tp[2] = S.has_vel[s] ? S.vel[(size_t)s * 2 + 1] : 0.0;   // vx
+                tp[3] = S.has_vel[s] ? S.vel[(size_t)s * 2 + 0] : 0.0;   // vy
+                tp[4] = ko[4] < 0 ? 0.0 : 1.0;
+            }
+            __syncthreads();
+            PH(12);
+            // two independent entries per trip: the chain sqrt -> 2 divisions -> acos -> division is pure FP64 latency with 8 warps
+#pragma unroll 2
+            for (int e = tid; e < nd * nt; e += OC_THREADS) {
+                const int d = e / nt, t = e - d * nt;
+                const double* db = D + (size_t)d_hi[d] * 7;
+                const double iou = iou_plain(db, trk_box + 4 * t);
+                const double* tp = tprm + 5 * t;
+                double dx = zbuf[2 * d] - tp[0], dy = zbuf[2 * d + 1] - tp[1];
                 const double norm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) + 1e-6;
                 dx = dx / norm; dy = dy / norm;
-                const double vy = S.has_vel[s] ? S.vel[(size_t)s * 2 + 0] : 0.0;
-                const double vx = S.has_vel[s] ? S.vel[(size_t)s * 2 + 1] : 0.0;
-                double c = __dadd_rn(__dmul_rn(vx, dx), __dmul_rn(vy, dy));
+                double c = __dadd_rn(__dmul_rn(tp[2], dx), __dmul_rn(tp[3], dy));
                 c = fmin(fmax(c, -1.0), 1.0);
                 const double pi = 3.141592653589793;
                 const double ang = (pi / 2.0 - fabs(acos(c))) / pi;
-                const double valid = ko[4] < 0 ? 0.0 : 1.0;
-                const double vdc = __dmul_rn(__dmul_rn(__dmul_rn(valid, ang), prm.inertia), db[5]);   // x class column (q1)
+                const double vdc = __dmul_rn(__dmul_rn(__dmul_rn(tp[4], ang), prm.inertia), db[5]);   // x class column (q1)
                 iou_m[(size_t)d * nt + t] = iou;
                 const double cc = -__dadd_rn(iou, vdc);
                 if (d_rows) cost[(size_t)d * ld + t] = cc; else cost[(size_t)t * ld + d] = cc;
                 if (iou > prm.iou_threshold) { atomicAdd(&rowcnt[d], 1); atomicAdd(&colcnt[t], 1); }
             }
+            PH(13);
             __syncthreads();
+            PH(4);
             for (int i = tid; i < nd; i += OC_THREADS) atomicMax(&sh->rowmax, rowcnt[i]);
             for (int i = tid; i < nt; i += OC_THREADS) atomicMax(&sh->colmax, colcnt[i]);
             __syncthreads();
@@ -485,26 +641,27 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
             }
         }
         __syncthreads();
-        if (tid == 0) {
-            // unmatched lists in the reference's order: not-in-pairs ascending, then low-IoU pairs in pair order
-            for (int t = 0; t < nt; ++t) flag_t[t] = 0;
-            int nud = 0, nut = 0;
-            for (int d = 0; d < nd; ++d) { if (match_d[d] < 0) un_d[nud++] = d; else flag_t[match_d[d]] = 1; }
-            if (nt == 0) { nud = 0; for (int d = 0; d < nd; ++d) un_d[nud++] = d; }
-            for (int t = 0; t < nt; ++t) if (!flag_t[t]) un_t[nut++] = t;
-            for (int d = 0; d < nd; ++d) {
-                const int t = match_d[d];
-                if (t >= 0 && iou_m[(size_t)d * nt + t] < prm.iou_threshold) { un_d[nud++] = d; un_t[nut++] = t; match_d[d] = -1; }
-            }
-            sh->n_ud = nud; sh->n_ut = nut;
+        PH(5);
+        // unmatched lists in the reference's order: not-in-pairs ascending, then low-IoU pairs in pair order
+        for (int t = tid; t < nt; t += OC_THREADS) flag_t[t] = 0;
+        __syncthreads();
+        for (int d = tid; d < nd; d += OC_THREADS) if (match_d[d] >= 0) flag_t[match_d[d]] = 1;
+        __syncthreads();
+        if (warp_id() == 0) {
+            const int nud0 = warp_compact(nd, 0, [&](int d) { return match_d[d] < 0; }, [&](int d, int p) { un_d[p] = d; });
+            const int nut0 = warp_compact(nt, 0, [&](int t) { return !flag_t[t]; }, [&](int t, int p) { un_t[p] = t; });
+            const int nlow = warp_compact(nd, 0, [&](int d) { const int t = match_d[d]; return t >= 0 && iou_m[(size_t)d * nt + t] < prm.iou_threshold; },
+                                          [&](int d, int p) { un_d[nud0 + p] = d; un_t[nut0 + p] = match_d[d]; match_d[d] = -1; });
+            if (lane_id() == 0) { sh->n_ud = nud0 + nlow; sh->n_ut = nut0 + nlow; }
         }
         __syncthreads();
-        for (int d = tid; d < nd; d += OC_THREADS) {   // ocsort.py:257-258
+        PH(10);
+        oc_apply_updates(S, nd, [&](int d, int& slot, const double*& db) {   // ocsort.py:257-258
             const int t = match_d[d];
-            if (t >= 0) { const double* db = D + (size_t)d_hi[d] * 7; oc_track_update(S, S.list[t], db, db[5], db[6], prm.delta_t, status); }
-        }
-        __syncthreads();
+            slot = t >= 0 ? S.list[t] : -1; db = D + (size_t)d_hi[d] * 7;
+        }, prm.delta_t, status, zbuf, oru_buf, colcnt, upd_need, rowcnt);
 
+        PH(6);
         // ---- BYTE round on low-score detections (ocsort.py:264-282) -----------------------------------
         if (prm.use_byte && nlo > 0 && sh->n_ut > 0) {
             const int nut = sh->n_ut;
@@ -534,14 +691,13 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
                 oc_solve(cost, nlo, nut, match_d, lap_u, col4row, row4col, path, &sh->lap_ok, status);
                 for (int t = tid; t < nut; t += OC_THREADS) flag_t[t] = 0;
                 __syncthreads();
-                for (int d = tid; d < nlo; d += OC_THREADS) {
+                oc_apply_updates(S, nlo, [&](int d, int& slot, const double*& db) {
                     const int t = match_d[d];
-                    if (t < 0 || iou_m[(size_t)d * nut + t] < prm.iou_threshold) continue;
-                    const double* db = D + (size_t)d_lo[d] * 7;
-                    oc_track_update(S, S.list[un_t[t]], db, db[5], db[6], prm.delta_t, status);
+                    db = D + (size_t)d_lo[d] * 7;
+                    if (t < 0 || iou_m[(size_t)d * nut + t] < prm.iou_threshold) { slot = -1; return; }
+                    slot = S.list[un_t[t]];
                     flag_t[t] = 1;
-                }
-                __syncthreads();
+                }, prm.delta_t, status, zbuf, oru_buf, colcnt, upd_need, rowcnt);
                 if (tid == 0) {   // np.setdiff1d: sorted remaining tracker indices
                     int n = 0;
                     for (int t = 0; t < nut; ++t) if (!flag_t[t]) tmp_t[n++] = un_t[t];
@@ -553,6 +709,7 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
             }
         }
 
+        PH(7);
         // ---- OCR round on the last observations (ocsort.py:284-306) -----------------------------------
         if (sh->n_ud > 0 && sh->n_ut > 0) {
             const int nud = sh->n_ud, nut = sh->n_ut;
@@ -583,14 +740,13 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
                 for (int t = tid; t < nut; t += OC_THREADS) flag_t[t] = 0;
                 for (int d = tid; d < nud; d += OC_THREADS) flag_d[d] = 0;
                 __syncthreads();
-                for (int d = tid; d < nud; d += OC_THREADS) {
+                oc_apply_updates(S, nud, [&](int d, int& slot, const double*& db) {
                     const int t = match_d[d];
-                    if (t < 0 || iou_m[(size_t)d * nut + t] < prm.iou_threshold) continue;
-                    const double* db = D + (size_t)d_hi[un_d[d]] * 7;
-                    oc_track_update(S, S.list[un_t[t]], db, db[5], db[6], prm.delta_t, status);
+                    db = D + (size_t)d_hi[un_d[d]] * 7;
+                    if (t < 0 || iou_m[(size_t)d * nut + t] < prm.iou_threshold) { slot = -1; return; }
+                    slot = S.list[un_t[t]];
                     flag_t[t] = 1; flag_d[d] = 1;
-                }
-                __syncthreads();
+                }, prm.delta_t, status, zbuf, oru_buf, colcnt, upd_need, rowcnt);
                 if (tid == 0) {   // np.setdiff1d on both lists (sorted)
                     int n = 0;
                     for (int t = 0; t < nut; ++t) if (!flag_t[t]) tmp_t[n++] = un_t[t];
@@ -607,19 +763,22 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
             }
         }
 
+        PH(8);
         // ---- unmatched trackers freeze; unmatched detections start trackers (ocsort.py:308-314) --------------
         for (int k = tid; k < sh->n_ut; k += OC_THREADS) oc_track_miss(S, S.list[un_t[k]]);
         __syncthreads();
-        if (tid == 0) {
-            int nfree = S.hdr[5], n = S.hdr[2], nb = 0;
-            for (int k = 0; k < sh->n_ud; ++k) {
-                if (nfree == 0) { atomicOr(status, TK_DEV_OVERFLOW_TRACKS); break; }
-                const int s = S.free_list[--nfree];
-                S.list[n++] = s;
-                tmp_d[nb] = un_d[k]; tmp_t[nb] = s; ++nb;
-                S.uid[s] = S.hdr[1]++;
+        if (warp_id() == 0) {
+            const int nfree = S.hdr[5], n = S.hdr[2], uid0 = S.hdr[1];
+            const int nb = sh->n_ud < nfree ? sh->n_ud : nfree;
+            if (sh->n_ud > nfree && lane_id() == 0) atomicOr(status, TK_DEV_OVERFLOW_TRACKS);
+            for (int k = lane_id(); k < nb; k += 32) {
+                const int s = S.free_list[nfree - 1 - k];
+                S.list[n + k] = s;
+                tmp_d[k] = un_d[k]; tmp_t[k] = s;
+                S.uid[s] = uid0 + k;
             }
-            S.hdr[5] = nfree; S.hdr[2] = n; sh->n_births = nb;
+            __syncwarp();
+            if (lane_id() == 0) { S.hdr[5] = nfree - nb; S.hdr[2] = n + nb; S.hdr[1] = uid0 + nb; sh->n_births = nb; }
         }
         __syncthreads();
         for (int k = tid; k < sh->n_births; k += OC_THREADS) {   // KalmanBoxTracker.__init__ (ocsort.py:63-101)
@@ -640,17 +799,16 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
         }
         __syncthreads();
 
+        PH(9);
         // ---- output rows + death (ocsort.py:315-334), walking the tracker list backwards ------------------------
-        if (tid == 0) {
+        if (warp_id() == 0) {
             const int n = S.hdr[2];
-            int cnt = 0;
-            for (int k = n - 1; k >= 0; --k) {
-                const int s = S.list[k];
-                const bool emit = (S.tsu[s] < 1) && (S.streak[s] >= prm.min_hits || frame_count <= prm.min_hits);
-                rowcnt[k] = emit ? cnt++ : -1;
-            }
-            sh->n_out = cnt;
-            out_frame_count[seq * n_frames + f] = cnt;
+            for (int k = lane_id(); k < n; k += 32) rowcnt[k] = -1;
+            __syncwarp();
+            const int cnt = warp_compact(n, 0, [&](int i) { const int s = S.list[n - 1 - i];
+                                                           return (S.tsu[s] < 1) && (S.streak[s] >= prm.min_hits || frame_count <= prm.min_hits); },
+                                         [&](int i, int p) { rowcnt[n - 1 - i] = p; });
+            if (lane_id() == 0) { sh->n_out = cnt; out_frame_count[seq * n_frames + f] = cnt; }
         }
         __syncthreads();
         {
@@ -670,16 +828,16 @@ ocsort_video_kernel(OcParams prm, char* state_base, size_t state_stride, int cap
             out_n += sh->n_out;
         }
         __syncthreads();
-        if (tid == 0) {
-            int n = 0, nfree = S.hdr[5];
+        if (warp_id() == 0) {
             const int n0 = S.hdr[2];
-            for (int k = 0; k < n0; ++k) {
-                const int s = S.list[k];
-                if (S.tsu[s] > prm.max_age) S.free_list[nfree++] = s; else S.list[n++] = s;
-            }
-            S.hdr[2] = n; S.hdr[5] = nfree;
+            const int nfree = warp_compact(n0, S.hdr[5], [&](int k) { return S.tsu[S.list[k]] > prm.max_age; }, [&](int k, int p) { S.free_list[p] = S.list[k]; });
+            const int n = warp_compact(n0, 0, [&](int k) { return !(S.tsu[S.list[k]] > prm.max_age); }, [&](int k, int p) { tmp_t[p] = S.list[k]; });
+            for (int k = lane_id(); k < n; k += 32) S.list[k] = tmp_t[k];
+            __syncwarp();
+            if (lane_id() == 0) { S.hdr[2] = n; S.hdr[5] = nfree; }
         }
         __syncthreads();
+        PH(11);
     }
     if (tid == 0) out_count[seq] = out_n;
     __syncthreads();
@@ -711,7 +869,8 @@ size_t oc_smem_fixed(int cap, int capd) {
     size_t s = al(sizeof(double) * side) + al(sizeof(double) * 4 * cap) + al(sizeof(double) * 5 * cap);
     s += 2 * al(sizeof(int) * capd) + 4 * al(sizeof(int) * side);
     s += al(sizeof(int) * capd) + al(sizeof(int) * cap) + al(sizeof(int) * capd) + al(sizeof(int) * cap);
-    s += 2 * al(sizeof(int) * side) + al((size_t)capd) + al((size_t)cap) + al(sizeof(OcShared));
+    s += 2 * al(sizeof(int) * (2 * side + 2)) + al((size_t)capd) + al((size_t)cap) + al(sizeof(OcShared));
+    s += al(sizeof(double) * 4 * capd) + al((size_t)capd) + al(sizeof(double) * 8 * capd) + al(sizeof(double) * 5 * cap);
     // book-keeping mirror: hdr + per-slot records (see OC_MIRROR in the kernel)
     s += al(8 * sizeof(int)) + al(sizeof(double) * cap * 5) + al(sizeof(double) * cap * 2) + al(sizeof(double) * cap * 4)
        + 3 * al(sizeof(double) * cap) + 10 * al(sizeof(int) * cap) + 3 * al((size_t)cap);
@@ -783,6 +942,15 @@ int tk_ocsort_status(void* handle, int* status_host, void* stream) {
     TK_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return TK_OK;
 }
+
+#ifdef TK_PHASE_PROF
+int tk_debug_ocsort_phases(unsigned long long* host_out64, int reset) {
+    cudaDeviceSynchronize();
+    if (host_out64) cudaMemcpyFromSymbol(host_out64, g_oc_prof, sizeof(unsigned long long) * 64);
+    if (reset) { unsigned long long z[64] = {0}; cudaMemcpyToSymbol(g_oc_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int tk_ocsort_destroy(void* handle) {
     if (!handle) return TK_ERR_ARG;
