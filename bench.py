@@ -363,11 +363,47 @@ def run_ours(args):
                 "per_video": {"frames": allm[:, 0].tolist(), "dets": allm[:, 1].tolist(), "rows": allm[:, 2].tolist(),
                               "ids": allm[:, 3].tolist(), "ms_per_step": allm[:, 4].tolist()},
                 "detector_rows_per_frame": det_rows / F}
+        if world == 1:
+            line["other_trackers"] = other_tracker_timings(dev)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args, video)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_tracker_timings(dev, frames=200):
+    """Whole-video kernels of the other association families on the generator video of this bench (tracker only, inputs in
+    HBM, CUDA events, second of two runs): the rows SURVEY.md section 8 lists next to ByteTrack. A few hundred ms in total."""
+    import numpy as np
+    import torch
+    from tracklab_b200.device_trackers import BpbreidStrongSortDevice, OCSortDevice, StrongSortDevice
+    from tracklab_b200.synth import make_video
+    out = {}
+
+    def timed(run):
+        run(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        return 1e3 * e0.elapsed_time(e1) / frames
+
+    v = make_video(seed=2000, n_frames=frames, n_ids=44, emb_dim=512)
+    dets = torch.from_numpy(v.dets).to(dev); offs = torch.from_numpy(v.offsets.astype(np.int32))[None].to(dev)
+    feats = torch.from_numpy(v.embeddings).to(dev)
+    oc = OCSortDevice(device=dev)
+    out["ocsort_us_per_frame"] = timed(lambda: (oc.reset(), oc.run(dets, offs)))
+    ss = StrongSortDevice(512, ctas_per_video=32, device=dev)
+    out["strongsort_e512_budget100_32ctas_us_per_frame"] = timed(lambda: (ss.reset(), ss.run(dets, offs, feats)))
+    vp = make_video(seed=2000, n_frames=frames, n_ids=44, emb_dim=512, n_parts=6)
+    d2 = vp.dets.copy(); d2[:, 2] -= d2[:, 0]; d2[:, 3] -= d2[:, 1]
+    bp = BpbreidStrongSortDevice(6, 512, ctas_per_video=24, device=dev)
+    pd_, pf, pv = torch.from_numpy(d2).to(dev), torch.from_numpy(vp.embeddings).to(dev), torch.from_numpy(vp.visibility.astype(np.float32)).to(dev)
+    po = torch.from_numpy(vp.offsets.astype(np.int32))[None].to(dev)
+    out["bpbreid_k6_e512_24ctas_us_per_frame"] = timed(lambda: (bp.reset(), bp.run(pd_, po, pf, pv)))
+    for t in (oc, ss, bp):
+        t.check_status(); t.close()
+    out["note"] = "%d frames, ~38 det/frame, reference hyper-parameters (YAML); see profiles/ for the larger configurations" % frames
+    return out
 
 
 def cpu_baseline(args, video):

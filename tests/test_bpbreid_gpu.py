@@ -95,3 +95,29 @@ def test_bpbreid_yaml_config_keeps_hundreds_of_stale_tracks():
     assert len(orc.tracks) > 300
     rows, fr = _run_device(v, hyper, ncta=8, chunks=3)
     assert_bpbreid_rows_match(rows, fr, ref_rows, ref_fr, box_tol=1e-6, dist_tol=1e-5, allow_relabel=True)
+
+
+def test_bpbreid_two_videos_in_one_launch():
+    """n_seq = 2: two cooperative CTA groups in one launch, each equal to its own single-video oracle run."""
+    from oracle.bpbreid_np import BpbreidStrongSortOracle
+    from tracklab_b200.device_trackers import BpbreidStrongSortDevice, rows_to_frames
+    hyper = dict(ema_alpha=0.9, mc_lambda=0.995, max_dist=0.5, max_iou_distance=0.8, max_age=30, n_init=1, min_bbox_confidence=0.2,
+                 max_kalman_prediction_without_update=7)
+    videos = [make_video(seed=6400 + i, n_frames=70, n_ids=18 + 6 * i, emb_dim=32, n_parts=4, conf_range=(0.1, 1.0)) for i in range(2)]
+    F = videos[0].n_frames
+    dets = torch.from_numpy(np.concatenate([_ltwh_rows(v) for v in videos])).cuda()
+    feats = torch.from_numpy(np.concatenate([v.embeddings for v in videos])).cuda()
+    vis = torch.from_numpy(np.concatenate([v.visibility.astype(np.float32) for v in videos])).cuda()
+    base = np.cumsum([0] + [v.n_dets for v in videos])
+    offs = torch.from_numpy(np.stack([v.offsets + base[i] for i, v in enumerate(videos)]).astype(np.int32)).cuda()
+    trk = BpbreidStrongSortDevice(4, 32, **hyper, ctas_per_video=3, n_seq=2, cap_tracks=256, cap_dets=64)
+    cap = max(v.n_dets for v in videos)
+    out_rows = torch.empty((2 * cap, 14), dtype=torch.float64, device="cuda")
+    out_start = torch.tensor([0, cap], dtype=torch.int32, device="cuda")
+    rows, fc, cnt = trk.run(dets, offs, feats, vis, out_rows=out_rows, out_start=out_start)
+    trk.check_status()
+    for i, v in enumerate(videos):
+        got, gf = rows_to_frames(rows, fc, out_start, seq=i)
+        want, wf = BpbreidStrongSortOracle(**hyper).run_video(v.dets, v.offsets, v.embeddings, v.visibility)
+        assert F == v.n_frames
+        assert_bpbreid_rows_match(got, gf, want, wf, box_tol=1e-6, dist_tol=1e-5, allow_relabel=True)
