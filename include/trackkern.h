@@ -45,7 +45,9 @@ int tk_last_cuda_error(void);
  * src: device uint8 [n_frames, H, W, 3] (16-byte aligned, frame pitch `frame_stride_bytes`);
  * dst: device tensor of out_dtype; out_layout 0 = planar [n,3,S,S], 1 = channels-last [n,S,S,3],
  * 2 = YOLOX Focus space-to-depth pre-applied, channels-last [n,S/2,S/2,16] (12 used, 4 zero pad channels the
- * caller must have zeroed once); swap_rb=1 turns the engine's RGB frames
+ * caller must have zeroed once); 3 = the same with a 32-channel pixel pitch [n,S/2,S/2,32] (channels 16..31 caller-zeroed:
+ * cuDNN's sm_100 kernels need 32 input channels, the 16-channel stem convolution falls back to a 2.6x slower sm_80 kernel);
+ * swap_rb=1 turns the engine's RGB frames
  * (/root/reference/tracklab/utils/cv2.py:54-66) into the BGR order cv2.imread feeds the detector
  * (rtmlib_api.py:28). *ratio_out (host, optional) receives the letterbox ratio.
  */

@@ -51,6 +51,11 @@ def test_letterbox_focus16_layout():
     tr, br = plain[..., ::2, 1::2], plain[..., 1::2, 1::2]
     assert torch.equal(x16[:, :12], torch.cat((tl, bl, tr, br), 1))
     assert torch.equal(x16[:, 12:], torch.zeros_like(x16[:, 12:]))
+    # same content with a 32-channel pixel pitch (the stem layout the detector uses); channels 16..31 are never written
+    x32 = torch.zeros((2, 32, 320, 320), dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
+    x32[:, 16:] = 7.0
+    kernels.letterbox(frames, 640, torch.bfloat16, swap_rb=True, out=x32, focus16=True)
+    assert torch.equal(x32[:, :16], x16) and bool((x32[:, 16:] == 7.0).all())
 
 
 @pytest.mark.parametrize("variant", ["s", "m"])
@@ -62,7 +67,7 @@ def test_fused_yolox_matches_module(variant):
     frames = torch.from_numpy(rng.integers(0, 256, size=(2, 1080, 1920, 3), dtype=np.uint8)).cuda()
     model = build_yolox(variant).cuda().bfloat16().to(memory_format=torch.channels_last)
     x, _ = kernels.letterbox(frames, 640, torch.bfloat16, swap_rb=True, channels_last=True)
-    x16 = torch.zeros((2, 16, 320, 320), dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
+    x16 = torch.zeros((2, YoloxFused.STEM_IN, 320, 320), dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
     kernels.letterbox(frames, 640, torch.bfloat16, swap_rb=True, out=x16, focus16=True)
     with torch.no_grad():
         ref = model(x).float()

@@ -171,11 +171,11 @@ template <typename OutT>
 __global__ void __launch_bounds__(LB_THREADS)
 letterbox_focus16_kernel(const unsigned char* __restrict__ src, size_t frame_stride, int H, int W, OutT* __restrict__ dst,
                          int S, int rw, int rh, double scale_x, double scale_y, int area2x, int pad, int swap_rb,
-                         const unsigned char* __restrict__ src_end) {
+                         const unsigned char* __restrict__ src_end, int pix_pitch) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar;
     const int fy = blockIdx.x, b = blockIdx.y, S2 = S >> 1;
-    OutT* orow = dst + (((size_t)b * S2 + fy) * S2) * 16;
+    OutT* orow = dst + (((size_t)b * S2 + fy) * S2) * pix_pitch;   // pix_pitch 16, or 32 with caller-zeroed channels 16..31
     const float padf = (float)pad;
     const size_t row_bytes = (size_t)W * 3;
     const size_t pitch = (row_bytes + 31 + 15) & ~(size_t)15;
@@ -259,7 +259,7 @@ letterbox_focus16_kernel(const unsigned char* __restrict__ src, size_t frame_str
         OutT o16[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) o16[k] = cvt_out<OutT>(px[k]);
-        uint4* d4 = reinterpret_cast<uint4*>(orow + (size_t)fx * 16);
+        uint4* d4 = reinterpret_cast<uint4*>(orow + (size_t)fx * pix_pitch);
         const uint4* s4 = reinterpret_cast<const uint4*>(o16);
 #pragma unroll
         for (int k = 0; k < (int)(16 * sizeof(OutT) / 16); ++k) d4[k] = s4[k];
@@ -277,7 +277,7 @@ extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, in
     const double ratio = fmin((double)S / (double)H, (double)S / (double)W);
     const int rw = (int)((double)W * ratio), rh = (int)((double)H * ratio);
     if (rw <= 0 || rh <= 0 || rw > S || rh > S) return TK_ERR_ARG;
-    if (out_layout < 0 || out_layout > 2 || (out_layout == 2 && (S & 1))) return TK_ERR_ARG;
+    if (out_layout < 0 || out_layout > 3 || (out_layout >= 2 && (S & 1))) return TK_ERR_ARG;
     if (ratio_out) *ratio_out = ratio;
     const double scale_x = 1.0 / ((double)rw / (double)W), scale_y = 1.0 / ((double)rh / (double)H);
     const int area2x = (W == 2 * rw && H == 2 * rh) ? 1 : 0;
@@ -287,19 +287,20 @@ extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, in
     if (((size_t)src & 15) != 0) return TK_ERR_ARG;  // bulk copies round spans down to 16 B
     const unsigned char* src_end = src + (size_t)(n_frames - 1) * (size_t)frame_stride_bytes + (size_t)H * W * 3;
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_layout == 2) {
+    if (out_layout >= 2) {
+        const int pix_pitch = out_layout == 3 ? 32 : 16;
         const size_t smem4 = 4 * pitch + 16;
         if (smem4 > 200 * 1024) return TK_ERR_CAPACITY;
         dim3 grid2(S / 2, n_frames);
         if (out_dtype == TK_DTYPE_F32) {
             TK_CUDA_TRY(cudaFuncSetAttribute(letterbox_focus16_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
             letterbox_focus16_kernel<float><<<grid2, LB_THREADS, smem4, st>>>(src, (size_t)frame_stride_bytes, H, W, (float*)dst, S, rw, rh,
-                                                                              scale_x, scale_y, area2x, pad_value, swap_rb, src_end);
+                                                                              scale_x, scale_y, area2x, pad_value, swap_rb, src_end, pix_pitch);
         } else {
             TK_CUDA_TRY(cudaFuncSetAttribute(letterbox_focus16_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
             letterbox_focus16_kernel<__nv_bfloat16><<<grid2, LB_THREADS, smem4, st>>>(src, (size_t)frame_stride_bytes, H, W,
                                                                                       (__nv_bfloat16*)dst, S, rw, rh, scale_x, scale_y,
-                                                                                      area2x, pad_value, swap_rb, src_end);
+                                                                                      area2x, pad_value, swap_rb, src_end, pix_pitch);
         }
         TK_CUDA_TRY(cudaGetLastError());
         return TK_OK;

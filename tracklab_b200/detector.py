@@ -35,8 +35,8 @@ class YoloxDetectorDevice:
             from .nets.yolox_fused import YoloxFused
             self._fused_cls = YoloxFused
             self.fused = YoloxFused(self.model, self.device)
-            # Focus-unfolded input written by the letterbox kernel; channels 12..15 are zero padding
-            self.x = torch.zeros((batch, 16, input_size // 2, input_size // 2), dtype=dtype,
+            # Focus-unfolded input written by the letterbox kernel; channels 12.. are zero padding (32-channel pitch, see yolox_fused)
+            self.x = torch.zeros((batch, self._fused_cls.STEM_IN, input_size // 2, input_size // 2), dtype=dtype,
                                  device=self.device).contiguous(memory_format=torch.channels_last)
         else:
             self.x = torch.empty((batch, 3, input_size, input_size), dtype=dtype, device=self.device,
@@ -124,7 +124,7 @@ class YoloxDetectorDevice:
         assert B <= self.batch
         if B < self.batch:   # ragged tail: run eagerly on a view (rare: once per video)
             if self.use_fused:
-                x = torch.zeros((B, 16, self.size // 2, self.size // 2), dtype=self.dtype,
+                x = torch.zeros((B, self._fused_cls.STEM_IN, self.size // 2, self.size // 2), dtype=self.dtype,
                                 device=self.device).contiguous(memory_format=torch.channels_last)
                 _, ratio = kernels.letterbox(frames, self.size, self.dtype, swap_rb=True, out=x, focus16=True)
             else:

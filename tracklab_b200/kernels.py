@@ -46,8 +46,9 @@ def letterbox(frames: torch.Tensor, size: int = 640, out_dtype=torch.bfloat16, p
         out = torch.empty((B, 3, size, size), dtype=out_dtype, device=frames.device,
                           memory_format=torch.channels_last if channels_last else torch.contiguous_format)
     if focus16:
-        assert out.shape == (B, 16, size // 2, size // 2) and out.is_contiguous(memory_format=torch.channels_last)
-        nhwc = 2
+        assert out.shape[1] in (16, 32) and out.shape == (B, out.shape[1], size // 2, size // 2)
+        assert out.is_contiguous(memory_format=torch.channels_last)
+        nhwc = 2 if out.shape[1] == 16 else 3   # pitch 32: channels 16..31 stay as the caller zeroed them
     else:
         nhwc = int(out.is_contiguous(memory_format=torch.channels_last) and not out.is_contiguous())
         assert nhwc or out.is_contiguous()

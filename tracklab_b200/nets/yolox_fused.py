@@ -31,6 +31,10 @@ class _Conv:
 
 
 class YoloxFused:
+    # input channels of the stem convolution: the 12 Focus channels zero-padded to 32 (with 16 cuDNN picks an sm_80 kernel,
+    # 425 us per 50 frames; with 32 an sm_100 one, 164 us — tools/probe_yolox_stem.py)
+    STEM_IN = 32
+
     def __init__(self, model: YOLOX, device):
         self.device = torch.device(device)
         self.nc = model.num_classes
@@ -44,7 +48,7 @@ class YoloxFused:
         for mod in model.modules():
             if isinstance(mod, ConvAct):
                 reg(mod)
-        self._convs[id(model.stem.conv)] = _Conv(model.stem.conv, dev, pad_in_to=16)
+        self._convs[id(model.stem.conv)] = _Conv(model.stem.conv, dev, pad_in_to=self.STEM_IN)
         # prediction convolutions keep their bias inside cuDNN (4 / 1 / nc output channels, no activation):
         # reg + obj share their input, so they are one 5-channel convolution.
         self.pred_ro = []
