@@ -32,12 +32,10 @@ __device__ __forceinline__ float silu_f(float x) {
 // Grid-stride over 16-byte vectors, two vectors in flight per thread; (pixel, channel-vector) coordinates are advanced
 // incrementally (stride = q * c_vec + r) so the loop has no integer division — the first version spent ~200 instructions
 // per vector on a 64-bit divide and was issue-bound at 45 % of HBM peak (profiles/r01_ncu_summary.md).
-__device__ __forceinline__ void epi_one(const __nv_bfloat16* __restrict__ src, const float* __restrict__ bias,
+__device__ __forceinline__ void epi_one(const __nv_bfloat16* __restrict__ src, const float4 b0, const float4 b1,
                                         __nv_bfloat16* __restrict__ dst, const __nv_bfloat16* __restrict__ res, long long i,
                                         long long pix, int cv, int dst_pitch, int dst_off, int res_pitch, int res_off, int act) {
     const bf16x8 x = *reinterpret_cast<const bf16x8*>(src + i * 8);
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + cv * 8);
-    const float4 b1 = *reinterpret_cast<const float4*>(bias + cv * 8 + 4);
     float f[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) { const float2 t = __bfloat1622float2(x.v[k]); f[2 * k] = t.x; f[2 * k + 1] = t.y; }
@@ -64,7 +62,7 @@ __device__ __forceinline__ void epi_one(const __nv_bfloat16* __restrict__ src, c
     *reinterpret_cast<bf16x8*>(dst + pix * dst_pitch + dst_off + cv * 8) = o;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 bias_act_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__ bias, __nv_bfloat16* __restrict__ dst,
                 const __nv_bfloat16* __restrict__ res, long long n_vec, int c_vec, int dst_pitch, int dst_off,
                 int res_pitch, int res_off, int act) {
@@ -74,15 +72,34 @@ bias_act_kernel(const __nv_bfloat16* __restrict__ src, const float* __restrict__
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long pix = i / c_vec;
     int cv = (int)(i - pix * c_vec);
+    if (sr == 0) {
+        // the host sizes the grid so that the stride is a multiple of the channel vectors: every thread keeps its 8 channels,
+        // the bias lives in registers (two 16-byte bias loads per vector were half of the L1 requests: 87 % l1tex throughput in ncu)
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + cv * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias + cv * 8 + 4);
+        for (; i + stride < n_vec; i += 2 * stride, pix += 2 * sq) {
+            epi_one(src, b0, b1, dst, res, i, pix, cv, dst_pitch, dst_off, res_pitch, res_off, act);
+            epi_one(src, b0, b1, dst, res, i + stride, pix + sq, cv, dst_pitch, dst_off, res_pitch, res_off, act);
+        }
+        if (i < n_vec) epi_one(src, b0, b1, dst, res, i, pix, cv, dst_pitch, dst_off, res_pitch, res_off, act);
+        return;
+    }
+    auto bias_of = [&](int c, float4& b0, float4& b1) {
+        b0 = *reinterpret_cast<const float4*>(bias + c * 8);
+        b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
+    };
+    float4 b0, b1;
     for (; i + stride < n_vec; i += 2 * stride) {
         long long pix2 = pix + sq; int cv2 = cv + sr;
         if (cv2 >= c_vec) { cv2 -= c_vec; ++pix2; }
-        epi_one(src, bias, dst, res, i, pix, cv, dst_pitch, dst_off, res_pitch, res_off, act);
-        epi_one(src, bias, dst, res, i + stride, pix2, cv2, dst_pitch, dst_off, res_pitch, res_off, act);
+        bias_of(cv, b0, b1);
+        epi_one(src, b0, b1, dst, res, i, pix, cv, dst_pitch, dst_off, res_pitch, res_off, act);
+        bias_of(cv2, b0, b1);
+        epi_one(src, b0, b1, dst, res, i + stride, pix2, cv2, dst_pitch, dst_off, res_pitch, res_off, act);
         pix = pix2 + sq; cv = cv2 + sr;
         if (cv >= c_vec) { cv -= c_vec; ++pix; }
     }
-    if (i < n_vec) epi_one(src, bias, dst, res, i, pix, cv, dst_pitch, dst_off, res_pitch, res_off, act);
+    if (i < n_vec) { bias_of(cv, b0, b1); epi_one(src, b0, b1, dst, res, i, pix, cv, dst_pitch, dst_off, res_pitch, res_off, act); }
 }
 
 // SPP: x [B, H, W, C] -> dst [B, H, W, 4C] = [x | max5 | max9 | max13] (stride 1, -inf padding).
@@ -142,6 +159,27 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ src, int src_pitch, int src_
         const long long dp = (bimg * 2 * h + oy) * (2 * w) + ox;
         *reinterpret_cast<bf16x8*>(dst + dp * dst_pitch + dst_off + cv * 8) = v;
     }
+}
+
+// bias_act: exactly one resident wave (occupancy queried once: the 48-register kernel fits 5 CTAs per SM, the previous fixed
+// 8 per SM ran 1.6 waves) and a grid whose thread count is a multiple of the channel vectors (register-resident bias).
+inline int bias_act_grid(long long n_vec, int c_vec) {
+    static int per_sm = 0, n_sm = 0;
+    if (per_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bias_act_kernel, 256, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+        if (n_sm <= 0) n_sm = 148;
+    }
+    long long blocks = (n_vec + 255) / 256;
+    const long long cap = (long long)n_sm * per_sm;
+    if (blocks > cap) blocks = cap;
+    int a = c_vec, b = 256;                       // g = c_vec / gcd(c_vec, 256): blocks * 256 % c_vec == 0 <=> blocks % g == 0
+    while (b) { const int t = a % b; a = b; b = t; }
+    const int g = c_vec / a;
+    if (blocks >= g) blocks = blocks / g * g;
+    return (int)(blocks > 0 ? blocks : 1);
 }
 
 inline int grid_for(long long n_vec) {
@@ -218,7 +256,7 @@ int tk_bias_act_nhwc(const void* src, const float* bias, void* dst, const void* 
     if ((channels & 7) || (dst_pitch & 7) || (dst_offset & 7) || (residual && ((res_pitch & 7) || (res_offset & 7)))) return TK_ERR_ARG;
     if (((size_t)src & 15) || ((size_t)dst & 15) || ((size_t)bias & 15) || (residual && ((size_t)residual & 15))) return TK_ERR_ARG;
     const long long n_vec = n_pixels * (channels / 8);
-    bias_act_kernel<<<grid_for(n_vec), 256, 0, (cudaStream_t)stream>>>(
+    bias_act_kernel<<<bias_act_grid(n_vec, channels / 8), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)src, bias, (__nv_bfloat16*)dst, (const __nv_bfloat16*)residual, n_vec, channels / 8, dst_pitch,
         dst_offset, res_pitch, res_offset, act);
     TK_CUDA_TRY(cudaGetLastError());
