@@ -102,3 +102,31 @@ def test_pack_detections_rows_match_wrapper():
     for b in range(B):
         ref = wrapper_rows(boxes[b, :cnt[b]], 1920, 1080, first_id=o[b])
         assert np.array_equal(dets[o[b]:o[b + 1]].cpu().numpy(), ref)
+
+
+def test_streamed_video_with_drain_schedule_equals_resident_video():
+    """DetectTrackPipeline from pinned host memory (H2D overlapped, last batch drained as 25/13/12 frames on their own CUDA
+    graphs) produces exactly the rows of the HBM-resident run, detector rows included."""
+    from tracklab_b200.detector import YoloxDetectorDevice
+    from tracklab_b200.device_trackers import ByteTrackDevice
+    from tracklab_b200.synth import make_frames, make_video
+    from tracklab_b200.video_pipeline import DetectTrackPipeline
+    dev = torch.device("cuda:0")
+    F, B = 150, 50
+    video = make_video(seed=31, n_frames=F, n_ids=30)
+    frames = make_frames(video, 0, F, device=dev)
+    det = YoloxDetectorDevice("s", device=dev, batch=B, frames_cap=F, dets_cap=1 << 16)
+    det.calibrate(frames[:B])
+    trk = ByteTrackDevice(device=dev)
+    pipe = DetectTrackPipeline(det, trk, B)
+    assert pipe._schedule(F, True)[-3:] == [(100, 125), (125, 138), (138, 150)] and pipe._schedule(F, False)[-1] == (100, 150)
+    rows_d, fc_d, cnt_d, cur_d = pipe.run_video(frames)
+    torch.cuda.synchronize()
+    a = (rows_d[: int(cnt_d)].clone(), fc_d.clone(), det.dets[: int(det.cursor[0])].clone(), det.offsets[: F + 1].clone())
+    host = frames.cpu().pin_memory()
+    for _ in range(2):   # second pass replays the tail graphs
+        rows_h, fc_h, cnt_h, cur_h = pipe.run_video(host)
+        torch.cuda.synchronize()
+        assert int(cnt_h) == int(cnt_d) and torch.equal(rows_h[: int(cnt_h)], a[0]) and torch.equal(fc_h, a[1])
+        assert torch.equal(det.dets[: int(det.cursor[0])], a[2]) and torch.equal(det.offsets[: F + 1], a[3])
+    det.check_status(); trk.check_status()

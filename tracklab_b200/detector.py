@@ -49,6 +49,8 @@ class YoloxDetectorDevice:
         self.geom = None
         self.graph = None
         self.use_graph = use_graph
+        self.tail_sizes = set()     # batch sizes < batch that get their own graph (set by the streaming pipeline's drain schedule)
+        self._tail_graphs = {}
         self.pred = None
         self.nms_out = None
         self.time_kernels = False
@@ -92,6 +94,7 @@ class YoloxDetectorDevice:
             self.model.obj_preds[lvl].bias.data += shift
             self.model.cls_preds[lvl].bias.data += shift
         self.graph = None
+        self._tail_graphs = {}
         if self.use_fused:
             self.fused = self._fused_cls(self.model, self.device)
         return shift
@@ -105,8 +108,8 @@ class YoloxDetectorDevice:
         self._forward_post_impl(W, H)
         self.launches_per_batch = kernels.LAUNCHES - n0   # libtrackkern launches of one batch (replayed by the CUDA graph)
 
-    def _forward_post_impl(self, W, H):
-        self.pred = self._net(self.x)
+    def _forward_post_impl(self, W, H, x=None):
+        self.pred = self._net(self.x if x is None else x)
         self.nms_out = kernels.yolox_nms(self.pred, self.ratio, self.size, logits=True, score_thr=self.score_thr,
                                          nms_thr=self.nms_thr, max_out=self.max_per_image, status=self.status)
         boxes, scores, cls, count, _ = self.nms_out
@@ -122,6 +125,32 @@ class YoloxDetectorDevice:
         """frames uint8 [B<=batch, H, W, 3] on the device; appends rows/offsets at the device cursor."""
         B, H, W, _ = frames.shape
         assert B <= self.batch
+        if B < self.batch and self.use_graph and self.use_fused and B in self.tail_sizes:
+            # pipeline drain (video_pipeline.py): a few smaller batches at the end of a streamed video, each with its own graph
+            ent = self._tail_graphs.get((B, H, W))
+            if ent is None:
+                x = torch.zeros((B, self._fused_cls.STEM_IN, self.size // 2, self.size // 2), dtype=self.dtype,
+                                device=self.device).contiguous(memory_format=torch.channels_last)
+                _, self.ratio = kernels.letterbox(frames, self.size, self.dtype, swap_rb=True, out=x, focus16=True)
+                cur = self.cursor.clone()
+                s = torch.cuda.Stream(device=self.device)
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    for _ in range(3):
+                        self._forward_post_impl(W, H, x)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                self.cursor.copy_(cur)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._forward_post_impl(W, H, x)
+                self.cursor.copy_(cur)
+                ent = (g, x)
+                self._tail_graphs[(B, H, W)] = ent
+            g, x = ent
+            _, self.ratio = kernels.letterbox(frames, self.size, self.dtype, swap_rb=True, out=x, focus16=True)
+            g.replay()
+            return
         if B < self.batch:   # ragged tail: run eagerly on a view (rare: once per video)
             if self.use_fused:
                 x = torch.zeros((B, self._fused_cls.STEM_IN, self.size // 2, self.size // 2), dtype=self.dtype,

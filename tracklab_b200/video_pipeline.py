@@ -27,6 +27,27 @@ class DetectTrackPipeline:
         self.kernel_events = []  # (name, start, end) CUDA events recorded on the launching stream
         self.launches = 0
 
+    def _schedule(self, F: int, host: bool):
+        """Frame ranges of the detector batches. Streaming from the host the video is PCIe-bound, so what is left after the
+        last frame has arrived (one detector batch + its tracker chunk) is pure tail: the last full batch is drained as a few
+        halving batches (each replaying its own CUDA graph) so that only a small one remains after the last copy."""
+        B = self.batch
+        bounds = [(f0, min(F, f0 + B)) for f0 in range(0, F, B)]
+        if not host or len(bounds) < 2 or bounds[-1][1] - bounds[-1][0] != B or B < 32:
+            return bounds
+        f0, f1 = bounds.pop()
+        rem, sizes = B, []
+        while rem > 12:
+            s = rem // 2
+            sizes.append(rem - s)
+            rem = s
+        sizes.append(rem)
+        self.det.tail_sizes.update(sizes)
+        for s in sizes:
+            bounds.append((f0, f0 + s))
+            f0 += s
+        return bounds
+
     def _staging(self, like: torch.Tensor):
         shape = (2, self.batch) + tuple(like.shape[1:])
         if self.stage is None or self.stage.shape != shape:
@@ -63,8 +84,7 @@ class DetectTrackPipeline:
         out_fc = torch.zeros((1, F), dtype=torch.int32, device=self.dev)
         stage = self._staging(frames) if host else None
         free_ev = [None, None]
-        for i, f0 in enumerate(range(0, F, B)):
-            f1 = min(F, f0 + B)
+        for i, (f0, f1) in enumerate(self._schedule(F, host)):
             n = f1 - f0
             if host:
                 slot = i & 1
