@@ -57,3 +57,16 @@ def test_bytetrack_matches_oracle_fresh_seed(seed):
     ref_rows, ref_frames = ByteTrackOracle(**hyper, min_confidence=0.4).run_video(video.dets, video.offsets)
     rows, frames = _run_device(video, hyper, 0.4)
     assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1e-6)
+
+
+def test_hota_of_device_rows_equals_hota_of_reference_rows():
+    """BASELINE metric 'HOTA vs ref': the device tracker's rows score exactly the reference plugin's HOTA on the same video
+    (oracle/hota_np.py restates the TrackEval HOTA vendored in the reference, tests/test_oracle_cpu.py)."""
+    from oracle.hota_np import hota_of_tracker_rows
+    g = load_golden("bytetrack_c2_s2000")
+    video = make_video(**g["gen"])
+    rows, frames = _run_device(video, g["hyper"], g["min_conf"])
+    dev, ref = hota_of_tracker_rows(video, rows, frames), hota_of_tracker_rows(video, g["rows"], g["frames"])
+    for k in ("HOTA", "DetA", "AssA", "LocA"):
+        assert np.array_equal(dev[k], ref[k]), k
+    print("HOTA", dev["HOTA"].mean(), "DetA", dev["DetA"].mean(), "AssA", dev["AssA"].mean())
