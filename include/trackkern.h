@@ -280,7 +280,19 @@ int tk_bpbreid_destroy(void* handle);
  *   tk_lap_batched  cost [B,N,M] float64 -> x [B,N] (column of each row or -1), y [B,M]; has_limit=1 gives
  *                   lap.lapjv(cost, extend_cost=True, cost_limit=L) semantics (byte_track/matching.py:37-48),
  *                   has_limit=0 assigns all min(N,M) pairs (oc_sort/association.py:187-191, scipy LSA)
+ *   tk_part_dist    a [B,N,K,E], va [B,N,K], b [B,M,K,E], vb [B,M,K] float32 -> out [B,N,M] float32: visibility-weighted mean
+ *                   over the K parts of the Euclidean distance between L2-normalised part embeddings, halved
+ *                   (/root/reference/plugins/track/bpbreid_strong_sort/sort/nn_matching.py:99-135; the torchreid function it
+ *                   calls is restated, see oracle/bpbreid_np.py); norm_scratch: float32 [B*(N+M)*K]
+ *   tk_kf_gate      squared Mahalanobis gating distances of xyah Kalman filters: mean [T,8], cov [T,8,8], z [D,4] float64
+ *                   -> out [T,D]; aspect_const 1 = ByteTrack / StrongSORT measurement noise (1e-1 on the aspect ratio,
+ *                   byte_track/kalman_filter.py:228-269, strong_sort/sort/kalman_filter.py:176-214), 0 = BPBReID (all
+ *                   terms scale with the height, bpbreid_strong_sort/sort/kalman_filter.py:168-227)
  */
+int tk_part_dist(const float* a, const float* va, const float* b, const float* vb, float* out, float* norm_scratch, int n_problems, int N,
+                 int M, int K, int E, void* stream);
+int tk_kf_gate(const double* mean, const double* cov, const double* z, double* out, int n_tracks, int n_dets, int aspect_const,
+               int* status_dev, void* stream);
 int tk_iou_matrix(const double* a, const double* b, double* out, int n_problems, int N, int M, int variant, void* stream);
 int tk_iou_p1_f32(const float* a_tlbr, const float* b_tlbr, float* dist_out, int n_problems, int N, int M, void* stream);
 int tk_cosine_dist(const float* a, const float* b, double* out, float* norm_scratch, int n_problems, int N, int M, int E,

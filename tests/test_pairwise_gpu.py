@@ -78,3 +78,37 @@ def test_lap_batched_matches_oracle(shape, limit):
     for p in range(B):
         rx, ry = lapjv_extended(cost[p], np.inf if limit is None else limit)
         assert np.array_equal(x[p], rx) and np.array_equal(y[p], ry)
+
+
+@pytest.mark.parametrize("shape", [(1, 40, 37, 6, 512), (2, 9, 150, 5, 64), (1, 1, 1, 3, 20)])
+def test_part_distance_matches_oracle(shape):
+    """Stateless part-based distance (BPBReID / KPR embeddings) vs oracle/bpbreid_np.part_distance, float32 within 1e-5."""
+    from oracle.bpbreid_np import part_distance
+    from tracklab_b200 import kernels
+    B, N, M, K, E = shape
+    rng = np.random.default_rng(11)
+    a = rng.normal(size=(B, N, K, E)).astype(np.float32); b = rng.normal(size=(B, M, K, E)).astype(np.float32)
+    va = (rng.uniform(size=(B, N, K)) < 0.8).astype(np.float32); vb = (rng.uniform(size=(B, M, K)) < 0.8).astype(np.float32)
+    va[..., 0] = 1.0; vb[..., 0] = 1.0
+    got = kernels.part_dist(*(torch.from_numpy(x).cuda() for x in (a, va, b, vb))).cpu().numpy()
+    for p in range(B):
+        for i in range(N):
+            ref = part_distance(a[p, i], va[p, i], b[p], vb[p])
+            assert np.abs(got[p, i] - ref).max() < 1e-5
+
+
+@pytest.mark.parametrize("aspect_const", [True, False])
+def test_kf_gate_matches_oracle(aspect_const):
+    from oracle import bpbreid_np, strongsort_np
+    from tracklab_b200 import kernels
+    rng = np.random.default_rng(12)
+    T, D = 37, 50
+    mean = np.zeros((T, 8)); mean[:, 0] = rng.uniform(100, 1800, T); mean[:, 1] = rng.uniform(100, 900, T)
+    mean[:, 2] = rng.uniform(0.3, 0.6, T); mean[:, 3] = rng.uniform(80, 300, T); mean[:, 4:] = rng.normal(0, 2, (T, 4))
+    A = rng.normal(size=(T, 8, 8)); cov = A @ A.transpose(0, 2, 1) + 5.0 * np.eye(8)
+    z = np.column_stack([rng.uniform(100, 1800, D), rng.uniform(100, 900, D), rng.uniform(0.3, 0.6, D), rng.uniform(80, 300, D)])
+    got, st = kernels.kf_gate(torch.from_numpy(mean).cuda(), torch.from_numpy(cov).cuda(), torch.from_numpy(z).cuda(), aspect_const)
+    got = got.cpu().numpy()
+    gate = strongsort_np.kf_gating if aspect_const else bpbreid_np.kf_gating
+    ref = np.stack([gate(mean[t], cov[t], z) for t in range(T)])
+    assert int(st.item()) == 0 and np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()

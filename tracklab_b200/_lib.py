@@ -74,6 +74,8 @@ def _declare(lib):
         "tk_iou_p1_f32": ([vp, vp, vp, ci, ci, ci, vp], ci),
         "tk_cosine_dist": ([vp, vp, vp, vp, ci, ci, ci, ci, vp], ci),
         "tk_lap_batched": ([vp, ci, ci, ci, cd, ci, vp, vp, vp, vp], ci),
+        "tk_part_dist": ([vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp], ci),
+        "tk_kf_gate": ([vp, vp, vp, vp, ci, ci, ci, vp, vp], ci),
         "tk_bytetrack_create": ([P(BytetrackParams), ci, ci, ci, P(vp)], ci),
         "tk_bytetrack_reset": ([vp, ci, vp], ci),
         "tk_bytetrack_run": ([vp, vp, vp, ci, vp, vp, vp, vp, vp], ci),

@@ -9,6 +9,7 @@
 //                                                                    strong_sort/sort/linear_assignment.py:55
 //
 // All are HBM/latency-bound: rows are staged once per CTA, outputs are written coalesced; batches fill the 148 SMs.
+#include "kf_xyah.cuh"
 #include "lap.cuh"
 #include "tk_common.cuh"
 #include "trackkern.h"
@@ -211,6 +212,68 @@ ct_dist_matrix_kernel(const double* __restrict__ a, const double* __restrict__ b
     for (int e = threadIdx.x; e < N * M; e += blockDim.x) op[e] = 1.0 - op[e] / dmax;
 }
 
+// Part-based appearance distance (BPBReID / KPR embeddings): a [B,N,K,E], va [B,N,K], b [B,M,K,E], vb [B,M,K] -> out [B,N,M] float32
+//   sum_k w_k * || a_k/|a_k| - b_k/|b_k| || / sum_k w_k / 2,  w_k = va_k * vb_k   (nn_matching.py:99-135 on the restated torchreid
+// function, see oracle/bpbreid_np.py). norms: scratch float32 [B*(N+M)*K] of the F.normalize denominators; one warp per pair.
+__global__ void __launch_bounds__(256)
+part_norm_kernel(const float* __restrict__ x, float* __restrict__ nrm, long long rows, int E) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    const float* p = x + r * E;
+    float s = 0.0f;
+    for (int k = threadIdx.x & 31; k < E; k += 32) s = fmaf(p[k], p[k], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) nrm[r] = fmaxf(sqrtf(s), 1e-12f);
+}
+
+__global__ void __launch_bounds__(256)
+part_dist_kernel(const float* __restrict__ a, const float* __restrict__ va, const float* __restrict__ b, const float* __restrict__ vb,
+                 const float* __restrict__ na, const float* __restrict__ nb, float* __restrict__ out, int N, int M, int K, int E) {
+    const int p = blockIdx.y, lane = threadIdx.x & 31;
+    const long long pair = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pair >= (long long)N * M) return;
+    const int i = (int)(pair / M), j = (int)(pair - (long long)i * M);
+    const size_t ra = (size_t)p * N + i, rb = (size_t)p * M + j;
+    float num = 0.0f, den = 0.0f;
+    for (int k = 0; k < K; ++k) {
+        const float* ap = a + (ra * K + k) * E;
+        const float* bp = b + (rb * K + k) * E;
+        const float an = na[ra * K + k], bn = nb[rb * K + k];
+        float acc = 0.0f;
+        for (int e = lane; e < E; e += 32) { const float d = __fdiv_rn(ap[e], an) - __fdiv_rn(bp[e], bn); acc = fmaf(d, d, acc); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const float w = __fmul_rn(va[ra * K + k], vb[rb * K + k]);
+        num = __fadd_rn(num, __fmul_rn(sqrtf(acc), w));
+        den = __fadd_rn(den, w);
+    }
+    if (lane == 0) out[((size_t)p * N + i) * M + j] = __fdiv_rn(__fdiv_rn(num, den), 2.0f);
+}
+
+// Squared Mahalanobis gating distances of the xyah Kalman filters (kalman_filter.py gating_distance of the ByteTrack /
+// StrongSORT / BPBReID plugins): mean [T,8], cov [T,8,8], z [D,4] (x, y, a, h) -> out [T,D].
+// aspect_const = 1: R = diag((h/20)^2, (h/20)^2, 1e-2, (h/20)^2) (byte_track/kalman_filter.py:126-153,
+// strong_sort/sort/kalman_filter.py:114-137 at confidence 0); 0: every term (h/20)^2 (bpbreid_strong_sort/sort/kalman_filter.py:106-136).
+__global__ void __launch_bounds__(128)
+kf_gate_kernel(const double* __restrict__ mean, const double* __restrict__ cov, const double* __restrict__ z, double* __restrict__ out,
+               int T, int D, int aspect_const, int* __restrict__ status) {
+    const int t = blockIdx.x;
+    __shared__ double c[24];
+    if (threadIdx.x == 0) {
+        const double* m = mean + (size_t)t * 8;
+        const double sp = (1.0 / 20) * m[3];
+        const double rr[4] = {sp * sp, sp * sp, aspect_const ? 1e-1 * 1e-1 : sp * sp, sp * sp};
+        double L[16], Sm[16], invd[4];
+        if (!tk::kf8_chol4(cov + (size_t)t * 64, rr, L, Sm, invd)) atomicOr(status, TK_DEV_BAD_CHOLESKY);
+        for (int i = 0; i < 4; ++i) c[i] = m[i];
+        for (int i = 0; i < 16; ++i) c[4 + i] = L[i];
+        for (int i = 0; i < 4; ++i) c[20 + i] = invd[i];
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) out[(size_t)t * D + d] = tk::kf8_maha(c, c + 4, c + 20, z + (size_t)d * 4);
+}
+
 }  // namespace
 
 extern "C" {
@@ -269,6 +332,31 @@ int tk_lap_batched(const double* cost, int n_problems, int N, int M, double cost
     if (smem > 220 * 1024) return TK_ERR_CAPACITY;
     TK_CUDA_TRY(cudaFuncSetAttribute(lap_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     lap_batched_kernel<<<n_problems, 128, smem, (cudaStream_t)stream>>>(cost, N, M, cost_limit, has_limit, x_out, y_out, status_dev);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_part_dist(const float* a, const float* va, const float* b, const float* vb, float* out, float* norm_scratch, int n_problems, int N,
+                 int M, int K, int E, void* stream) {
+    if (!a || !va || !b || !vb || !out || !norm_scratch || n_problems <= 0 || N < 0 || M < 0 || K <= 0 || E <= 0) return TK_ERR_ARG;
+    if (N == 0 || M == 0) return TK_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* na = norm_scratch;
+    float* nb = norm_scratch + (size_t)n_problems * N * K;
+    const long long rows_a = (long long)n_problems * N * K, rows_b = (long long)n_problems * M * K;
+    part_norm_kernel<<<(unsigned)((rows_a + 7) / 8), 256, 0, st>>>(a, na, rows_a, E);
+    part_norm_kernel<<<(unsigned)((rows_b + 7) / 8), 256, 0, st>>>(b, nb, rows_b, E);
+    dim3 grid((unsigned)(((long long)N * M + 7) / 8), n_problems);
+    part_dist_kernel<<<grid, 256, 0, st>>>(a, va, b, vb, na, nb, out, N, M, K, E);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_kf_gate(const double* mean, const double* cov, const double* z, double* out, int n_tracks, int n_dets, int aspect_const,
+               int* status_dev, void* stream) {
+    if (!mean || !cov || !z || !out || !status_dev || n_tracks < 0 || n_dets < 0) return TK_ERR_ARG;
+    if (n_tracks == 0 || n_dets == 0) return TK_OK;
+    kf_gate_kernel<<<n_tracks, 128, 0, (cudaStream_t)stream>>>(mean, cov, z, out, n_tracks, n_dets, aspect_const, status_dev);
     TK_CUDA_TRY(cudaGetLastError());
     return TK_OK;
 }

@@ -234,6 +234,39 @@ def lap_batched(cost: torch.Tensor, cost_limit: float | None = None, status: tor
     return x, y, status
 
 
+def part_dist(a: torch.Tensor, va: torch.Tensor, b: torch.Tensor, vb: torch.Tensor) -> torch.Tensor:
+    """Part-based appearance distance: a [B,N,K,E], va [B,N,K], b [B,M,K,E], vb [B,M,K] float32 -> [B,N,M] float32
+    (C ABI: tk_part_dist)."""
+    lib = _lib.load()
+    for t in (a, va, b, vb):
+        _cuda(t, "part_dist input")
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    B, N, K, E = a.shape
+    M = b.shape[1]
+    out = torch.empty((B, N, M), dtype=torch.float32, device=a.device)
+    scratch = torch.empty((B * (N + M) * K,), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.tk_part_dist(a.data_ptr(), va.data_ptr(), b.data_ptr(), vb.data_ptr(), out.data_ptr(), scratch.data_ptr(), B, N, M, K, E,
+                                    _stream()), "tk_part_dist"); _count()
+    return out
+
+
+def kf_gate(mean: torch.Tensor, cov: torch.Tensor, z: torch.Tensor, aspect_const: bool = True, status: torch.Tensor | None = None):
+    """Squared Mahalanobis gating distances: mean [T,8], cov [T,8,8], z [D,4] float64 -> [T,D] (C ABI: tk_kf_gate)."""
+    lib = _lib.load()
+    for t in (mean, cov, z):
+        _cuda(t, "kf_gate input")
+        assert t.dtype == torch.float64 and t.is_contiguous()
+    T, D = mean.shape[0], z.shape[0]
+    out = torch.empty((T, D), dtype=torch.float64, device=mean.device)
+    if status is None:
+        status = torch.zeros((1,), dtype=torch.int32, device=mean.device)
+    with torch.cuda.device(mean.device):
+        _lib.check(lib.tk_kf_gate(mean.data_ptr(), cov.data_ptr(), z.data_ptr(), out.data_ptr(), T, D, int(aspect_const), status.data_ptr(),
+                                  _stream()), "tk_kf_gate"); _count()
+    return out, status
+
+
 REID_MEAN = (0.485, 0.456, 0.406)
 REID_STD = (0.229, 0.224, 0.225)
 
