@@ -330,6 +330,7 @@ extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, in
 // One CTA per (output row, crop): the vertical taps are shared by the row, each thread owns one output column.
 namespace {
 
+constexpr int CR_ROWS = 8;    // output rows per CTA of the crop / frame resize kernels
 constexpr int CR_KMAX = 64;   // taps per axis: 2*ceil(scale)+1 -> crops up to ~31x the output size (a full 4K row into 128 px)
 
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for one output index (bilinear filter, support 1)
@@ -368,9 +369,9 @@ __global__ void __launch_bounds__(128)
 crop_resize_norm_kernel(const unsigned char* __restrict__ frames, size_t frame_stride, int H, int W,
                         const double* __restrict__ dets, const int* __restrict__ det_frame, OutT* __restrict__ out,
                         int out_h, int out_w, float m0, float m1, float m2, float s0, float s1, float s2, int nhwc) {
-    __shared__ int kv[CR_KMAX];
-    __shared__ int s_ymin, s_ny;
-    const int n = blockIdx.y, yy = blockIdx.x;
+    __shared__ int kv[CR_ROWS][CR_KMAX];
+    __shared__ int s_ymin[CR_ROWS], s_ny[CR_ROWS];
+    const int n = blockIdx.y, y0 = blockIdx.x * CR_ROWS;
     const double* d = dets + (size_t)n * 7;
     // StrongSORT crop rule (strong_sort.py:102-108): centre box -> int() truncation -> clip
     const double cx = (d[0] + d[2]) / 2, cy = (d[1] + d[3]) / 2, bw = d[2] - d[0], bh = d[3] - d[1];
@@ -379,38 +380,48 @@ crop_resize_norm_kernel(const unsigned char* __restrict__ frames, size_t frame_s
     const int cw = x2 - x1, ch = y2 - y1;
     const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
     const unsigned char* img = frames + (size_t)det_frame[n] * frame_stride;
-    if (threadIdx.x == 0 && cw > 0 && ch > 0) { int ym; s_ny = pil_taps(ch, out_h, yy, kv, ym); s_ymin = ym; }
+    // the vertical taps of the CTA's rows (one thread each); the horizontal taps of a column are derived once per thread and
+    // reused for all CR_ROWS rows (they only depend on the crop width and the column: ncu showed the one-row version
+    // issue-bound on re-deriving them in double precision for every output pixel)
+    if (threadIdx.x < CR_ROWS && y0 + threadIdx.x < out_h && cw > 0 && ch > 0) {
+        int ym;
+        s_ny[threadIdx.x] = pil_taps(ch, out_h, y0 + threadIdx.x, kv[threadIdx.x], ym);
+        s_ymin[threadIdx.x] = ym;
+    }
     __syncthreads();
     for (int xx = threadIdx.x; xx < out_w; xx += blockDim.x) {
-        int v[3] = {0, 0, 0};
-        if (cw > 0 && ch > 0) {
-            int kh[CR_KMAX], xmin;
-            const int nx = pil_taps(cw, out_w, xx, kh, xmin);
-            int acc[3] = {1 << 21, 1 << 21, 1 << 21};
-            for (int ky = 0; ky < s_ny; ++ky) {
-                const unsigned char* row = img + ((size_t)(y1 + s_ymin + ky) * W + (x1 + xmin)) * 3;
-                int h[3] = {1 << 21, 1 << 21, 1 << 21};
-                // (when a size already matches, Pillow skips that pass; the taps then are {1<<22, 0}, i.e. the identity)
-                for (int kx = 0; kx < nx; ++kx) {
-                    h[0] += row[kx * 3 + 0] * kh[kx]; h[1] += row[kx * 3 + 1] * kh[kx]; h[2] += row[kx * 3 + 2] * kh[kx];
+        int kh[CR_KMAX], xmin = 0, nx = 0;
+        if (cw > 0 && ch > 0) nx = pil_taps(cw, out_w, xx, kh, xmin);
+        for (int r = 0; r < CR_ROWS && y0 + r < out_h; ++r) {
+            const int yy = y0 + r;
+            int v[3] = {0, 0, 0};
+            if (cw > 0 && ch > 0) {
+                int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+                for (int ky = 0; ky < s_ny[r]; ++ky) {
+                    const unsigned char* row = img + ((size_t)(y1 + s_ymin[r] + ky) * W + (x1 + xmin)) * 3;
+                    int h[3] = {1 << 21, 1 << 21, 1 << 21};
+                    // (when a size already matches, Pillow skips that pass; the taps then are {1<<22, 0}, i.e. the identity)
+                    for (int kx = 0; kx < nx; ++kx) {
+                        h[0] += row[kx * 3 + 0] * kh[kx]; h[1] += row[kx * 3 + 1] * kh[kx]; h[2] += row[kx * 3 + 2] * kh[kx];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) acc[c] += clip8(h[c]) * kv[r][ky];
                 }
 #pragma unroll
-                for (int c = 0; c < 3; ++c) acc[c] += clip8(h[c]) * kv[ky];
+                for (int c = 0; c < 3; ++c) v[c] = clip8(acc[c]);
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[c] = clip8(acc[c]);
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float t = __fdiv_rn((float)v[c], 255.0f);                 // ToTensor
-            const float o = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);      // Normalize
-            size_t idx;
-            if (nhwc == TK_CROP_LAYOUT_S2D16)   // 2x2 space-to-depth, 16-channel pitch, zero border of 2 before / 1 after (see trackkern.h)
-                idx = ((((size_t)n * (out_h / 2 + 3) + (yy >> 1) + 2) * (out_w / 2 + 3) + (xx >> 1) + 2) << 4) + (((yy & 1) * 2 + (xx & 1)) * 3 + c);
-            else
-                idx = nhwc ? (((size_t)n * out_h + yy) * out_w + xx) * nhwc + c   // nhwc = channel pitch (3, or 8 with zero padding)
-                           : (((size_t)n * 3 + c) * out_h + yy) * out_w + xx;
-            out[idx] = cvt_out<OutT>(o);
+            for (int c = 0; c < 3; ++c) {
+                const float t = __fdiv_rn((float)v[c], 255.0f);                 // ToTensor
+                const float o = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);      // Normalize
+                size_t idx;
+                if (nhwc == TK_CROP_LAYOUT_S2D16)   // 2x2 space-to-depth, 16-channel pitch, zero border of 2 before / 1 after (see trackkern.h)
+                    idx = ((((size_t)n * (out_h / 2 + 3) + (yy >> 1) + 2) * (out_w / 2 + 3) + (xx >> 1) + 2) << 4) + (((yy & 1) * 2 + (xx & 1)) * 3 + c);
+                else
+                    idx = nhwc ? (((size_t)n * out_h + yy) * out_w + xx) * nhwc + c   // nhwc = channel pitch (3, or 8 with zero padding)
+                               : (((size_t)n * 3 + c) * out_h + yy) * out_w + xx;
+                out[idx] = cvt_out<OutT>(o);
+            }
         }
     }
 }
@@ -422,28 +433,34 @@ template <typename OutT>
 __global__ void __launch_bounds__(128)
 resize_frames_kernel(const unsigned char* __restrict__ frames, size_t frame_stride, int H, int W, OutT* __restrict__ out,
                      int out_h, int out_w, float scale) {
-    __shared__ int kv[CR_KMAX];
-    __shared__ int s_ymin, s_ny;
-    const int n = blockIdx.y, yy = blockIdx.x;
+    __shared__ int kv[CR_ROWS][CR_KMAX];
+    __shared__ int s_ymin[CR_ROWS], s_ny[CR_ROWS];
+    const int n = blockIdx.y, y0 = blockIdx.x * CR_ROWS;
     const unsigned char* img = frames + (size_t)n * frame_stride;
-    if (threadIdx.x == 0) { int ym; s_ny = pil_taps(H, out_h, yy, kv, ym); s_ymin = ym; }
+    if (threadIdx.x < CR_ROWS && y0 + threadIdx.x < out_h) {
+        int ym;
+        s_ny[threadIdx.x] = pil_taps(H, out_h, y0 + threadIdx.x, kv[threadIdx.x], ym);
+        s_ymin[threadIdx.x] = ym;
+    }
     __syncthreads();
     for (int xx = threadIdx.x; xx < out_w; xx += blockDim.x) {
         int kh[CR_KMAX], xmin;
-        const int nx = pil_taps(W, out_w, xx, kh, xmin);
-        int acc[3] = {1 << 21, 1 << 21, 1 << 21};
-        for (int ky = 0; ky < s_ny; ++ky) {
-            const unsigned char* row = img + ((size_t)(s_ymin + ky) * W + xmin) * 3;
-            int h[3] = {1 << 21, 1 << 21, 1 << 21};
-            for (int kx = 0; kx < nx; ++kx) {
-                h[0] += row[kx * 3 + 0] * kh[kx]; h[1] += row[kx * 3 + 1] * kh[kx]; h[2] += row[kx * 3 + 2] * kh[kx];
+        const int nx = pil_taps(W, out_w, xx, kh, xmin);   // once per column, reused for the CTA's rows
+        for (int r = 0; r < CR_ROWS && y0 + r < out_h; ++r) {
+            int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+            for (int ky = 0; ky < s_ny[r]; ++ky) {
+                const unsigned char* row = img + ((size_t)(s_ymin[r] + ky) * W + xmin) * 3;
+                int h[3] = {1 << 21, 1 << 21, 1 << 21};
+                for (int kx = 0; kx < nx; ++kx) {
+                    h[0] += row[kx * 3 + 0] * kh[kx]; h[1] += row[kx * 3 + 1] * kh[kx]; h[2] += row[kx * 3 + 2] * kh[kx];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) acc[c] += clip8(h[c]) * kv[r][ky];
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) acc[c] += clip8(h[c]) * kv[ky];
+            for (int c = 0; c < 3; ++c)
+                out[(((size_t)n * 3 + c) * out_h + y0 + r) * out_w + xx] = cvt_out<OutT>(__fmul_rn((float)clip8(acc[c]), scale));
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-            out[(((size_t)n * 3 + c) * out_h + yy) * out_w + xx] = cvt_out<OutT>(__fmul_rn((float)clip8(acc[c]), scale));
     }
 }
 
@@ -455,7 +472,7 @@ extern "C" int tk_resize_frames_u8(const unsigned char* frames, int n_frames, in
     if (out_dtype != TK_DTYPE_F32 && out_dtype != TK_DTYPE_BF16) return TK_ERR_ARG;
     if (n_frames == 0) return TK_OK;
     if (2 * ((W + out_w - 1) / out_w) + 1 > CR_KMAX || 2 * ((H + out_h - 1) / out_h) + 1 > CR_KMAX) return TK_ERR_CAPACITY;
-    dim3 grid(out_h, n_frames);
+    dim3 grid((out_h + CR_ROWS - 1) / CR_ROWS, n_frames);
     if (out_dtype == TK_DTYPE_F32)
         resize_frames_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(frames, (size_t)frame_stride_bytes, H, W, (float*)out, out_h, out_w, scale);
     else
@@ -473,7 +490,7 @@ extern "C" int tk_crop_resize_norm(const unsigned char* frames, int H, int W, lo
     if (out_nhwc == TK_CROP_LAYOUT_S2D16 && ((out_h | out_w) & 1)) return TK_ERR_ARG;
     if (n_dets == 0) return TK_OK;
     if (2 * ((W + out_w - 1) / out_w) + 1 > CR_KMAX || 2 * ((H + out_h - 1) / out_h) + 1 > CR_KMAX) return TK_ERR_CAPACITY;
-    dim3 grid(out_h, n_dets);
+    dim3 grid((out_h + CR_ROWS - 1) / CR_ROWS, n_dets);
     cudaStream_t st = (cudaStream_t)stream;
     if (out_dtype == TK_DTYPE_F32)
         crop_resize_norm_kernel<float><<<grid, 128, 0, st>>>(frames, (size_t)frame_stride_bytes, H, W, dets, det_frame, (float*)out, out_h,
