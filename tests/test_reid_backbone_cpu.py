@@ -53,3 +53,41 @@ def test_osnet_reid_equals_vendored_reference(ibn):
         a, b = ref(x), mine(x)
     assert a.shape == b.shape == (2, 512)
     assert torch.allclose(a, b, rtol=1e-4, atol=1e-4 * a.abs().max().item())
+
+
+def test_space_to_depth_stem_weights_reproduce_the_7x7_stride2_convolution():
+    """Host logic of the fused ReID executor: the 4x4 / stride-1 weights on the padded 2x2 space-to-depth crop (the layout
+    tk_crop_resize_norm writes, TK_CROP_LAYOUT_S2D16) give the 7x7 / stride-2 / pad-3 stem output exactly (fp64)."""
+    import torch.nn.functional as F
+    from tracklab_b200.nets.resnet_fused import stem_weight_s2d16
+    torch.manual_seed(3)
+    x = torch.randn(2, 3, 32, 16, dtype=torch.float64)
+    w = torch.randn(8, 3, 7, 7, dtype=torch.float64)
+    ref = F.conv2d(x, w, None, 2, 3)
+    N, _, H, W = x.shape
+    buf = torch.zeros(N, H // 2 + 3, W // 2 + 3, 16, dtype=torch.float64)                       # NHWC, zero border 2 before / 1 after
+    for yy in range(H):
+        for xx in range(W):
+            c0 = ((yy & 1) * 2 + (xx & 1)) * 3
+            buf[:, (yy >> 1) + 2, (xx >> 1) + 2, c0:c0 + 3] = x[:, :, yy, xx]
+    got = F.conv2d(buf.permute(0, 3, 1, 2), stem_weight_s2d16(w), None, 1, 0)
+    assert got.shape == ref.shape and torch.allclose(got, ref, rtol=0, atol=1e-12)
+
+
+def test_streaming_drain_schedule_and_crop_buckets():
+    from tracklab_b200.nets.resnet_fused import ResNet50Fused
+    from tracklab_b200.video_pipeline import DetectTrackPipeline
+
+    class _Det:
+        tail_sizes = set()
+
+    pipe = DetectTrackPipeline.__new__(DetectTrackPipeline)
+    pipe.batch, pipe.det = 50, _Det()
+    sched = pipe._schedule(500, True)
+    assert sched[:9] == [(i, i + 50) for i in range(0, 450, 50)] and sched[9:] == [(450, 475), (475, 488), (488, 500)]
+    assert sorted(_Det.tail_sizes) == [12, 13, 25]
+    assert pipe._schedule(500, False) == [(i, i + 50) for i in range(0, 500, 50)]                 # HBM-resident frames: no drain
+    assert pipe._schedule(480, True)[-1] == (450, 480)                                             # ragged tail: left as it is
+    covered = [f for a, b in sched for f in range(a, b)]
+    assert covered == list(range(500))
+    assert [ResNet50Fused.bucket(n) for n in (1, 64, 65, 572, 760)] == [64, 64, 128, 576, 768]
