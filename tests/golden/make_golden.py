@@ -42,6 +42,10 @@ CASES = {
     "ocsort_ctdist_byte_s1003": ("ocsort", dict(seed=1003, n_frames=120, n_ids=30, conf_range=(0.05, 1.0)),
                                  dict(det_thresh=0.5, max_age=10, min_hits=2, iou_threshold=0.3,
                                       delta_t=2, asso_func="ct_dist", inertia=0.2, use_byte=True)),
+    "ocsort_diou_s1004": ("ocsort", dict(seed=1004, n_frames=80, n_ids=24, conf_range=(0.05, 1.0)),
+                          dict(det_thresh=0.5, max_age=12, min_hits=2, iou_threshold=0.3, delta_t=3, asso_func="diou", inertia=0.2, use_byte=True)),
+    "ocsort_ciou_s1005": ("ocsort", dict(seed=1005, n_frames=80, n_ids=24, conf_range=(0.05, 1.0)),
+                          dict(det_thresh=0.5, max_age=12, min_hits=2, iou_threshold=0.3, delta_t=1, asso_func="ciou", inertia=0.3, use_byte=False)),
     "strongsort_s4000": ("strongsort", dict(seed=4000, n_frames=160, n_ids=30, emb_dim=64),
                          dict(max_dist=0.1594374041012136, max_iou_dist=0.5431835667667874, max_age=40, max_unmatched_preds=0,
                               n_init=3, nn_budget=100, mc_lambda=0.995, ema_alpha=0.8962157769329083)),
