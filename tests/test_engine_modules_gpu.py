@@ -86,3 +86,29 @@ def test_bpbreid_module_through_engine_matches_reference_plugin():
     assert np.abs(box - ref[:, 1:5]).max() < 1e-6
     born = np.isnan(ref[:, 5])
     assert all((not isinstance(p, np.ndarray)) == b for p, b in zip(sel["track_bbox_pred_kf_ltwh"], born))
+
+
+def test_bpbreid_module_matches_the_real_engine_golden():
+    """tests/golden/engine_bpbreid.npz was produced by the REAL OfflineTrackingEngine + the reference BPBReIDStrongSORT wrapper
+    (make_engine_bpbreid_golden.py); the drop-in through the mirrored engine protocol must give the same per-detection columns."""
+    from tracklab_b200 import modules
+    from tracklab_b200.engine_mirror import OfflineEngineMirror
+    g = np.load(os.path.join(HERE, "golden", "engine_bpbreid.npz"))
+    video = make_video(**ast.literal_eval(str(g["gen"])))
+    cfgd = ast.literal_eval(str(g["cfg"]))
+    vmd, imd, det = _tracking_frames([video])
+    det["embeddings"] = list(video.embeddings)
+    det["visibility_scores"] = list(video.visibility.astype(bool))
+    out = OfflineEngineMirror([modules.BPBReIDStrongSORT(types.SimpleNamespace(**cfgd), "cuda:0")], vmd, imd, det).track_dataset().sort_index()
+    assert np.array_equal(out.index.to_numpy(), g["det_index"])
+    has, ref_has = out["track_id"].notna().to_numpy(), ~np.isnan(g["track_id"])
+    assert np.array_equal(has, ref_has)
+    fwd, bwd = {}, {}
+    for x, y in zip(out["track_id"].to_numpy(dtype=float, na_value=np.nan)[has], g["track_id"][ref_has]):
+        assert fwd.setdefault(x, y) == y and bwd.setdefault(y, x) == x
+    sel = out[has]
+    assert np.array_equal(sel["hits"].to_numpy(dtype=float), g["hits"][ref_has]) and np.array_equal(sel["age"].to_numpy(dtype=float), g["age"][ref_has])
+    code = np.array([(1 if m[0] == "R" else 2) if isinstance(m, tuple) else 0 for m in sel["matched_with"]])
+    assert np.array_equal(code, g["matched_code"][ref_has])
+    box = np.stack([np.asarray(b, dtype=np.float64) for b in sel["track_bbox_kf_ltwh"]])
+    assert np.abs(box - g["kf_ltwh"][ref_has]).max() < 1e-6
