@@ -17,13 +17,18 @@
 // for 300 frames, so T is several hundred while D is ~40, and the reference evaluates T x D x K part distances of
 // length E per frame although the Mahalanobis gate then overwrites nearly all of them with 1e5. Here the gate goes
 // first:
-//   master CTA : predict only the filters still being predicted (octets); a per-track gate rectangle
-//                (|dx| <= sqrt(chi2 * S_xx), a necessary condition of the 4-d gate by Cauchy-Schwarz) prunes T x D
-//                with two compares per pair out of shared memory; survivors get the exact Cholesky gate;
-//   all CTAs   : the part-based distance of the surviving pairs only, one warp per pair (group barrier either side);
-//   master CTA : fuse, keep the rows that still have a feasible entry, solve both assignments on that compacted
-//                problem (lap.cuh: entries above the threshold are "unmatched at cost 0", so all-zero rows cannot change
-//                the optimum), update filters / features, births, deletions, 14-column rows.
+//   master CTA : predict only the filters still being predicted (octets); a per-track float32 gate rectangle
+//                (|dx| <= sqrt(chi2 * S_xx), a necessary condition of the 4-d gate by Cauchy-Schwarz, widened by a margin)
+//                prunes T x D with two compares per pair out of shared memory (count / scan / write, no atomics);
+//   worker CTAs: meanwhile apply the previous frame's feature updates (visibility-aware EMA, births) and L2-normalise
+//                the frame's detection parts;
+//   all CTAs   : (group barrier) 4 rectangle hits per warp step get the exact Mahalanobis distance from the per-track
+//                cached Cholesky factor; the survivors' part-based distance is evaluated by the whole warp on the
+//                pre-normalised part embeddings, software-pipelined over the parts;
+//   master CTA : (group barrier) fuse, keep the rows that still have a feasible entry, solve both assignments on that
+//                compacted problem (lap.cuh: entries above the threshold are "unmatched at cost 0", so all-zero rows cannot
+//                change the optimum), update filters, births, deletions, 14-column rows, publish the feature updates
+//                (third group barrier).
 // Ages and time_since_update are differences of a per-video tick, so stale tracks cost nothing per frame; the hot
 // per-track integers and gate rectangles are mirrored in shared memory for the launch.
 #include <cooperative_groups.h>
