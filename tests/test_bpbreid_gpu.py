@@ -121,3 +121,19 @@ def test_bpbreid_two_videos_in_one_launch():
         want, wf = BpbreidStrongSortOracle(**hyper).run_video(v.dets, v.offsets, v.embeddings, v.visibility)
         assert F == v.n_frames
         assert_bpbreid_rows_match(got, gf, want, wf, box_tol=1e-6, dist_tol=1e-5, allow_relabel=True)
+
+
+def test_bpbreid_frames_whose_detections_are_all_filtered_out():
+    """A frame with rows, all below min_bbox_confidence: predict only, no tracker.update (strong_sort.py:86-89) — the group
+    barriers of the cooperative kernel must still pair up on that path."""
+    from oracle.bpbreid_np import BpbreidStrongSortOracle
+    hyper = dict(ema_alpha=0.9, mc_lambda=0.995, max_dist=0.5, max_iou_distance=0.8, max_age=30, n_init=0, min_bbox_confidence=0.3,
+                 max_kalman_prediction_without_update=3)
+    v = make_video(seed=6600, n_frames=40, n_ids=10, emb_dim=16, n_parts=3, conf_range=(0.4, 1.0), fp_rate=0.0)
+    for f in (5, 6, 17, 39):
+        v.dets[v.offsets[f]:v.offsets[f + 1], 4] = 0.1
+    ref_rows, ref_fr = BpbreidStrongSortOracle(**hyper).run_video(v.dets, v.offsets, v.embeddings, v.visibility)
+    assert not np.isin(ref_fr, [5, 6, 17, 39]).any()
+    for ncta in (1, 4):
+        rows, fr = _run_device(v, hyper, ncta=ncta, chunks=2)
+        assert_bpbreid_rows_match(rows, fr, ref_rows, ref_fr, allow_relabel=True)
