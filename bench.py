@@ -346,7 +346,10 @@ def run_ours(args):
                     "achieved": epi["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
                     "bytes_per_launch": epi["bytes"] / epi["launches"], "avg_launch_ms": epi["total_ms"] / epi["launches"],
                     "launches_timed": epi["launches"], "us_per_frame": epi["us_per_frame"],
-                    "how": "CUDA events around each of the launches of one eager detector forward (batch %d), sums" % B}
+                    "how": "CUDA events around each of the launches of one eager detector forward (batch %d), sums" % B,
+                    "traffic_note": "ncu --set full (profiles/r01b_ncu_summary.md): a launch with 41.0 MB in / 41.0 MB out reads 41.0 MB "
+                                    "from DRAM and writes 0.0-3.4 MB: the output stays in the 126 MB L2 for the next convolution, so DRAM "
+                                    "traffic is below the algorithmic bytes; no re-reads"}
         else:
             roof = dict(lb_roof, peak_source=peak_src, traffic=None)
         roof["frac"] = roof["achieved"] / peak
