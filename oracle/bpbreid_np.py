@@ -10,8 +10,9 @@ Restates
   /root/reference/plugins/track/bpbreid_strong_sort/sort/linear_assignment.py:11-73,132-175
   /root/reference/plugins/track/bpbreid_strong_sort/sort/iou_matching.py:42-78
 and the wrapper /root/reference/tracklab/wrappers/track/bpbreid_strong_sort_api.py:73-118 (frames without rows are skipped;
-no confidence filter besides ``min_bbox_confidence``). Only ``matching_strategy="strong_sort_matching"`` with
-``motion_criterium="iou"`` (the reference YAML) is restated.
+no confidence filter besides ``min_bbox_confidence``). Both matching strategies are restated (``strong_sort_matching``, the
+reference YAML and what the device kernel implements, and the single-stage ``bot_sort_matching`` of tracker.py:335-363 with
+``_full_cost_metric`` :169-240) for ``motion_criterium="iou"``.
 
 PARITY UNPINNED for the appearance term: ``compute_distance_matrix_using_bp_features`` lives in the un-vendored torchreid
 git dependency; it is restated (SURVEY.md §8c [3P-memory]) as the visibility-weighted mean over parts of the Euclidean
@@ -128,7 +129,9 @@ def _min_cost(cost, max_distance, t_idx, d_idx):  # linear_assignment.py:11-73
 
 class BpbreidStrongSortOracle:
     def __init__(self, ema_alpha=0.9, mc_lambda=0.995, max_dist=0.5, max_iou_distance=0.8, max_age=300, n_init=0,
-                 min_bbox_confidence=0.0, max_kalman_prediction_without_update=7):
+                 min_bbox_confidence=0.0, max_kalman_prediction_without_update=7, matching_strategy="strong_sort_matching",
+                 gating_thres_factor=1.0, w_kfgd=1.0, w_reid=1.0, w_st=1.0):
+        self.strategy, self.gtf, self.w = matching_strategy, gating_thres_factor, (w_kfgd, w_reid, w_st)
         self.alpha, self.lam, self.max_dist, self.max_iou = ema_alpha, mc_lambda, max_dist, max_iou_distance
         self.max_age, self.n_init, self.min_conf, self.max_pred = max_age, n_init, min_bbox_confidence, max_kalman_prediction_without_update
         self.tracks, self.next_id = [], 1
@@ -146,7 +149,9 @@ class BpbreidStrongSortOracle:
                 t.mean, t.cov = kf_predict(t.mean, t.cov)
             t.age += 1
             t.tsu += 1
-        if len(dets) > 0:
+        if len(dets) > 0 and self.strategy == "bot_sort_matching":
+            self._update_bot_sort(dets, cls_of, conf_of)
+        elif len(dets) > 0:
             confirmed = [i for i, t in enumerate(self.tracks) if t.state == "c"]
             unconfirmed = [i for i, t in enumerate(self.tracks) if t.state != "c"]
             all_d = list(range(len(dets)))
@@ -187,33 +192,7 @@ class BpbreidStrongSortOracle:
                 m = {dd: tt for tt, dd in pairs_b}
                 for i, di in enumerate(un_d_a):
                     dets[di].matched_with = ("S", cost_b[cand.index(m[di]), i]) if di in m else None
-            for k, j in pairs_a + pairs_b:  # Track.update (track.py:137-174)
-                t, d = self.tracks[k], dets[j]
-                t.conf, t.cls, t.last_det = conf_of[id(d)], int(cls_of[id(d)]), d
-                t.last_pred_ltwh = t.ltwh()
-                t.mean, t.cov = kf_update(t.mean, t.cov, d.xyah(), d.confidence)
-                tv, dv_ = t.vis, d.vis
-                xor = np.logical_xor(tv, dv_)
-                et = (tv * dv_) * np.float32(self.alpha) + xor * tv
-                ed = (tv * dv_) * np.float32(1 - self.alpha) + xor * dv_
-                sm = np.expand_dims(et, 1) * t.feat + np.expand_dims(ed, 1) * d.feat
-                sm[np.logical_and(et == 0.0, ed == 0.0)] = 1
-                t.feat, t.vis = sm, np.maximum(tv, dv_)
-                t.hits += 1
-                t.tsu = 0
-                if t.state == "t" and t.hits >= self.n_init:
-                    t.state = "c"
-            for k in list(set(un_t_a + un_t_b)):  # mark_missed (track.py:181-187)
-                t = self.tracks[k]
-                if t.state == "t":
-                    t.state = "d"
-                elif t.tsu > self.max_age:
-                    t.state = "d"
-            for j in un_d:
-                d = dets[j]
-                self.tracks.append(_Trk(d, self.next_id, cls_of[id(d)], conf_of[id(d)], self.n_init))
-                self.next_id += 1
-            self.tracks = [t for t in self.tracks if t.state != "d"]
+            self._apply(dets, pairs_a + pairs_b, list(set(un_t_a + un_t_b)), un_d, cls_of, conf_of)
         rows = []
         for t in self.tracks:  # strong_sort.py:96-120
             if t.state != "c" or t.tsu > 0:
@@ -223,6 +202,73 @@ class BpbreidStrongSortOracle:
             pred = t.last_pred_ltwh if t.last_pred_ltwh is not None else np.full(4, np.nan)
             rows.append([t.id, *t.ltwh(), *pred, code, dist, t.hits, t.age, float(d.id)])
         return np.asarray(rows, dtype=np.float64).reshape(-1, 14)
+
+    def _update_bot_sort(self, dets, cls_of, conf_of):
+        """tracker.py:335-363 + _full_cost_metric :169-240: one stage over ALL tracks on (w_kfgd * pos + w_reid * app + w_st * st) /
+        sum(w), pos = sqrt(gating distance) / (sqrt(chi2) * gating_thres_factor); entries are voided where the position OR the
+        appearance gate fails — np.logical_or(pos_gate, app_gate, st_gate) uses its third argument as the OUTPUT array, so the
+        spatio-temporal gate is never applied (reproduced)."""
+        w_k, w_r, w_s = self.w
+        idx, all_d = list(range(len(self.tracks))), list(range(len(dets)))
+        for d in dets:
+            d.matched_with = None
+        if not idx:
+            return self._apply(dets, [], [], all_d, cls_of, conf_of)
+        zs = np.asarray([d.xyah() for d in dets])
+        df, dv = np.stack([d.feat for d in dets]), np.stack([d.vis for d in dets])
+        boxes = np.asarray([d.ltwh for d in dets])
+        thr = np.sqrt(CHI2_4)
+        pos, app, st = (np.empty((len(idx), len(dets))) for _ in range(3))
+        for r, k in enumerate(idx):
+            t = self.tracks[k]
+            pos[r] = np.sqrt(kf_gating(t.mean, t.cov, zs)) / (thr * self.gtf)
+            app[r] = part_distance(t.feat, t.vis, df, dv)
+            st[r] = 1.0 - iou_tlwh_one_to_many(t.ltwh(), boxes)
+        cost = (w_k * pos + w_r * app + st * w_s) / (w_k + w_r + w_s)
+        pos_gate = pos > 1.0 if w_k > 0 else np.zeros_like(pos, dtype=bool)
+        app_gate = app > self.max_dist if w_r > 0 else np.zeros_like(app, dtype=bool)
+        st_gate = st > self.max_iou if w_s > 0 else np.zeros_like(st, dtype=bool)
+        if w_k > 0:
+            cost[np.logical_or(pos_gate, app_gate)] = INFTY
+        elif w_s > 0:
+            cost[np.logical_or(app_gate, st_gate)] = INFTY
+        else:
+            cost[app_gate] = INFTY
+        pairs, _, un_d = _min_cost(cost, self.max_dist, idx, all_d)
+        un_t = list(set(idx) - set(k for k, _ in pairs))
+        m = {dd: tt for tt, dd in pairs}
+        for i, di in enumerate(all_d):
+            dets[di].matched_with = ("R", cost[idx.index(m[di]), i]) if di in m else None
+        self._apply(dets, pairs, un_t, un_d, cls_of, conf_of)
+
+    def _apply(self, dets, pairs, unmatched_tracks, un_d, cls_of, conf_of):
+        for k, j in pairs:  # Track.update (track.py:137-174)
+            t, d = self.tracks[k], dets[j]
+            t.conf, t.cls, t.last_det = conf_of[id(d)], int(cls_of[id(d)]), d
+            t.last_pred_ltwh = t.ltwh()
+            t.mean, t.cov = kf_update(t.mean, t.cov, d.xyah(), d.confidence)
+            tv, dv_ = t.vis, d.vis
+            xor = np.logical_xor(tv, dv_)
+            et = (tv * dv_) * np.float32(self.alpha) + xor * tv
+            ed = (tv * dv_) * np.float32(1 - self.alpha) + xor * dv_
+            sm = np.expand_dims(et, 1) * t.feat + np.expand_dims(ed, 1) * d.feat
+            sm[np.logical_and(et == 0.0, ed == 0.0)] = 1
+            t.feat, t.vis = sm, np.maximum(tv, dv_)
+            t.hits += 1
+            t.tsu = 0
+            if t.state == "t" and t.hits >= self.n_init:
+                t.state = "c"
+        for k in unmatched_tracks:  # mark_missed (track.py:181-187)
+            t = self.tracks[k]
+            if t.state == "t":
+                t.state = "d"
+            elif t.tsu > self.max_age:
+                t.state = "d"
+        for j in un_d:
+            d = dets[j]
+            self.tracks.append(_Trk(d, self.next_id, cls_of[id(d)], conf_of[id(d)], self.n_init))
+            self.next_id += 1
+        self.tracks = [t for t in self.tracks if t.state != "d"]
 
     def run_video(self, dets, offsets, feats, vis):
         """dets float64 [N,7] wrapper rows (l,t,r,b,conf,cls,id); feats float32 [N,K,E]; vis [N,K]."""

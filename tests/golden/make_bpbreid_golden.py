@@ -30,6 +30,10 @@ CASES = {
     "bpbreid_tight_s6001": (dict(seed=6001, n_frames=120, n_ids=44, emb_dim=64, n_parts=9, conf_range=(0.2, 1.0), p_visible=0.6),
                             dict(YAML, max_dist=0.3, max_iou_distance=0.7, max_age=10, n_init=2, ema_alpha=0.8, mc_lambda=0.98,
                                  min_bbox_confidence=0.3, max_kalman_prediction_without_update=3)),
+    # single-stage weighted-sum matching (tracker.py:335-363): oracle only, the device kernel implements strong_sort_matching
+    "bpbreid_botsort_s6002": (dict(seed=6002, n_frames=100, n_ids=28, emb_dim=32, n_parts=6, conf_range=(0.3, 1.0)),
+                              dict(YAML, matching_strategy="bot_sort_matching", gating_thres_factor=1.5, w_kfgd=1, w_reid=2, w_st=1, max_age=20,
+                                   n_init=1)),
 }
 
 

@@ -20,6 +20,7 @@ def load_bpbreid_golden(name):
 
 BPB_KEYS = ("ema_alpha", "mc_lambda", "max_dist", "max_iou_distance", "max_age", "n_init", "min_bbox_confidence",
             "max_kalman_prediction_without_update")
+BPB_ORACLE_KEYS = BPB_KEYS + ("matching_strategy", "gating_thres_factor", "w_kfgd", "w_reid", "w_st")   # the oracle also restates bot_sort_matching
 
 
 def assert_bpbreid_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1e-6, dist_tol=1e-5, allow_relabel=False):
