@@ -367,7 +367,10 @@ def run_ours(args):
                               "ids": allm[:, 3].tolist(), "ms_per_step": allm[:, 4].tolist()},
                 "detector_rows_per_frame": det_rows / F}
         if world == 1:
-            line["other_trackers"] = other_tracker_timings(dev)
+            try:
+                line["other_trackers"] = other_tracker_timings(dev)
+            except Exception as e:   # secondary figures must never cost the headline line
+                line["other_trackers"] = {"error": f"{type(e).__name__}: {e}"}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args, video)
         print(json.dumps(line))
