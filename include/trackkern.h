@@ -73,6 +73,17 @@ int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, int W, long l
 int tk_crop_resize_norm(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,
                         const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,
                         const float* mean3, const float* std3, void* stream);
+/* crop_rule selects how a row becomes a pixel rectangle:
+ *   TK_CROP_RULE_STRONGSORT    rows [l,t,r,b,..]: centre box, int() truncation, clip (strong_sort.py:102-108) — tk_crop_resize_norm
+ *   TK_CROP_RULE_LTWH_ROUNDED  rows [l,t,w,h,..] (the detector's float32 bbox_ltwh): the ReID wrapper's rule
+ *                              /root/reference/tracklab/wrappers/reid/kpreid_api.py:118-121 = sanitize_bbox_ltwh + ltwh_to_ltrb in
+ *                              float32 + round-half-even (/root/reference/tracklab/utils/coordinates.py:216-267), crop = image[t:b, l:r]
+ */
+#define TK_CROP_RULE_STRONGSORT 0
+#define TK_CROP_RULE_LTWH_ROUNDED 1
+int tk_crop_resize_norm_ex(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,
+                           const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,
+                           const float* mean3, const float* std3, int crop_rule, void* stream);
 
 /* ---- RT-DETR detector pre/post-processing ---------------------------------------------------------------------
  * Replace transformers' RTDetrImageProcessor around the model call of
@@ -123,6 +134,16 @@ int tk_pack_detections(const float* boxes, const float* scores, const int* cls, 
                        int max_per_image, int keep_class, int img_w, int img_h, double fixed_conf, double category_id,
                        int* cursor_dev, double* dets_out, int* offsets_out, int dets_cap, int frames_cap,
                        int* status_dev, void* stream);
+/* Same, for the connected detect -> ReID -> associate pipeline: row_format TK_ROWS_LTRB writes [l,t,r,b,...] (the tracker
+ * wrappers' rows), TK_ROWS_LTWH writes [l,t,w,h,...] = the detector's float32 bbox_ltwh column as is (what the ReID wrapper
+ * kpreid_api.py:115-144 and bpbreid_strong_sort_api.py:73-90 read); frame_of_row_out (nullable, int[dets_cap]) receives for
+ * every appended row the index of its image inside this batch (the det_frame input of tk_crop_resize_norm). */
+#define TK_ROWS_LTRB 0
+#define TK_ROWS_LTWH 1
+int tk_pack_detections_ex(const float* boxes, const float* scores, const int* cls, const int* counts, int n_images,
+                          int max_per_image, int keep_class, int img_w, int img_h, double fixed_conf, double category_id,
+                          int* cursor_dev, double* dets_out, int* offsets_out, int dets_cap, int frames_cap,
+                          int* status_dev, int row_format, int* frame_of_row_out, void* stream);
 
 /* ---- Backbone epilogues (channels-last bf16; the convolutions themselves stay in cuDNN) ----------------
  * Replace the separate bias / activation / concat / max-pool / up-sampling passes the reference's runtimes
@@ -299,6 +320,12 @@ int tk_cosine_dist(const float* a, const float* b, double* out, float* norm_scra
                    void* stream);
 int tk_lap_batched(const double* cost, int n_problems, int N, int M, double cost_limit, int has_limit, int* x_out, int* y_out,
                    int* status_dev, void* stream);
+/* scipy.optimize.linear_sum_assignment(cost) restated operation by operation INCLUDING its tie-breaking (the solver of
+ * /root/reference/plugins/track/strong_sort/sort/linear_assignment.py:55 and bpbreid_strong_sort/sort/linear_assignment.py:56,
+ * whose equal `max_distance + 1e-5` entries make the tie order decide the birth order of tracks): cost [B,N,M] float64 ->
+ * x [B,N] = column of each row (or -1 when N > M leaves it unassigned), y [B,M] = row of each column (or -1). The whole-video
+ * StrongSORT / BPBReID kernels use the same routine in shared memory (csrc/lsap_scipy.cuh). */
+int tk_lsap_scipy_batched(const double* cost, int n_problems, int N, int M, int* x_out, int* y_out, int* status_dev, void* stream);
 
 #ifdef __cplusplus
 }

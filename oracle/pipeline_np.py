@@ -46,3 +46,57 @@ def detect_track_video(model_cpu, frames_rgb, tracker_dets=None, tracker_offsets
     rows = np.concatenate(out) if out else np.zeros((0, 8))
     frames = np.concatenate(fr) if fr else np.zeros((0,), dtype=np.int32)
     return rows, frames, det_rows
+
+
+def kpreid_crop_box(ltwh, width, height):
+    """ReID wrapper crop rule (/root/reference/tracklab/wrappers/reid/kpreid_api.py:118-121 -> utils/__init__.py:47-48 ->
+    utils/coordinates.py:216-267): float32 bbox_ltwh, sanitize_bbox_ltwh in place, ltrb, round half-to-even."""
+    b = np.asarray(ltwh, dtype=np.float32).copy()
+    b[0] = max(0, min(b[0], width - 2))
+    b[1] = max(0, min(b[1], height - 2))
+    b[2] = max(1, min(b[2], width - 1 - b[0]))
+    b[3] = max(1, min(b[3], height - 1 - b[1]))
+    l, t, r, bb = np.array([b[0], b[1], b[0] + b[2], b[1] + b[3]]).round().astype(int)
+    return int(l), int(t), int(r), int(bb)
+
+
+@torch.no_grad()
+def reid_features_frame(reid_model_cpu, frame_rgb, rows, batch=64):
+    """Per-frame in-tracker ReID of the StrongSORT plugin (/root/reference/plugins/track/strong_sort/strong_sort.py:135-145,
+    reid_multibackend.py:184-237): PIL crops -> float32 network -> float32 features [D,E]."""
+    from .preprocess_np import reid_crops
+    if len(rows) == 0:
+        return np.zeros((0, reid_model_cpu.feature_dim), dtype=np.float32)
+    x = torch.from_numpy(reid_crops(frame_rgb, rows[:, :4]))
+    return torch.cat([reid_model_cpu(x[i:i + batch]) for i in range(0, len(x), batch)]).numpy().astype(np.float32)
+
+
+def detect_reid_track_video(det_model_cpu, reid_model_cpu, frames_rgb, hyper, min_conf=0.4, detector_rows=None, score_thr=0.7):
+    """CPU restatement of the connected detect -> ReID -> associate loop for one video, frame by frame like the reference
+    (rtmlib_api.py:27-46 -> strong_sort_api.py:43-93 -> strong_sort.py:41-85). ``detector_rows`` (list of [D,7] per frame)
+    replaces the CPU detector forward — used to check the stages downstream of given rows.
+    Returns (tracker rows [R,8], frame [R], list of detector rows per frame, list of features per frame)."""
+    from .strongsort_np import StrongSortOracle
+    H, W = frames_rgb.shape[1:3]
+    trk = StrongSortOracle(**hyper, min_confidence=min_conf, image_size=(W, H))
+    out, fr, det_rows, feats = [], [], [], []
+    next_id = 0
+    for f in range(len(frames_rgb)):
+        if detector_rows is None:
+            rows = detect_frame(det_model_cpu, frames_rgb[f], first_id=next_id, score_thr=score_thr)
+        else:
+            rows = detector_rows[f]
+        next_id += len(rows)
+        det_rows.append(rows)
+        if len(rows) == 0:
+            feats.append(np.zeros((0, reid_model_cpu.feature_dim), np.float32))
+            continue
+        keep = rows[:, 4] > min_conf               # strong_sort_api.py:54-56
+        e = reid_features_frame(reid_model_cpu, frames_rgb[f], rows[keep])
+        feats.append(e)
+        r = trk.update(rows[keep], e)
+        out.append(r)
+        fr.append(np.full(len(r), f, dtype=np.int32))
+    rows = np.concatenate(out) if out else np.zeros((0, 8))
+    frames = np.concatenate(fr) if fr else np.zeros((0,), dtype=np.int32)
+    return rows, frames, det_rows, feats

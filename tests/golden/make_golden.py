@@ -104,7 +104,7 @@ def run_reference(tracker, video, hyper):
     return np.concatenate(rows), np.concatenate(frames)
 
 
-def run_strongsort_end_to_end(name="strongsort_e2e_s5000"):
+def run_strongsort_end_to_end(name="strongsort_e2e_s5000", gen=None):
     """The UNMODIFIED StrongSORT plugin incl. its in-tracker ReID (vendored ResNet-50, PIL crops) on synthetic frames.
     Weights: tracklab_b200.nets.resnet_reid.build_resnet50_reid(seed) exported into the reference's conv+BN format
     (identity BatchNorm statistics), so both sides hold the same function without committing 94 MB of weights."""
@@ -115,7 +115,7 @@ def run_strongsort_end_to_end(name="strongsort_e2e_s5000"):
 
     from tracklab_b200.nets.resnet_reid import build_resnet50_reid
     from tracklab_b200.synth import make_frames
-    gen = dict(seed=5000, n_frames=30, n_ids=12)
+    gen = gen or dict(seed=5000, n_frames=30, n_ids=12)
     hyper = dict(max_dist=0.1594374041012136, max_iou_dist=0.5431835667667874, max_age=40, max_unmatched_preds=0,
                  n_init=3, nn_budget=100, mc_lambda=0.995, ema_alpha=0.8962157769329083)
     video = make_video(**gen)
@@ -174,6 +174,11 @@ if __name__ == "__main__":
     if "strongsort_e2e" in args:
         run_strongsort_end_to_end()
         args.remove("strongsort_e2e")
+        if not args:
+            sys.exit(0)
+    if "strongsort_e2e_long" in args:   # 200 frames / 44 identities (~7.5k crops through the plugin's CPU ResNet-50: minutes)
+        run_strongsort_end_to_end("strongsort_e2e_s5001", dict(seed=5001, n_frames=200, n_ids=44))
+        args.remove("strongsort_e2e_long")
         if not args:
             sys.exit(0)
     main(args or list(CASES))

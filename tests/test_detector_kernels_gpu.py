@@ -123,13 +123,15 @@ def test_streamed_video_with_drain_schedule_equals_resident_video():
     trk = ByteTrackDevice(device=dev)
     pipe = DetectTrackPipeline(det, trk, B)
     assert pipe._schedule(F, True)[-3:] == [(100, 125), (125, 138), (138, 150)] and pipe._schedule(F, False)[-1] == (100, 150)
-    rows_d, fc_d, cnt_d, _ = pipe.run_video(frames, tracker_dets=gen_dets, tracker_offsets=gen_offs)
+    rd = pipe.run_video(frames, tracker_dets=gen_dets, tracker_offsets=gen_offs)
+    rows_d, fc_d, cnt_d = rd.out_rows, rd.out_fc, rd.out_count
     torch.cuda.synchronize()
     a = (rows_d[: int(cnt_d)].clone(), fc_d.clone(), int(det.cursor[0]), det.offsets[: F + 1].clone())
     assert a[2] > 0 and int(a[3][-1]) == a[2]
     host = frames.cpu().pin_memory()
     for _ in range(2):   # the second pass replays the tail graphs
-        rows_h, fc_h, cnt_h, _ = pipe.run_video(host, tracker_dets=gen_dets, tracker_offsets=gen_offs)
+        rh = pipe.run_video(host, tracker_dets=gen_dets, tracker_offsets=gen_offs)
+        rows_h, fc_h, cnt_h = rh.out_rows, rh.out_fc, rh.out_count
         torch.cuda.synchronize()
         assert int(cnt_h) == int(cnt_d) and torch.equal(rows_h[: int(cnt_h)], a[0]) and torch.equal(fc_h, a[1])
         n = int(det.cursor[0])

@@ -112,3 +112,34 @@ def test_kf_gate_matches_oracle(aspect_const):
     gate = strongsort_np.kf_gating if aspect_const else bpbreid_np.kf_gating
     ref = np.stack([gate(mean[t], cov[t], z) for t in range(T)])
     assert int(st.item()) == 0 and np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()
+
+
+def test_lsap_scipy_batched_reproduces_scipy_including_ties():
+    """tk_lsap_scipy_batched (csrc/lsap_scipy.cuh, the solver of the StrongSORT / BPBReID whole-video kernels) against
+    scipy.optimize.linear_sum_assignment itself on tie-heavy matrices, tall and wide: identical pairs, not just equal cost."""
+    from scipy.optimize import linear_sum_assignment
+    from tracklab_b200 import kernels
+    rng = np.random.default_rng(1)
+    for (N, M) in [(1, 1), (5, 9), (9, 5), (40, 44), (44, 40), (37, 300), (300, 37), (128, 128)]:
+        B = 24
+        cs = []
+        for b in range(B):
+            kind = b % 4
+            if kind == 0:
+                c = rng.integers(0, 3, size=(N, M)).astype(float)
+            elif kind == 1:
+                c = rng.uniform(0, 1, size=(N, M)); c[c > 0.3] = 0.3 + 1e-5
+            elif kind == 2:
+                c = rng.uniform(0, 1, size=(N, M)); c[rng.uniform(size=(N, M)) < 0.8] = 0.8 + 1e-5
+            else:
+                c = np.full((N, M), 0.5)
+            cs.append(c)
+        cost = np.stack(cs)
+        x, y, st = kernels.lsap_scipy_batched(torch.from_numpy(cost).cuda())
+        assert int(st.item()) == 0
+        x, y = x.cpu().numpy(), y.cpu().numpy()
+        for b in range(B):
+            rows, cols = linear_sum_assignment(cost[b])
+            want_x = -np.ones(N, dtype=np.int64); want_x[rows] = cols
+            want_y = -np.ones(M, dtype=np.int64); want_y[cols] = rows
+            assert np.array_equal(x[b], want_x) and np.array_equal(y[b], want_y), (N, M, b)

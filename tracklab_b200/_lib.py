@@ -61,8 +61,10 @@ def _declare(lib):
         "tk_last_cuda_error": ([], ci),
         "tk_letterbox_u8": ([vp, ci, ci, ci, ctypes.c_longlong, vp, ci, ci, ci, ci, ci, P(cd), vp], ci),
         "tk_crop_resize_norm": ([vp, ci, ci, ctypes.c_longlong, vp, vp, ci, vp, ci, ci, ci, ci, P(ctypes.c_float), P(ctypes.c_float), vp], ci),
+        "tk_crop_resize_norm_ex": ([vp, ci, ci, ctypes.c_longlong, vp, vp, ci, vp, ci, ci, ci, ci, P(ctypes.c_float), P(ctypes.c_float), ci, vp], ci),
         "tk_yolox_nms": ([vp, ci, ci, ci, ci, ci, ci, ctypes.c_float, ctypes.c_float, ctypes.c_float, ci, vp, vp, vp, vp, vp, vp], ci),
         "tk_pack_detections": ([vp, vp, vp, vp, ci, ci, ci, ci, ci, cd, cd, vp, vp, vp, ci, ci, vp, vp], ci),
+        "tk_pack_detections_ex": ([vp, vp, vp, vp, ci, ci, ci, ci, ci, cd, cd, vp, vp, vp, ci, ci, vp, ci, vp, vp], ci),
         "tk_bias_act_nhwc": ([vp, vp, vp, vp, ctypes.c_longlong, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_spp_nhwc": ([vp, vp, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_upsample2x_nhwc": ([vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, vp], ci),
@@ -74,6 +76,7 @@ def _declare(lib):
         "tk_iou_p1_f32": ([vp, vp, vp, ci, ci, ci, vp], ci),
         "tk_cosine_dist": ([vp, vp, vp, vp, ci, ci, ci, ci, vp], ci),
         "tk_lap_batched": ([vp, ci, ci, ci, cd, ci, vp, vp, vp, vp], ci),
+        "tk_lsap_scipy_batched": ([vp, ci, ci, ci, vp, vp, vp, vp], ci),
         "tk_part_dist": ([vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp], ci),
         "tk_kf_gate": ([vp, vp, vp, vp, ci, ci, ci, vp, vp], ci),
         "tk_bytetrack_create": ([P(BytetrackParams), ci, ci, ci, P(vp)], ci),

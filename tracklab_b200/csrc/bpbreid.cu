@@ -34,6 +34,7 @@
 #include <cooperative_groups.h>
 #include "kf_xyah.cuh"
 #include "lap.cuh"
+#include "lsap_scipy.cuh"
 #include "trackkern.h"
 
 namespace {
@@ -52,7 +53,7 @@ constexpr int BP_THREADS = 256;
 enum : unsigned char { BP_FREE = 0, BP_TENTATIVE = 1, BP_CONFIRMED = 2, BP_DELETED = 3 };
 constexpr double W_POS = 1.0 / 20, W_VEL = 1.0 / 160, CHI2_4 = 9.4877;
 constexpr int BP_COLS = 14;
-constexpr int BP_NARR = 36;
+constexpr int BP_NARR = 37;
 
 struct BpParams {
     double max_dist, max_iou_dist, mc_lambda, min_conf;
@@ -68,6 +69,7 @@ struct BpDev {
     int *ema_slot, *ema_row, *born_slot, *born_row;   // feature updates of the frame, published for the worker CTAs
     unsigned char *state, *has_pred, *m_code;
     float *feat, *featn, *dfeatn, *vis, *dvis, *pa;   // featn / dfeatn: L2-normalised parts of the tracks / of the frame's detections
+    unsigned char* lsap_ws;   // column-side scratch of the scipy-exact assignment (up to max(cap, capd) columns), see bp_lsap_ws
 };
 
 __host__ __device__ inline size_t bp_al(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -86,6 +88,7 @@ __host__ __device__ inline void bp_layout(int cap, int capd, int K, int E, F&& f
     f(i++, (size_t)cap * K * E * 4); f(i++, (size_t)cap * K * E * 4); f(i++, (size_t)capd * K * E * 4); f(i++, (size_t)cap * K * 4); f(i++, (size_t)capd * K * 4);   // feat featn dfeatn vis dvis
     f(i++, np * 4);                                                                                    // pa
     for (int k = 0; k < 4; ++k) f(i++, (size_t)capd * 4);                                              // ema_slot ema_row born_slot born_row
+    f(i++, (size_t)(cap > capd ? cap : capd) * 40 + 64);                                               // lsap_ws
 }
 
 __host__ __device__ inline size_t bp_state_bytes(int cap, int capd, int K, int E) {
@@ -101,7 +104,8 @@ __host__ __device__ inline BpDev bp_carve(char* base, int cap, int capd, int K, 
         (void**)&d.pred, (void**)&d.pg, (void**)&d.pf, (void**)&d.hits, (void**)&d.birth, (void**)&d.last, (void**)&d.track_id,
         (void**)&d.list, (void**)&d.list_tmp, (void**)&d.free_list, (void**)&d.conf_list, (void**)&d.det_rows, (void**)&d.ppack,
         (void**)&d.cpack, (void**)&d.state, (void**)&d.has_pred, (void**)&d.m_code, (void**)&d.feat, (void**)&d.featn,
-        (void**)&d.dfeatn, (void**)&d.vis, (void**)&d.dvis, (void**)&d.pa, (void**)&d.ema_slot, (void**)&d.ema_row, (void**)&d.born_slot, (void**)&d.born_row};
+        (void**)&d.dfeatn, (void**)&d.vis, (void**)&d.dvis, (void**)&d.pa, (void**)&d.ema_slot, (void**)&d.ema_row, (void**)&d.born_slot, (void**)&d.born_row,
+        (void**)&d.lsap_ws};
     char* p = base;
     bp_layout(cap, capd, K, E, [&](int i, size_t b) { *slots[i] = (void*)p; p += bp_al(b); });
     return d;
@@ -278,7 +282,19 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
     unsigned char* state_m = (unsigned char*)take(cap);           // mirror of S.state
     unsigned char* t_flag = (unsigned char*)take(cap);
     unsigned char* t_live = (unsigned char*)take(cap);
+    int* cmap = (int*)take(sizeof(int) * cap);                    // confirmed position -> row of the dense stage-A matrix, -1: no feasible entry
+    unsigned char* lap_sr = (unsigned char*)take(side);
+    unsigned char* touch_d = (unsigned char*)take(capd);          // 1 when the solver paired the detection column (accepted or not)
     BpShared* sh = (BpShared*)take(sizeof(BpShared));
+    // column side of the scipy-exact solver (all confirmed tracks can be columns): global scratch, L1/L2 resident
+    const int big = cap > capd ? cap : capd;
+    double* lap_v = (double*)S.lsap_ws;
+    double* lap_spc = lap_v + big;
+    int* lap_path = (int*)(lap_spc + big);
+    int* lap_r4c = lap_path + big;
+    int* lap_rem = lap_r4c + big;
+    int* rej_t = lap_rem + big;                                   // detection of a row's rejected pair (cost above the threshold) or -1
+    unsigned char* lap_sc = (unsigned char*)(rej_t + big);
 
     int* status = &S.hdr[4];
     const int F1 = n_frames + 1;
@@ -517,27 +533,45 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
         const int nlive = sh->nlive <= capl ? sh->nlive : 0;
         PH(7);
         {
-            const bool a_rows = nlive <= nd;
-            const int ld = lap_pitch(a_rows ? nd : nlive);
-            for (int e = tid; e < (a_rows ? nlive : nd) * ld; e += BP_THREADS) cost[e] = 0.0;
+            // Dense matrix of the live rows only: dense[p * ldd + d], everything that is not feasible holds the clamped value
+            // max_dist + 1e-5 (linear_assignment.py:52-53); confirmed tracks without any feasible entry are whole rows of that
+            // value and exist only through cmap (-1). scipy solves the FULL confirmed x detections problem, transposed when it
+            // is tall (more tracks than detections), and its tie-breaking among the equal clamped entries decides which
+            // rejected pairs it returns — lsap_scipy.cuh reproduces it.
+            const int ldd = capd + 1;
+            for (int e = tid; e < nlive * ldd; e += BP_THREADS) cost[e] = L_app;
+            for (int r = tid; r < nconf; r += BP_THREADS) { const int sl = conf_m[r]; cmap[r] = (nlive > 0 && t_live[sl]) ? scr[sl] : -1; rej_t[r] = -1; }
             for (int i = tid; i < nlive; i += BP_THREADS) match_a[i] = -1;
-            for (int i = tid; i < nd; i += BP_THREADS) match_b[i] = -1;
+            for (int i = tid; i < nd; i += BP_THREADS) { match_b[i] = -1; touch_d[i] = 0; }
+            if (tid == 0) sh->lap_ok = 1;
             __syncthreads();
             if (nlive > 0)
                 for (int i = tid; i < nap; i += BP_THREADS) {
                     const double fused = S.pf[i];
                     if (fused > prm.max_dist) continue;
                     const int pk = S.ppack[i], r = scr[pk >> 8], d = pk & 255;
-                    if (a_rows) cost[(size_t)r * ld + d] = fused - L_app; else cost[(size_t)d * ld + r] = fused - L_app;
+                    cost[(size_t)r * ldd + d] = fused;
                 }
             __syncthreads();
             PH(8);
-            if (nlive > 0) {
-                const int nr = a_rows ? nlive : nd, nc = a_rows ? nd : nlive;
-                if (!lap_solve_cta(cost, ld, nr, nc, true, lap_u, col4row, row4col, path, &sh->lap_ok)) { if (tid == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); }
-                else for (int r = tid; r < nr; r += BP_THREADS) {
-                    const int c = col4row[r];
-                    if (c >= 0 && cost[(size_t)r * ld + c] < 0.0) { if (a_rows) { match_a[r] = c; match_b[c] = r; } else { match_a[c] = r; match_b[r] = c; } }
+            if (nconf > 0 && nd > 0) {
+                const bool t_rows = nconf <= nd;                   // rows = tracks unless the matrix is tall
+                const int nr = t_rows ? nconf : nd, nc = t_rows ? nd : nconf;
+                auto cval = [&](int r, int d) { const int p = cmap[r]; return p >= 0 ? cost[(size_t)p * ldd + d] : L_app; };
+                if (warp_id() == 0) {
+                    bool ok;
+                    if (t_rows) ok = lsap_scipy_warp(nr, nc, [&](int i, int j) { return cval(i, j); }, lap_u, lap_v, lap_spc, lap_path, col4row,
+                                                     lap_r4c, lap_rem, lap_sr, lap_sc);
+                    else ok = lsap_scipy_warp(nr, nc, [&](int i, int j) { return cval(j, i); }, lap_u, lap_v, lap_spc, lap_path, col4row,
+                                              lap_r4c, lap_rem, lap_sr, lap_sc);
+                    if (!ok && lane_id() == 0) { atomicOr(status, TK_DEV_LAP_INFEASIBLE); sh->lap_ok = 0; }
+                }
+                __syncthreads();
+                if (sh->lap_ok) for (int i = tid; i < nr; i += BP_THREADS) {
+                    const int j = col4row[i];
+                    const int r = t_rows ? i : j, d = t_rows ? j : i;
+                    touch_d[d] = 1;
+                    if (cval(r, d) > prm.max_dist) rej_t[r] = d; else { match_a[cmap[r]] = d; match_b[d] = cmap[r]; }
                 }
             }
             __syncthreads();
@@ -559,7 +593,10 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
             int nc = warp_compact(nt, 0, [&](int k) { return state_m[list_m[k]] != BP_CONFIRMED; }, [&](int k, int p) { if (p < capl) cand[p] = list_m[k]; });
             nc = warp_compact(nconf, nc, [&](int r) { const int s = conf_m[r]; return !t_flag[s] && tick - last_m[s] == 1; },
                               [&](int r, int p) { if (p < capl) cand[p] = conf_m[r]; });
-            const int nu = warp_compact(nd, 0, [&](int d) { return match_b[d] < 0; }, [&](int d, int p) { un_d[p] = d; });
+            // unmatched_detections_a in the reference's order (linear_assignment.py:57-68): untouched columns in detection order,
+            // then the detections of the rejected pairs in confirmed-track order
+            int nu = warp_compact(nd, 0, [&](int d) { return !touch_d[d]; }, [&](int d, int p) { un_d[p] = d; });
+            nu = warp_compact(nconf, nu, [&](int r) { return rej_t[r] >= 0; }, [&](int r, int p) { un_d[p] = rej_t[r]; });
             if (lane_id() == 0) { if (nc > capl) { atomicOr(status, TK_DEV_OVERFLOW_ASSIGN); nc = 0; } sh->ncand = nc; sh->nud = nu; }
         }
         __syncthreads();
@@ -583,19 +620,27 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
                 const double uni = __dsub_rn(__dadd_rn(__dmul_rn(w, m[3]), __dmul_rn(cb[2], cb[3])), inter);
                 const double v = 1.0 - inter / uni;
                 vmat[(size_t)r * capd + c] = v;
-                const double red = v > prm.max_iou_dist ? 0.0 : v - L_iou;
-                if (a_rows) cost[(size_t)r * ld + c] = red; else cost[(size_t)c * ld + r] = red;
+                const double cl = v > prm.max_iou_dist ? L_iou : v;
+                if (a_rows) cost[(size_t)r * ld + c] = cl; else cost[(size_t)c * ld + r] = cl;
             }
-            for (int i = tid; i < ncand; i += BP_THREADS) match_a[i] = -1;
-            for (int i = tid; i < nud; i += BP_THREADS) match_b[i] = -1;
+            for (int i = tid; i < ncand; i += BP_THREADS) { match_a[i] = -1; rej_t[i] = -1; }
+            for (int i = tid; i < nud; i += BP_THREADS) { match_b[i] = -1; touch_d[i] = 0; }
+            if (tid == 0) sh->lap_ok = 1;
             __syncthreads();
             PH(11);
             if (ncand > 0 && nud > 0) {
                 const int nr = a_rows ? ncand : nud, nc = a_rows ? nud : ncand;
-                if (!lap_solve_cta(cost, ld, nr, nc, true, lap_u, col4row, row4col, path, &sh->lap_ok)) { if (tid == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); }
-                else for (int r = tid; r < nr; r += BP_THREADS) {
-                    const int c = col4row[r];
-                    if (c >= 0 && cost[(size_t)r * ld + c] < 0.0) { if (a_rows) { match_a[r] = c; match_b[c] = r; } else { match_a[c] = r; match_b[r] = c; } }
+                if (warp_id() == 0) {
+                    const bool ok = lsap_scipy_warp(nr, nc, [&](int i, int j) { return cost[(size_t)i * ld + j]; }, lap_u, lap_v, lap_spc, lap_path,
+                                                    col4row, lap_r4c, lap_rem, lap_sr, lap_sc);
+                    if (!ok && lane_id() == 0) { atomicOr(status, TK_DEV_LAP_INFEASIBLE); sh->lap_ok = 0; }
+                }
+                __syncthreads();
+                if (sh->lap_ok) for (int i = tid; i < nr; i += BP_THREADS) {
+                    const int j = col4row[i];
+                    const int r = a_rows ? i : j, c = a_rows ? j : i;
+                    touch_d[c] = 1;
+                    if (cost[(size_t)i * ld + j] > prm.max_iou_dist) rej_t[r] = c; else { match_a[r] = c; match_b[c] = r; }
                 }
             }
             __syncthreads();
@@ -606,7 +651,8 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
                                                  pair_t[p] = s; pair_d[p] = un_d[match_a[r]]; t_flag[s] = 1;
                                                  S.m_code[s] = 2; S.m_dist[s] = vmat[(size_t)r * capd + match_a[r]];   // ("S", dist)
                                              });
-                const int nu = warp_compact(nud, 0, [&](int c) { return match_b[c] < 0; }, [&](int c, int p) { tmp_d[p] = un_d[c]; });
+                int nu = warp_compact(nud, 0, [&](int c) { return !touch_d[c]; }, [&](int c, int p) { tmp_d[p] = un_d[c]; });
+                nu = warp_compact(ncand, nu, [&](int r) { return rej_t[r] >= 0; }, [&](int r, int p) { tmp_d[p] = un_d[rej_t[r]]; });
                 if (lane_id() == 0) { sh->npairs = np_; sh->nud = nu; }
             }
             __syncthreads();
@@ -657,8 +703,8 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
         }
         if (warp_id() == 0) {
             const int lane = lane_id();
-            // births in the order of unmatched_detections_b; rejected pairs are never returned by the device solver, see
-            // strongsort.cu and DESIGN.md §3 (solver-tie caveat).
+            // births in the order of unmatched_detections_b (untouched columns, then the rejected pairs scipy's tie-breaking
+            // returns, in row order — reproduced by lsap_scipy.cuh)
             const int nfree = S.hdr[5];
             const int nb = sh->nud < nfree ? sh->nud : nfree;
             if (sh->nud > nfree && lane == 0) atomicOr(status, TK_DEV_OVERFLOW_TRACKS);
@@ -772,6 +818,7 @@ size_t bp_smem(int cap, int capd, int capl) {
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
     size_t s = al(8 * (size_t)(capl + 1) * (capd + 1)) + al(8 * side) + 2 * al(8 * 4 * capd) + al(16 * cap) + al(8 * capd);
     s += 4 * al(4 * cap) + 5 * al(4 * side) + 2 * al(4 * capl) + 4 * al(4 * capd) + 3 * al(cap) + al(sizeof(BpShared));
+    s += al(4 * cap) + al(side) + al(capd);   // cmap, lap_sr, touch_d
     return s;
 }
 
@@ -820,6 +867,7 @@ int tk_bpbreid_run(void* handle, const double* dets, const float* features, cons
     void* args[] = {&h->prm, &h->state, &h->state_stride, &cap, &capd, &capl, &ncta, &dets, &features, &visibility, &offsets, &n_frames,
                     &out_rows, &out_start, &out_frame_count, &out_count, &out_capacity_rows};
     // cooperative launch: every CTA of a video group must be co-resident for the group barrier
+    TK_CUDA_TRY(cudaFuncSetAttribute(bpbreid_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));   // per function, not per handle
     TK_CUDA_TRY(cudaLaunchCooperativeKernel((void*)bpbreid_video_kernel, dim3(h->n_seq * ncta), dim3(BP_THREADS), args, h->smem_bytes,
                                             (cudaStream_t)stream));
     return TK_OK;

@@ -758,6 +758,8 @@ int tk_bytetrack_run(void* handle, const double* dets, const int* offsets, int n
     if (!handle || !offsets || !out_rows || !out_start || !out_frame_count || !out_count || n_frames < 0) return TK_ERR_ARG;
     BtHandle* h = (BtHandle*)handle;
     if (n_frames == 0) return TK_OK;
+    // the attribute is per kernel function, not per handle: another handle with smaller capacities may have lowered it
+    TK_CUDA_TRY(cudaFuncSetAttribute(bytetrack_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
     bytetrack_video_kernel<<<h->n_seq, BT_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(
         h->prm, h->state, h->state_stride, h->cap, h->capd, dets, offsets, n_frames, out_rows, out_start,
         out_frame_count, out_count, h->cost, h->cost_stride, h->cost_in_smem);

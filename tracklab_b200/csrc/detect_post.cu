@@ -171,7 +171,8 @@ __global__ void pack_detections_kernel(const float* __restrict__ boxes, const fl
                                        const int* __restrict__ cls, const int* __restrict__ counts, int B, int K,
                                        int keep_class, float W, float H, double fixed_conf, double category_id,
                                        int* __restrict__ cursor, double* __restrict__ dets, int* __restrict__ offsets_all,
-                                       int dets_cap, int frames_cap, int* __restrict__ status) {
+                                       int dets_cap, int frames_cap, int* __restrict__ status, int row_format,
+                                       int* __restrict__ frame_of_row) {
     __shared__ int s_off[1025];
     __shared__ int s_cnt[1024];
     const int tid = threadIdx.x;
@@ -209,7 +210,12 @@ __global__ void pack_detections_kernel(const float* __restrict__ boxes, const fl
             const float w = __fsub_rn(rr, l), h = __fsub_rn(bb, t);      // ltrb_to_ltwh (coordinates.py:318-328)
             double* d = dets + (size_t)r * 7;
             d[0] = (double)l; d[1] = (double)t;
-            d[2] = (double)__fadd_rn(l, w); d[3] = (double)__fadd_rn(t, h);  // ltwh_to_ltrb (coordinates.py:257-267)
+            if (row_format == TK_ROWS_LTWH) {      // the detector's bbox_ltwh column as is (ReID / BPBReID wrappers read it)
+                d[2] = (double)w; d[3] = (double)h;
+            } else {
+                d[2] = (double)__fadd_rn(l, w); d[3] = (double)__fadd_rn(t, h);  // ltwh_to_ltrb (coordinates.py:257-267)
+            }
+            if (frame_of_row) frame_of_row[r] = b;   // image index inside this batch (what tk_crop_resize_norm gathers from)
             d[4] = fixed_conf >= 0.0 ? fixed_conf : (double)scores[(size_t)b * K + k];
             d[5] = category_id;
             d[6] = (double)r;
@@ -248,17 +254,28 @@ int tk_yolox_nms(const void* pred, int pred_dtype, int n_images, int n_anchors, 
     return TK_OK;
 }
 
+int tk_pack_detections_ex(const float* boxes, const float* scores, const int* cls, const int* counts, int n_images,
+                          int max_per_image, int keep_class, int img_w, int img_h, double fixed_conf, double category_id,
+                          int* cursor_dev, double* dets_out, int* offsets_out, int dets_cap, int frames_cap,
+                          int* status_dev, int row_format, int* frame_of_row_out, void* stream) {
+    if (!boxes || !scores || !cls || !counts || !dets_out || !offsets_out || !cursor_dev || !status_dev) return TK_ERR_ARG;
+    if (n_images <= 0 || n_images > 1024) return TK_ERR_ARG;
+    if (row_format != TK_ROWS_LTRB && row_format != TK_ROWS_LTWH) return TK_ERR_ARG;
+    pack_detections_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(boxes, scores, cls, counts, n_images, max_per_image, keep_class,
+                                                              (float)img_w, (float)img_h, fixed_conf, category_id,
+                                                              cursor_dev, dets_out, offsets_out, dets_cap, frames_cap, status_dev,
+                                                              row_format, frame_of_row_out);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
 int tk_pack_detections(const float* boxes, const float* scores, const int* cls, const int* counts, int n_images,
                        int max_per_image, int keep_class, int img_w, int img_h, double fixed_conf, double category_id,
                        int* cursor_dev, double* dets_out, int* offsets_out, int dets_cap, int frames_cap,
                        int* status_dev, void* stream) {
-    if (!boxes || !scores || !cls || !counts || !dets_out || !offsets_out || !cursor_dev || !status_dev) return TK_ERR_ARG;
-    if (n_images <= 0 || n_images > 1024) return TK_ERR_ARG;
-    pack_detections_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(boxes, scores, cls, counts, n_images, max_per_image, keep_class,
-                                                              (float)img_w, (float)img_h, fixed_conf, category_id,
-                                                              cursor_dev, dets_out, offsets_out, dets_cap, frames_cap, status_dev);
-    TK_CUDA_TRY(cudaGetLastError());
-    return TK_OK;
+    return tk_pack_detections_ex(boxes, scores, cls, counts, n_images, max_per_image, keep_class, img_w, img_h, fixed_conf,
+                                 category_id, cursor_dev, dets_out, offsets_out, dets_cap, frames_cap, status_dev, TK_ROWS_LTRB,
+                                 nullptr, stream);
 }
 
 }  // extern "C"

@@ -11,6 +11,7 @@
 // All are HBM/latency-bound: rows are staged once per CTA, outputs are written coalesced; batches fill the 148 SMs.
 #include "kf_xyah.cuh"
 #include "lap.cuh"
+#include "lsap_scipy.cuh"
 #include "tk_common.cuh"
 #include "trackkern.h"
 
@@ -274,9 +275,54 @@ kf_gate_kernel(const double* __restrict__ mean, const double* __restrict__ cov, 
     for (int d = threadIdx.x; d < D; d += blockDim.x) out[(size_t)t * D + d] = tk::kf8_maha(c, c + 4, c + 20, z + (size_t)d * 4);
 }
 
+// scipy.optimize.linear_sum_assignment, one warp per problem, cost read from global memory (stateless form of lsap_scipy.cuh)
+__global__ void __launch_bounds__(32)
+lsap_scipy_batched_kernel(const double* __restrict__ cost, int N, int M, int* __restrict__ x_out, int* __restrict__ y_out,
+                          int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int p = blockIdx.x;
+    const double* c = cost + (size_t)p * N * M;
+    const bool transpose = M < N;                       // tall matrix: scipy solves the transposed problem
+    const int nr = transpose ? M : N, nc = transpose ? N : M;
+    tk::LsapScratch S;
+    S.carve(smem_raw, nr, nc);
+    bool ok;
+    if (transpose) ok = tk::lsap_scipy_warp(nr, nc, [&](int i, int j) { return c[(size_t)j * M + i]; }, S.u, S.v, S.spc, S.path,
+                                            S.col4row, S.row4col, S.remaining, S.SR, S.SC);
+    else ok = tk::lsap_scipy_warp(nr, nc, [&](int i, int j) { return c[(size_t)i * M + j]; }, S.u, S.v, S.spc, S.path, S.col4row,
+                                  S.row4col, S.remaining, S.SR, S.SC);
+    __syncwarp();
+    int* x = x_out + (size_t)p * N;
+    int* y = y_out + (size_t)p * M;
+    if (!ok) {
+        if (threadIdx.x == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE);
+        for (int i = threadIdx.x; i < N; i += 32) x[i] = -1;
+        for (int j = threadIdx.x; j < M; j += 32) y[j] = -1;
+        return;
+    }
+    if (transpose) {   // solver rows are the columns of the caller
+        for (int j = threadIdx.x; j < M; j += 32) y[j] = S.col4row[j];
+        for (int i = threadIdx.x; i < N; i += 32) x[i] = S.row4col[i];
+    } else {
+        for (int i = threadIdx.x; i < N; i += 32) x[i] = S.col4row[i];
+        for (int j = threadIdx.x; j < M; j += 32) y[j] = S.row4col[j];
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int tk_lsap_scipy_batched(const double* cost, int n_problems, int N, int M, int* x_out, int* y_out, int* status_dev, void* stream) {
+    if (!cost || !x_out || !y_out || !status_dev || n_problems <= 0 || N <= 0 || M <= 0) return TK_ERR_ARG;
+    const int nr = N <= M ? N : M, nc = N <= M ? M : N;
+    const size_t smem = tk::lsap_scipy_scratch_bytes(nr, nc);
+    if (smem > 220 * 1024) return TK_ERR_CAPACITY;
+    TK_CUDA_TRY(cudaFuncSetAttribute(lsap_scipy_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lsap_scipy_batched_kernel<<<n_problems, 32, smem, (cudaStream_t)stream>>>(cost, N, M, x_out, y_out, status_dev);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
 
 int tk_iou_matrix(const double* a, const double* b, double* out, int n_problems, int N, int M, int variant, void* stream) {
     if (!a || !b || !out || n_problems <= 0 || N < 0 || M < 0 || variant < 0 || variant > TK_ASSO_CT_DIST) return TK_ERR_ARG;

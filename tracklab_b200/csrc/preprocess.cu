@@ -368,15 +368,27 @@ template <typename OutT>
 __global__ void __launch_bounds__(128)
 crop_resize_norm_kernel(const unsigned char* __restrict__ frames, size_t frame_stride, int H, int W,
                         const double* __restrict__ dets, const int* __restrict__ det_frame, OutT* __restrict__ out,
-                        int out_h, int out_w, float m0, float m1, float m2, float s0, float s1, float s2, int nhwc) {
+                        int out_h, int out_w, float m0, float m1, float m2, float s0, float s1, float s2, int nhwc,
+                        int crop_rule) {
     __shared__ int kv[CR_ROWS][CR_KMAX];
     __shared__ int s_ymin[CR_ROWS], s_ny[CR_ROWS];
     const int n = blockIdx.y, y0 = blockIdx.x * CR_ROWS;
     const double* d = dets + (size_t)n * 7;
-    // StrongSORT crop rule (strong_sort.py:102-108): centre box -> int() truncation -> clip
-    const double cx = (d[0] + d[2]) / 2, cy = (d[1] + d[3]) / 2, bw = d[2] - d[0], bh = d[3] - d[1];
-    const int x1 = max((int)(cx - bw / 2), 0), x2 = min((int)(cx + bw / 2), W - 1);
-    const int y1 = max((int)(cy - bh / 2), 0), y2 = min((int)(cy + bh / 2), H - 1);
+    int x1, x2, y1, y2;
+    if (crop_rule == TK_CROP_RULE_LTWH_ROUNDED) {
+        // ReID wrapper rule (kpreid_api.py:118-121 -> utils/__init__.py:47-48 -> coordinates.py:216-267): the detector's float32
+        // bbox_ltwh is clipped in place (sanitize_bbox_ltwh), turned into ltrb in float32 and rounded half-to-even; crop = [t:b, l:r]
+        const float l = fmaxf(0.0f, fminf((float)d[0], (float)(W - 2))), t = fmaxf(0.0f, fminf((float)d[1], (float)(H - 2)));
+        const float w = fmaxf(1.0f, fminf((float)d[2], __fsub_rn((float)(W - 1), l)));
+        const float h = fmaxf(1.0f, fminf((float)d[3], __fsub_rn((float)(H - 1), t)));
+        x1 = __float2int_rn(l); y1 = __float2int_rn(t);
+        x2 = __float2int_rn(__fadd_rn(l, w)); y2 = __float2int_rn(__fadd_rn(t, h));
+    } else {
+        // StrongSORT crop rule (strong_sort.py:102-108): centre box -> int() truncation -> clip
+        const double cx = (d[0] + d[2]) / 2, cy = (d[1] + d[3]) / 2, bw = d[2] - d[0], bh = d[3] - d[1];
+        x1 = max((int)(cx - bw / 2), 0); x2 = min((int)(cx + bw / 2), W - 1);
+        y1 = max((int)(cy - bh / 2), 0); y2 = min((int)(cy + bh / 2), H - 1);
+    }
     const int cw = x2 - x1, ch = y2 - y1;
     const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
     const unsigned char* img = frames + (size_t)det_frame[n] * frame_stride;
@@ -485,6 +497,14 @@ extern "C" int tk_resize_frames_u8(const unsigned char* frames, int n_frames, in
 extern "C" int tk_crop_resize_norm(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,
                                    const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,
                                    const float* mean3, const float* std3, void* stream) {
+    return tk_crop_resize_norm_ex(frames, H, W, frame_stride_bytes, dets, det_frame, n_dets, out, out_dtype, out_nhwc, out_h, out_w,
+                                  mean3, std3, TK_CROP_RULE_STRONGSORT, stream);
+}
+
+extern "C" int tk_crop_resize_norm_ex(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,
+                                      const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,
+                                      const float* mean3, const float* std3, int crop_rule, void* stream) {
+    if (crop_rule != TK_CROP_RULE_STRONGSORT && crop_rule != TK_CROP_RULE_LTWH_ROUNDED) return TK_ERR_ARG;
     if (!frames || !dets || !det_frame || !out || !mean3 || !std3 || n_dets < 0 || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0) return TK_ERR_ARG;
     if (out_dtype != TK_DTYPE_F32 && out_dtype != TK_DTYPE_BF16) return TK_ERR_ARG;
     if (out_nhwc == TK_CROP_LAYOUT_S2D16 && ((out_h | out_w) & 1)) return TK_ERR_ARG;
@@ -494,11 +514,11 @@ extern "C" int tk_crop_resize_norm(const unsigned char* frames, int H, int W, lo
     cudaStream_t st = (cudaStream_t)stream;
     if (out_dtype == TK_DTYPE_F32)
         crop_resize_norm_kernel<float><<<grid, 128, 0, st>>>(frames, (size_t)frame_stride_bytes, H, W, dets, det_frame, (float*)out, out_h,
-                                                            out_w, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], out_nhwc);
+                                                            out_w, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], out_nhwc, crop_rule);
     else
         crop_resize_norm_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(frames, (size_t)frame_stride_bytes, H, W, dets, det_frame,
                                                                     (__nv_bfloat16*)out, out_h, out_w, mean3[0], mean3[1], mean3[2],
-                                                                    std3[0], std3[1], std3[2], out_nhwc);
+                                                                    std3[0], std3[1], std3[2], out_nhwc, crop_rule);
     TK_CUDA_TRY(cudaGetLastError());
     return TK_OK;
 }

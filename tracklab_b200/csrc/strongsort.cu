@@ -22,6 +22,7 @@
 #include <cooperative_groups.h>
 #include "kf_xyah.cuh"
 #include "lap.cuh"
+#include "lsap_scipy.cuh"
 #include "trackkern.h"
 
 namespace {
@@ -216,6 +217,14 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
     int* upd_row = (int*)take(sizeof(int) * cap);                   // absolute detection row that updated / created the slot this frame
     unsigned char* t_flag = (unsigned char*)take(cap);
     unsigned char* d_flag = (unsigned char*)take(capd);
+    // scratch of the scipy-exact assignment (lsap_scipy.cuh) + bookkeeping of the pairs it returns
+    double* lap_v = (double*)take(sizeof(double) * side);
+    double* lap_spc = (double*)take(sizeof(double) * side);
+    int* lap_rem = (int*)take(sizeof(int) * side);
+    int* rej_t = (int*)take(sizeof(int) * side);                    // detection of a row's rejected pair (cost above the threshold) or -1
+    unsigned char* lap_sr = (unsigned char*)take(side);
+    unsigned char* lap_sc = (unsigned char*)take(side);
+    unsigned char* touch_d = (unsigned char*)take(side);            // 1 when the solver paired the detection column (accepted or not)
     SsShared* sh = (SsShared*)take(sizeof(SsShared));
 
     int* status = &S.hdr[4];
@@ -370,18 +379,28 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
                 double a = (double)__int_as_float(akey);
                 if (g > CHI2_4) a = INFTY_COST;
                 const double fused = __dadd_rn(__dmul_rn(prm.mc_lambda, a), __dmul_rn(1.0 - prm.mc_lambda, g));
-                const double red = fused > prm.max_dist ? 0.0 : fused - L_app;   // cost[cost > max] = max + 1e-5, pairs above max dropped
-                if (a_rows) cost[(size_t)r * ld + d] = red; else cost[(size_t)d * ld + r] = red;
+                const double cl = fused > prm.max_dist ? L_app : fused;   // cost_matrix[cost_matrix > max_distance] = max_distance + 1e-5
+                if (a_rows) cost[(size_t)r * ld + d] = cl; else cost[(size_t)d * ld + r] = cl;
             }
-            for (int i = tid; i < nconf; i += SS_THREADS) match_a[i] = -1;
-            for (int i = tid; i < nd; i += SS_THREADS) match_b[i] = -1;
+            for (int i = tid; i < nconf; i += SS_THREADS) { match_a[i] = -1; rej_t[i] = -1; }
+            for (int i = tid; i < nd; i += SS_THREADS) { match_b[i] = -1; touch_d[i] = 0; }
+            if (tid == 0) sh->lap_ok = 1;
             __syncthreads();
             if (nconf > 0 && nd > 0) {
+                // scipy.optimize.linear_sum_assignment on the full clamped matrix (linear_assignment.py:53-55), same tie-breaking:
+                // the solver pairs every row of the smaller side; pairs above the threshold are "rejected" (:62-68)
                 const int nr = a_rows ? nconf : nd, nc = a_rows ? nd : nconf;
-                if (!lap_solve_cta(cost, ld, nr, nc, true, lap_u, col4row, row4col, path, &sh->lap_ok)) { if (tid == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); }
-                else for (int r = tid; r < nr; r += SS_THREADS) {
-                    const int c = col4row[r];
-                    if (c >= 0 && cost[(size_t)r * ld + c] < 0.0) { if (a_rows) { match_a[r] = c; match_b[c] = r; } else { match_a[c] = r; match_b[r] = c; } }
+                if (warp_id() == 0) {
+                    const bool ok = lsap_scipy_warp(nr, nc, [&](int i, int j) { return cost[(size_t)i * ld + j]; }, lap_u, lap_v, lap_spc, path,
+                                                    col4row, row4col, lap_rem, lap_sr, lap_sc);
+                    if (!ok && lane_id() == 0) { atomicOr(status, TK_DEV_LAP_INFEASIBLE); sh->lap_ok = 0; }
+                }
+                __syncthreads();
+                if (sh->lap_ok) for (int i = tid; i < nr; i += SS_THREADS) {
+                    const int j = col4row[i];
+                    const int r = a_rows ? i : j, d = a_rows ? j : i;
+                    touch_d[d] = 1;
+                    if (cost[(size_t)i * ld + j] > prm.max_dist) rej_t[r] = d; else { match_a[r] = d; match_b[d] = r; }
                 }
             }
             __syncthreads();
@@ -393,7 +412,10 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
             int nc = warp_compact(nt, 0, [&](int k) { return S.state[S.list[k]] != SS_CONFIRMED; }, [&](int k, int p) { cand[p] = S.list[k]; });
             nc = warp_compact(nconf, nc, [&](int r) { return match_a[r] < 0 && S.tsu[S.conf_list[r]] == 1; },
                               [&](int r, int p) { cand[p] = S.conf_list[r]; });
-            const int nu = warp_compact(nd, 0, [&](int d) { return match_b[d] < 0; }, [&](int d, int p) { un_d[p] = d; });
+            // unmatched_detections in the reference's order (linear_assignment.py:57-68): columns the solver left alone, in
+            // detection order, then the detections of the rejected pairs in ROW (track list) order
+            int nu = warp_compact(nd, 0, [&](int d) { return !touch_d[d]; }, [&](int d, int p) { un_d[p] = d; });
+            nu = warp_compact(nconf, nu, [&](int r) { return rej_t[r] >= 0; }, [&](int r, int p) { un_d[p] = rej_t[r]; });
             if (lane_id() == 0) { sh->npairs = np_; sh->ncand = nc; sh->nud = nu; }
         }
         for (int k = tid; k < cap; k += SS_THREADS) t_flag[k] = 0;     // t_flag[slot] = 1 when the track got a detection this frame
@@ -421,26 +443,35 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
                     const double uni = __dsub_rn(__dadd_rn(__dmul_rn(w, m[3]), (double)__fmul_rn(cb[2], cb[3])), inter);
                     v = 1.0 - inter / uni;
                 }
-                const double red = v > prm.max_iou_dist ? 0.0 : v - L_iou;
-                if (a_rows) cost[(size_t)r * ld + c] = red; else cost[(size_t)c * ld + r] = red;
+                const double cl = v > prm.max_iou_dist ? L_iou : v;
+                if (a_rows) cost[(size_t)r * ld + c] = cl; else cost[(size_t)c * ld + r] = cl;
             }
-            for (int i = tid; i < ncand; i += SS_THREADS) match_a[i] = -1;
-            for (int i = tid; i < nud; i += SS_THREADS) match_b[i] = -1;
+            for (int i = tid; i < ncand; i += SS_THREADS) { match_a[i] = -1; rej_t[i] = -1; }
+            for (int i = tid; i < nud; i += SS_THREADS) { match_b[i] = -1; touch_d[i] = 0; }
+            if (tid == 0) sh->lap_ok = 1;
             __syncthreads();
             if (ncand > 0 && nud > 0) {
                 const int nr = a_rows ? ncand : nud, nc = a_rows ? nud : ncand;
-                if (!lap_solve_cta(cost, ld, nr, nc, true, lap_u, col4row, row4col, path, &sh->lap_ok)) { if (tid == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); }
-                else for (int r = tid; r < nr; r += SS_THREADS) {
-                    const int c = col4row[r];
-                    if (c >= 0 && cost[(size_t)r * ld + c] < 0.0) { if (a_rows) { match_a[r] = c; match_b[c] = r; } else { match_a[c] = r; match_b[r] = c; } }
+                if (warp_id() == 0) {
+                    const bool ok = lsap_scipy_warp(nr, nc, [&](int i, int j) { return cost[(size_t)i * ld + j]; }, lap_u, lap_v, lap_spc, path,
+                                                    col4row, row4col, lap_rem, lap_sr, lap_sc);
+                    if (!ok && lane_id() == 0) { atomicOr(status, TK_DEV_LAP_INFEASIBLE); sh->lap_ok = 0; }
+                }
+                __syncthreads();
+                if (sh->lap_ok) for (int i = tid; i < nr; i += SS_THREADS) {
+                    const int j = col4row[i];
+                    const int r = a_rows ? i : j, c = a_rows ? j : i;
+                    touch_d[c] = 1;
+                    if (cost[(size_t)i * ld + j] > prm.max_iou_dist) rej_t[r] = c; else { match_a[r] = c; match_b[c] = r; }
                 }
             }
             __syncthreads();
             if (warp_id() == 0) {
                 const int np_ = warp_compact(ncand, sh->npairs, [&](int r) { return match_a[r] >= 0; },
                                              [&](int r, int p) { pair_t[p] = cand[r]; pair_d[p] = un_d[match_a[r]]; });
-                // detections that stay unmatched, in the reference's order: untouched columns first, then the rejected pairs
-                int nu = warp_compact(nud, 0, [&](int c) { return match_b[c] < 0; }, [&](int c, int p) { tmp_d[p] = un_d[c]; });
+                // detections that stay unmatched, in the reference's order: untouched columns first, then the rejected pairs in row order
+                int nu = warp_compact(nud, 0, [&](int c) { return !touch_d[c]; }, [&](int c, int p) { tmp_d[p] = un_d[c]; });
+                nu = warp_compact(ncand, nu, [&](int r) { return rej_t[r] >= 0; }, [&](int r, int p) { tmp_d[p] = un_d[rej_t[r]]; });
                 if (lane_id() == 0) { sh->npairs = np_; sh->nud = nu; }
             }
             __syncthreads();
@@ -481,9 +512,8 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
                 if (!t_flag[s]) { if (S.state[s] == SS_TENTATIVE || S.tsu[s] > prm.max_age) S.state[s] = SS_DELETED; }
             }
             __syncwarp();
-            // births in the order of the reference's unmatched_detections: untouched columns (tmp_d), then rejected pairs — the
-            // device solver never returns rejected pairs (they are cost 0 and dropped), so those detections are exactly the
-            // columns without a match; their relative order is the solver-tie caveat of DESIGN.md §3.
+            // births in the order of the reference's unmatched_detections (tmp_d: untouched columns, then the rejected pairs in
+            // row order — the pairs scipy's tie-breaking picks among the equal clamped costs, reproduced by lsap_scipy.cuh)
             const int nfree = S.hdr[5];
             const int nb = sh->nud < nfree ? sh->nud : nfree;
             if (sh->nud > nfree && lane == 0) atomicOr(status, TK_DEV_OVERFLOW_TRACKS);
@@ -591,6 +621,7 @@ size_t ss_smem(int cap, int capd) {
     size_t s = 0;
     s += al(8 * (size_t)(cap + 1) * (capd + 1)) + al(8 * side) + al(8 * 4 * capd) + al(4 * 4 * capd) + al(8 * 24 * cap);
     s += 5 * al(4 * side) + al(4 * cap) + 2 * al(4 * capd) + 4 * al(4 * cap) + al(cap) + al(capd) + al(sizeof(SsShared));
+    s += 2 * al(8 * side) + 2 * al(4 * side) + 3 * al(side);   // lsap_scipy scratch
     return s;
 }
 
@@ -638,6 +669,7 @@ int tk_strongsort_run(void* handle, const double* dets, const float* features, c
     void* args[] = {&h->prm, &h->state, &h->state_stride, &cap, &capd, &ncta, &dets, &features, &offsets, &n_frames,
                     &out_rows, &out_start, &out_frame_count, &out_count, &out_capacity_rows};
     // cooperative launch: every CTA of a video group must be co-resident for the group barrier
+    TK_CUDA_TRY(cudaFuncSetAttribute(strongsort_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));   // per function, not per handle
     TK_CUDA_TRY(cudaLaunchCooperativeKernel((void*)strongsort_video_kernel, dim3(h->n_seq * ncta), dim3(SS_THREADS), args,
                                             h->smem_bytes, (cudaStream_t)stream));
     return TK_OK;

@@ -8,6 +8,7 @@ for a whole batch of frames at once; nothing returns to the host until the video
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -15,16 +16,42 @@ from . import _lib, kernels
 from .nets.yolox import build_yolox
 
 
+WEIGHTS_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "weights")
+
+
+def synth_weights_path(variant: str):
+    """weights/yolox_<variant>_synth.pt (tools/train_synth_detector.py: the restated YOLOX trained on the synthetic generator so
+    that it localises the synthetic targets) or None when the file is not there."""
+    p = os.path.join(WEIGHTS_DIR, f"yolox_{variant}_synth.pt")
+    return p if os.path.isfile(p) else None
+
+
+def load_yolox_weights(variant: str, path, num_classes: int = 1):
+    """state_dict file of tracklab_b200.nets.yolox.YOLOX -> module. A path that does not exist is an error (never a silent
+    fall back to random weights)."""
+    if not os.path.isfile(str(path)):
+        raise _lib.TrackKernError(f"detector weights {path!r} not found")
+    blob = torch.load(str(path), map_location="cpu")
+    sd = blob.get("state_dict", blob)
+    m = build_yolox(variant, num_classes, 0)
+    m.load_state_dict({k: v.float() for k, v in sd.items()})
+    return m.eval()
+
+
 class YoloxDetectorDevice:
     def __init__(self, variant="s", device="cuda:0", batch=32, input_size=640, dtype=torch.bfloat16,
                  score_thr=0.7, nms_thr=0.45, max_per_image=256, num_classes=1, seed=1234,
-                 frames_cap=4096, dets_cap=1 << 18, use_graph=True, model=None, fused=True):
+                 frames_cap=4096, dets_cap=1 << 18, use_graph=True, model=None, fused=True, weights=None, rows_ltwh=False):
         if not torch.cuda.is_available():
             raise _lib.TrackKernError("YoloxDetectorDevice needs a CUDA device (no CPU path)")
         _lib.load()
         self.device = torch.device(device)
         self.batch, self.size, self.dtype = batch, input_size, dtype
         self.score_thr, self.nms_thr, self.max_per_image = score_thr, nms_thr, max_per_image
+        if model is None and weights is not None:
+            model = load_yolox_weights(variant, weights, num_classes)
+        self.trained = weights is not None
+        self.rows_ltwh = bool(rows_ltwh)
         self.model = (model if model is not None else build_yolox(variant, num_classes, seed))
         self.model = self.model.to(self.device).to(dtype).to(memory_format=torch.channels_last).eval()
         for p in self.model.parameters():
@@ -45,6 +72,7 @@ class YoloxDetectorDevice:
         self.cursor = torch.zeros((2,), dtype=torch.int32, device=self.device)      # {next row, next frame}
         self.dets = torch.zeros((dets_cap, 7), dtype=torch.float64, device=self.device)
         self.offsets = torch.zeros((frames_cap + 1,), dtype=torch.int32, device=self.device)
+        self.frame_of_row = torch.zeros((dets_cap,), dtype=torch.int32, device=self.device)   # batch-local image index of every row
         self.ratio = None
         self.geom = None
         self.graph = None
@@ -114,7 +142,7 @@ class YoloxDetectorDevice:
                                          nms_thr=self.nms_thr, max_out=self.max_per_image, status=self.status)
         boxes, scores, cls, count, _ = self.nms_out
         kernels.pack_detections(boxes, scores, cls, count, W, H, self.cursor, self.dets, self.offsets, self.status,
-                                keep_class=0, fixed_conf=1.0, category_id=1.0)
+                                keep_class=0, fixed_conf=1.0, category_id=1.0, ltwh=self.rows_ltwh, frame_of_row=self.frame_of_row)
 
     def reset(self):
         self.cursor.zero_()
@@ -132,11 +160,14 @@ class YoloxDetectorDevice:
                 x = torch.zeros((B, self._fused_cls.STEM_IN, self.size // 2, self.size // 2), dtype=self.dtype,
                                 device=self.device).contiguous(memory_format=torch.channels_last)
                 _, self.ratio = kernels.letterbox(frames, self.size, self.dtype, swap_rb=True, out=x, focus16=True)
-                cur = self.cursor.clone()
+                # the warm-up / capture runs append at the live cursor and may trip the sticky capacity bit near the end of
+                # the buffers: cursor AND status are restored afterwards (each run restarts at the saved cursor)
+                cur, st = self.cursor.clone(), self.status.clone()
                 s = torch.cuda.Stream(device=self.device)
                 s.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(s):
                     for _ in range(3):
+                        self.cursor.copy_(cur)
                         self._forward_post_impl(W, H, x)
                 torch.cuda.current_stream().wait_stream(s)
                 torch.cuda.synchronize()
@@ -144,7 +175,7 @@ class YoloxDetectorDevice:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._forward_post_impl(W, H, x)
-                self.cursor.copy_(cur)
+                self.cursor.copy_(cur); self.status.copy_(st)
                 ent = (g, x)
                 self._tail_graphs[(B, H, W)] = ent
             g, x = ent
@@ -161,7 +192,8 @@ class YoloxDetectorDevice:
             pred = self._net(x)
             boxes, scores, cls, count, _ = kernels.yolox_nms(pred, ratio, self.size, True, self.score_thr, self.nms_thr,
                                                              self.max_per_image, status=self.status)
-            kernels.pack_detections(boxes, scores, cls, count, W, H, self.cursor, self.dets, self.offsets, self.status)
+            kernels.pack_detections(boxes, scores, cls, count, W, H, self.cursor, self.dets, self.offsets, self.status,
+                                    ltwh=self.rows_ltwh, frame_of_row=self.frame_of_row)
             return
         if self.time_kernels:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -175,11 +207,12 @@ class YoloxDetectorDevice:
             return
         if self.graph is None or self.geom != (H, W):
             self.geom = (H, W)
-            cur = self.cursor.clone()
+            cur, st = self.cursor.clone(), self.status.clone()
             s = torch.cuda.Stream(device=self.device)
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                for _ in range(3):   # warm-up (cuDNN autotune) outside capture
+                for _ in range(3):   # warm-up (cuDNN autotune) outside capture; every run restarts at the saved cursor
+                    self.cursor.copy_(cur)
                     self._forward_post(W, H)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
@@ -187,7 +220,7 @@ class YoloxDetectorDevice:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._forward_post(W, H)
-            self.cursor.copy_(cur)
+            self.cursor.copy_(cur); self.status.copy_(st)
         self.graph.replay()
 
     def detect_into(self, frames: torch.Tensor) -> int:

@@ -82,17 +82,22 @@ def yolox_nms(pred: torch.Tensor, ratio: float, input_size: int = 640, logits: b
 
 def pack_detections(boxes, scores, cls, count, width: int, height: int, cursor: torch.Tensor, dets_out: torch.Tensor,
                     offsets_out: torch.Tensor, status: torch.Tensor, keep_class: int = 0, fixed_conf: float = 1.0,
-                    category_id: float = 1.0):
+                    category_id: float = 1.0, ltwh: bool = False, frame_of_row: torch.Tensor | None = None):
     """NMS output -> tracker rows float64[.,7] appended at row cursor[0]; frame offsets written at
-    offsets_out[cursor[1]:cursor[1]+B+1]; cursor (device int32[2]) is advanced by the kernel."""
+    offsets_out[cursor[1]:cursor[1]+B+1]; cursor (device int32[2]) is advanced by the kernel. ``ltwh`` writes [l,t,w,h,..]
+    rows (the detector's bbox_ltwh column) instead of [l,t,r,b,..]; ``frame_of_row`` (int32[dets_cap]) receives the batch-local
+    image index of every appended row (C ABI: tk_pack_detections_ex)."""
     lib = _lib.load()
     B, K = scores.shape
+    if frame_of_row is not None:
+        assert frame_of_row.dtype == torch.int32 and frame_of_row.numel() >= dets_out.shape[0]
     with torch.cuda.device(boxes.device):
-        _lib.check(lib.tk_pack_detections(boxes.data_ptr(), scores.data_ptr(), cls.data_ptr(), count.data_ptr(), B, K,
-                                          keep_class, width, height, float(fixed_conf), float(category_id),
-                                          cursor.data_ptr(), dets_out.data_ptr(), offsets_out.data_ptr(),
-                                          dets_out.shape[0], offsets_out.shape[0] - 1, status.data_ptr(), _stream()),
-                   "tk_pack_detections"); _count()
+        _lib.check(lib.tk_pack_detections_ex(boxes.data_ptr(), scores.data_ptr(), cls.data_ptr(), count.data_ptr(), B, K,
+                                             keep_class, width, height, float(fixed_conf), float(category_id),
+                                             cursor.data_ptr(), dets_out.data_ptr(), offsets_out.data_ptr(),
+                                             dets_out.shape[0], offsets_out.shape[0] - 1, status.data_ptr(), int(bool(ltwh)),
+                                             frame_of_row.data_ptr() if frame_of_row is not None else None, _stream()),
+                   "tk_pack_detections_ex"); _count()
     return dets_out, offsets_out
 
 
@@ -219,6 +224,22 @@ def cosine_dist(a: torch.Tensor, b: torch.Tensor):
     return out
 
 
+def lsap_scipy_batched(cost: torch.Tensor, status: torch.Tensor | None = None):
+    """cost float64 [B,N,M] -> (x int32 [B,N], y int32 [B,M], status): scipy.optimize.linear_sum_assignment including its
+    tie-breaking (C ABI: tk_lsap_scipy_batched)."""
+    lib = _lib.load()
+    _cuda(cost, "cost")
+    B, N, M = cost.shape
+    x = torch.empty((B, N), dtype=torch.int32, device=cost.device)
+    y = torch.empty((B, M), dtype=torch.int32, device=cost.device)
+    if status is None:
+        status = torch.zeros((1,), dtype=torch.int32, device=cost.device)
+    with torch.cuda.device(cost.device):
+        _lib.check(lib.tk_lsap_scipy_batched(cost.data_ptr(), B, N, M, x.data_ptr(), y.data_ptr(), status.data_ptr(), _stream()),
+                   "tk_lsap_scipy_batched"); _count()
+    return x, y, status
+
+
 def lap_batched(cost: torch.Tensor, cost_limit: float | None = None, status: torch.Tensor | None = None):
     """cost float64 [B,N,M] -> (x int32 [B,N], y int32 [B,M], status) (C ABI: tk_lap_batched)."""
     lib = _lib.load()
@@ -273,8 +294,10 @@ REID_STD = (0.229, 0.224, 0.225)
 
 def crop_resize_norm(frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.Tensor, out_hw=(256, 128),
                      out_dtype=torch.float32, channels_last: bool = False, mean=REID_MEAN, std=REID_STD, pad_channels_to: int = 3,
-                     s2d16_out: torch.Tensor | None = None, out: torch.Tensor | None = None):
-    """frames uint8 [F,H,W,3], dets float64 [N,7], det_frame int32 [N] -> ReID input [N,3,h,w] (C ABI: tk_crop_resize_norm).
+                     s2d16_out: torch.Tensor | None = None, out: torch.Tensor | None = None, ltwh_rows: bool = False):
+    """frames uint8 [F,H,W,3], dets float64 [N,7], det_frame int32 [N] -> ReID input [N,3,h,w] (C ABI: tk_crop_resize_norm_ex).
+    ltwh_rows: rows are [l,t,w,h,..] and the crop follows the ReID wrapper's rounded/clipped rule (kpreid_api.py:118-121)
+    instead of StrongSORT's centre/int() rule on [l,t,r,b,..] rows.
     pad_channels_to=8 (channels-last only) returns [N,8,h,w] with zero channels 3..7 for the fused backbone."""
     lib = _lib.load()
     _cuda(frames, "frames"); _cuda(dets, "dets"); _cuda(det_frame, "det_frame")
@@ -287,9 +310,9 @@ def crop_resize_norm(frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.
         m = (ctypes.c_float * 3)(*mean)
         sd = (ctypes.c_float * 3)(*std)
         with torch.cuda.device(frames.device):
-            _lib.check(lib.tk_crop_resize_norm(frames.data_ptr(), H, W, frames.stride(0), dets.data_ptr(), det_frame.data_ptr(), N,
-                                               s2d16_out.data_ptr(), _dtype_code(s2d16_out.dtype), -16, out_hw[0], out_hw[1], m, sd,
-                                               _stream()), "tk_crop_resize_norm"); _count()
+            _lib.check(lib.tk_crop_resize_norm_ex(frames.data_ptr(), H, W, frames.stride(0), dets.data_ptr(), det_frame.data_ptr(), N,
+                                                  s2d16_out.data_ptr(), _dtype_code(s2d16_out.dtype), -16, out_hw[0], out_hw[1], m, sd,
+                                                  int(ltwh_rows), _stream()), "tk_crop_resize_norm_ex"); _count()
         return s2d16_out
     if out is not None:   # caller-owned (bucket-sized) buffer: the first N crops are written
         assert out.shape[0] >= N and out.dtype == out_dtype and pad_channels_to == 3
@@ -304,7 +327,7 @@ def crop_resize_norm(frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.
     m = (ctypes.c_float * 3)(*mean)
     sd = (ctypes.c_float * 3)(*std)
     with torch.cuda.device(frames.device):
-        _lib.check(lib.tk_crop_resize_norm(frames.data_ptr(), H, W, frames.stride(0), dets.data_ptr(), det_frame.data_ptr(), N,
-                                           out.data_ptr(), _dtype_code(out_dtype), (pad_channels_to if channels_last else 0), out_hw[0], out_hw[1], m, sd,
-                                           _stream()), "tk_crop_resize_norm"); _count()
+        _lib.check(lib.tk_crop_resize_norm_ex(frames.data_ptr(), H, W, frames.stride(0), dets.data_ptr(), det_frame.data_ptr(), N,
+                                              out.data_ptr(), _dtype_code(out_dtype), (pad_channels_to if channels_last else 0), out_hw[0], out_hw[1], m, sd,
+                                              int(ltwh_rows), _stream()), "tk_crop_resize_norm_ex"); _count()
     return out

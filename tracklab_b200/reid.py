@@ -96,14 +96,15 @@ class ReidStageDevice:
         torch.backends.cudnn.benchmark = True
 
     @torch.no_grad()
-    def features(self, frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.Tensor) -> torch.Tensor:
-        """frames uint8 [F,H,W,3], dets float64 [N,7], det_frame int32 [N] (frame index of each row) -> float32 [N,E]."""
+    def features(self, frames: torch.Tensor, dets: torch.Tensor, det_frame: torch.Tensor, ltwh_rows: bool = False) -> torch.Tensor:
+        """frames uint8 [F,H,W,3], dets float64 [N,7], det_frame int32 [N] (frame index of each row) -> float32 [N,E].
+        ltwh_rows: rows are the detector's [l,t,w,h,..] and the crop follows the ReID wrapper's rule (kernels.crop_resize_norm)."""
         N = dets.shape[0]
         out = torch.empty((N, self.feature_dim), dtype=torch.float32, device=self.device)
         for i in range(0, N, self.max_crops):
             j = min(N, i + self.max_crops)
             if self.precision == "fp32":
-                x = kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.float32)
+                x = kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.float32, ltwh_rows=ltwh_rows)
                 tf32 = torch.backends.cudnn.allow_tf32
                 torch.backends.cudnn.allow_tf32 = False
                 try:
@@ -112,17 +113,17 @@ class ReidStageDevice:
                     torch.backends.cudnn.allow_tf32 = tf32
             elif self.generic is not None:
                 buf = self.generic.input_buffer(j - i)
-                kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.bfloat16, channels_last=True, out=buf)
+                kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.bfloat16, channels_last=True, out=buf, ltwh_rows=ltwh_rows)
                 out[i:j] = self.generic(buf, j - i)
             elif self.fused is not None and not self.fused.legacy:
                 buf = self.fused.input_buffer(j - i)   # s2d16 stem layout, crop count rounded up to the bucket
-                kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], s2d16_out=buf)
+                kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], s2d16_out=buf, ltwh_rows=ltwh_rows)
                 out[i:j] = self.fused(buf, n_valid=j - i)
             elif self.fused is not None:
                 x = kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.bfloat16, channels_last=True,
-                                             pad_channels_to=8)
+                                             pad_channels_to=8, ltwh_rows=ltwh_rows)
                 out[i:j] = self.fused(x)
             else:
-                x = kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.bfloat16, channels_last=True)
+                x = kernels.crop_resize_norm(frames, dets[i:j], det_frame[i:j], out_dtype=torch.bfloat16, channels_last=True, ltwh_rows=ltwh_rows)
                 out[i:j] = self.model(x).float()
         return out
