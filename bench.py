@@ -1,24 +1,24 @@
 #!/usr/bin/env python
-"""Benchmark of the tracking hot path (BASELINE.json metric: tracking FPS, 1080p, ~40 det/frame).
+"""Benchmark of the tracking hot path (BASELINE.json metric: tracking FPS, 1080p, ~40 det/frame, detect -> ReID -> associate).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F] [--batch B] [--config config3]
 
-Workload (BASELINE.json configs[1]): YOLOX-s detector + ByteTrack association on a synthetic 1080p video,
-500 frames, ~38 detections/frame after the wrapper filter. One STEP = one pass of the whole video through
-letterbox -> YOLOX-s (bf16, PyTorch/cuDNN) -> decode+NMS -> row packing -> ByteTrack.
+Headline workload = BASELINE.json configs[2] ("config3"): YOLOX-m detector + ResNet-50 ReID embeddings (256x128 crops, 2048-d)
++ StrongSORT association (cosine + IoU + Kalman gating) on a synthetic 1080p video, 500 frames, ~38 detections/frame.
+One STEP = one pass of the whole video through the CONNECTED product pipeline
+(tracklab_b200.video_pipeline.DetectReidTrackPipeline): letterbox -> YOLOX-m (bf16) -> decode+NMS -> tk_pack_detections_ex rows at
+the device cursor -> tk_crop_resize_norm_ex crops of THOSE rows -> ResNet-50 (bf16) -> tk_strongsort_run on THOSE rows and features.
+The detector is the restated YOLOX trained on the synthetic generator (weights/yolox_<v>_synth.pt, tools/train_synth_detector.py)
+so it localises the synthetic targets: the tracker tracks what the detector emitted, on both arms.
+BASELINE.json configs[1] (YOLOX-s + ByteTrack, "config2") is measured in the same run and reported as a second object.
 
-  * ours      : frames resident in HBM (`value`) and frames in pinned host memory with the H2D copies and the
-                D2H read of the result rows inside the timed region (`e2e`). Multi-GPU: one video per rank
-                (weak scaling, no data-path collective), one all_gather of the per-video metrics at the end.
-  * reference : the CPU restatement of the same loop (oracle/pipeline_np.py: cv2 letterbox, the same YOLOX-s in
-                fp32 on the host threads at batch 1, NumPy decode/NMS, NumPy ByteTrack) on a bounded sample of
-                the same video. /root/reference does not exist on the GPU box and its detector back-end
-                (rtmlib + onnxruntime) is not installable offline, so the oracle port IS the reference arm here.
-
-Synthetic-data note: the detector has seeded random weights (calibrated so that NMS sees
-~100 candidates per frame) and therefore cannot localise the synthetic targets; its rows are computed in full and
-discarded, while the tracker consumes the generator's ~38 det/frame stream — batch k of the tracker still waits
-for batch k of the detector. Both arms do the same.
+  * ours      : frames resident in HBM (`value`) and frames in pinned host memory with the H2D copies and the D2H read of the
+                result rows inside the timed region (`e2e`). Multi-GPU: one video per rank (weak scaling, no data-path
+                collective), ONE all_gather of the per-video metrics (incl. every rank's own step time) at the end.
+  * reference : the CPU restatement of the same loop (oracle/pipeline_np.py: cv2 letterbox, the same YOLOX in fp32 on the host
+                threads at batch 1, NumPy decode/NMS, PIL crops, the same ResNet-50 in fp32, NumPy StrongSORT) on a bounded
+                sample of the same video. /root/reference does not exist on the GPU box and its detector back-end (rtmlib +
+                onnxruntime) is not installable offline, so the oracle port IS the reference arm here (kind "port").
 """
 import argparse
 import json
@@ -33,22 +33,25 @@ sys.path.insert(0, ROOT)
 
 METRIC = "tracking_fps_1080p_40det"
 UNIT = "frames/s"
-HYPER = dict(track_thresh=0.6, match_thresh=0.8, track_buffer=30, frame_rate=30)
 MIN_CONF = 0.4
+FLOPS_PER_FRAME = {"s": 26.8e9, "m": 73.8e9}      # YOLOX @640x640
+RESNET50_FLOPS_PER_CROP = 5.4e9                    # 256x128 crop
+VIDEO_SEED = {"config2": 2000, "config3": 3000, "config3_bpbreid": 3000, "config2_ocsort": 2000}
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=500)
-    ap.add_argument("--batch", type=int, default=50)
-    ap.add_argument("--variant", default="s")
-    ap.add_argument("--ref-frames", type=int, default=24, help="frames per step of the CPU arm (bounded sample)")
+    ap.add_argument("--batch", type=int, default=20, help="detector batch of the headline configuration")
+    ap.add_argument("--config", default="config3")
+    ap.add_argument("--ref-frames", type=int, default=6, help="frames per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-config2", action="store_true")
     return ap.parse_args()
 
 
@@ -100,30 +103,84 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads (and therefore its first-touch pinned buffers and the H2D source pages) to the NUMA node of
+    its GPU. Unbound ranks on a 2-socket host cost 21 % of the 8-GPU end-to-end rate in round 1 (cross-socket H2D reads)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "kernel reports no NUMA affinity for the GPU"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus), "pci": bdf}
+    except Exception as e:      # binding is an optimisation, never a reason to fail the bench
+        return {"numa_node": None, "note": f"{type(e).__name__}: {e}"}
+
+
+def workload_config(args, config, variant, tracker, reid, trained, world):
+    det = f"YOLOX-{variant}"
+    return {"workload": f"{config}: {det}{' + ResNet-50 ReID (256x128, 2048-d)' if reid else ''} + {tracker}, 1080p synthetic video, "
+                        f"{args.frames} frames, ~38 det/frame (44 identities, 10% misses, occlusion bursts)",
+            "frames_per_step": args.frames, "resolution": "1920x1080",
+            "tracker_input": "the detector's own rows (connected chain: tk_pack_detections_ex -> crops -> ReID -> tracker)",
+            "detector_weights": ("trained on the synthetic generator (weights/, tools/train_synth_detector.py)" if trained
+                                 else "seeded random, calibrated heads (weights/ file absent)"),
+            "l2_policy": "inputs larger than L2: 3.1 GB of frames are read per step, no explicit flush",
+            "parallelism": f"{world} video(s), one per GPU"}
 
 
 # ---------------------------------------------------------------------------------------------------
-def pick_cpu_threads(model, frames, video, cores):
-    """The CPU arm gets the thread count that serves it best: batch-1 convolutions on small feature maps do not
-    scale to every hardware thread of a 100+ core host (oversubscription makes them slower, not faster)."""
+def cpu_chain(config, variant, frames_np, video, n, threads=None):
+    """One pass of the CPU restatement over the first n frames; returns (seconds, tracker rows, frame index, detector rows)."""
+    import torch
+
+    from oracle import pipeline_np
+    from tracklab_b200.detector import load_yolox_weights, synth_weights_path
+    from tracklab_b200.nets.yolox import build_yolox
+    from tracklab_b200.video_pipeline import CONFIGS
+    wp = synth_weights_path(variant)
+    det = (load_yolox_weights(variant, wp) if wp else build_yolox(variant, 1, 1234, prior_prob=0.01)).float().eval()
+    hyper = CONFIGS[config]["hyper"]
+    if CONFIGS[config]["reid"] is None:
+        t0 = time.perf_counter()
+        rows, fr, det_rows = pipeline_np.detect_track_video(det, frames_np[:n], None, None, hyper, MIN_CONF)
+        return time.perf_counter() - t0, rows, fr, det_rows
+    from tracklab_b200.nets.resnet_reid import build_resnet50_reid
+    reid = build_resnet50_reid(1234).float().eval()
+    t0 = time.perf_counter()
+    rows, fr, det_rows, _ = pipeline_np.detect_reid_track_video(det, reid, frames_np[:n], hyper, MIN_CONF)
+    return time.perf_counter() - t0, rows, fr, det_rows
+
+
+def pick_cpu_threads(cores):
+    """Batch-1 convolutions on small feature maps do not scale to every hardware thread of a 100+ core host; the CPU arm gets
+    the best of a few thread counts (measured on one YOLOX-s frame)."""
     import torch
 
     from oracle.pipeline_np import detect_frame
+    from tracklab_b200.nets.yolox import build_yolox
+    import numpy as np
+    m = build_yolox("s", 1, 1234).float().eval()
+    img = np.zeros((1080, 1920, 3), np.uint8)
     best, best_t = None, None
-    cands = sorted({c for c in (4, 8, 16, 32, 64, cores) if c <= cores})
-    for c in cands:
+    for c in sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}):
         torch.set_num_threads(c)
-        detect_frame(model, frames[0])
+        detect_frame(m, img)
         t0 = time.perf_counter()
-        for k in range(2):
-            detect_frame(model, frames[k % len(frames)])
-        dt = (time.perf_counter() - t0) / 2
+        detect_frame(m, img)
+        dt = time.perf_counter() - t0
         if best_t is None or dt < best_t:
             best, best_t = c, dt
-        if dt > 4 * best_t:
-            break
     torch.set_num_threads(best)
     return best
 
@@ -131,66 +188,250 @@ def pick_cpu_threads(model, frames, video, cores):
 def run_reference(args):
     """CPU arm: bounded sample of the same workload per step, all host threads torch/BLAS will use."""
     import numpy as np
-    import torch
 
-    from oracle.pipeline_np import detect_track_video
-    from tracklab_b200.nets.yolox import build_yolox
     from tracklab_b200.synth import make_frames, make_video
-
+    from tracklab_b200.video_pipeline import CONFIGS
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    video = make_video(seed=2000, n_frames=args.frames, n_ids=44)
+    used = pick_cpu_threads(cores)
+    video = make_video(seed=VIDEO_SEED[args.config], n_frames=args.frames, n_ids=44)
     n = min(args.ref_frames, args.frames)
     frames = make_frames(video, 0, n, device="cpu").numpy()
-    model = build_yolox(args.variant).float().eval()
-    offs = video.offsets
-    used = pick_cpu_threads(model, frames, video, cores)
-
-    def one_step():
-        t0 = time.perf_counter()
-        rows, fr, det_rows = detect_track_video(model, frames, video.dets, offs, HYPER, MIN_CONF)
-        return time.perf_counter() - t0, rows
-
-    for _ in range(max(1, min(args.warmup, 1))):
-        one_step()
-    times = [one_step()[0] for _ in range(args.steps)]
+    cpu_chain(args.config, cfg["variant"], frames, video, min(2, n))
+    times = [cpu_chain(args.config, cfg["variant"], frames, video, n)[0] for _ in range(max(1, min(args.steps, 3)))]
     total = sum(times)
-    fps = args.steps * n / total
-    sample = (f"first {n} frames of the {args.frames}-frame video per step (detector batch 1, fp32, {used} of {cores} "
-              "host threads: best of 4/8/16/32/64/all)")
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 detector / f64 association", "data": "synthetic",
-            "config": workload_config(args),
+    fps = len(times) * n / total
+    from tracklab_b200.detector import synth_weights_path
+    sample = (f"first {n} frames of the {args.frames}-frame video per step x {len(times)} steps (detector + ReID batch 1 per frame, fp32, "
+              f"{used} of {cores} host threads: best of 8/16/32/64/all)")
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": 1, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 detector + ReID / f64 association", "data": "synthetic",
+            "config": workload_config(args, args.config, cfg["variant"], cfg["tracker"], cfg["reid"], synth_weights_path(cfg["variant"]) is not None, args.gpus),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def workload_config(args):
-    return {"workload": f"config2: YOLOX-{args.variant} + ByteTrack, 1080p synthetic video, {args.frames} frames, "
-                        "~38 det/frame (44 identities, 10% misses, occlusion bursts)",
-            "frames_per_step": args.frames, "detector_batch": args.batch, "resolution": "1920x1080",
-            "tracker_input": "generator detections (random-weight detector rows are computed in full and discarded)",
-            "l2_policy": "inputs larger than L2: 3.1 GB of frames are read per step, no explicit flush",
-            "parallelism": f"{args.gpus} video(s), one per GPU"}
-
-
 # ---------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """CUDA events around every libtrackkern launch of one eager (non-graph) pass: per-kernel device time, algorithmic bytes
+    and flops. Wraps the Python entry points of tracklab_b200.kernels for the duration of a `with` block."""
+
+    def __init__(self):
+        self.rec = {}
+
+    def __enter__(self):
+        import torch
+
+        from tracklab_b200 import kernels as k
+        self.k, self.orig = k, {}
+
+        def wrap(name, cost):
+            fn = getattr(k, name)
+            self.orig[name] = fn
+
+            def timed(*a, **kw):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(*a, **kw)
+                e1.record()
+                nbytes, flops = cost(a, kw, out)
+                self.rec.setdefault(name, []).append((e0, e1, nbytes, flops))
+                return out
+            setattr(k, name, timed)
+
+        def c_conv1x1(a, kw, out):
+            x, w = a[0], a[1]
+            M = x.numel() // x.shape[1] if x.dim() == 4 else x.shape[0]
+            K, N = w.shape[1], w.shape[0]
+            res = kw.get("residual") is not None
+            return M * (2 * K + 2 * N + (2 * N if res else 0)) + 2 * N * K, 2.0 * M * K * N
+
+        def c_bias_act(a, kw, out):
+            src = a[0]
+            res = (kw.get("residual") is not None) or (len(a) > 5 and a[5] is not None)
+            return src.numel() * 2 * (3 if res else 2), 0.0
+
+        def c_crop(a, kw, out):
+            n = a[1].shape[0]
+            return n * 256 * 128 * 3 * 2 * 2, 0.0          # ~output-sized read of source pixels + bf16 crop written
+
+        wrap("conv1x1_bias_act", c_conv1x1)
+        wrap("bias_act", c_bias_act)
+        wrap("crop_resize_norm", c_crop)
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self.orig.items():
+            setattr(self.k, name, fn)
+
+    def summary(self):
+        out = {}
+        for name, rec in self.rec.items():
+            ms = sum(a.elapsed_time(b) for a, b, _, _ in rec)
+            out[name] = {"launches": len(rec), "total_ms": ms, "bytes": sum(r[2] for r in rec), "flops": sum(r[3] for r in rec)}
+        return out
+
+
+def profile_repo_kernels(pipe, frames, B):
+    """Per-kernel device time of the repo's kernels in one eager detector forward + one eager ReID forward (events on the launching stream)."""
+    import torch
+    det, reid = pipe.det, pipe.reid
+    with KernelTimer() as kt:
+        with torch.no_grad():
+            for _ in range(2):
+                kt.rec.clear()
+                det.fused(det.x)
+                n_crops = 0
+                if reid is not None and reid.fused is not None:
+                    n = int(pipe._host_cursor[0, 0]) if pipe._host_cursor is not None else 0
+                    n = max(64, min(n, 1024))
+                    buf = reid.fused.input_buffer(n)
+                    g = reid.fused.use_graphs
+                    reid.fused.use_graphs = False
+                    try:
+                        reid.fused(buf, n_valid=n)
+                    finally:
+                        reid.fused.use_graphs = g
+                    n_crops = buf.shape[0]
+            torch.cuda.synchronize()
+    s = kt.summary()
+    s["_frames"] = B
+    s["_crops"] = n_crops
+    return s
+
+
+def run_config(config, args, dev, rank, world, local, frames_cap, batch, steps, warmup, sampler=None, want_e2e=True):
+    """Time one BASELINE configuration on this rank. Returns a dict of local measurements (device-timed)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from tracklab_b200.synth import make_frames, make_video
+    from tracklab_b200.video_pipeline import CONFIGS, build_pipeline
+    cfg = CONFIGS[config]
+    F = args.frames
+    video = make_video(seed=VIDEO_SEED[config] + rank, n_frames=F, n_ids=44)     # video `rank` of the 8-video set
+    frames = torch.empty((F, video.height, video.width, 3), dtype=torch.uint8, device=dev)
+    for f0 in range(0, F, 25):
+        frames[f0:min(F, f0 + 25)] = make_frames(video, f0, min(F, f0 + 25), device="cpu").to(dev)
+    pipe = build_pipeline(config, device=dev, batch=batch, frames_cap=F, image_size=(video.width, video.height))
+    if not pipe.det.trained:
+        pipe.det.calibrate(frames[:batch], target_per_image=60.0)
+    cols = 14 if cfg["tracker"] == "bpbreid" else 8
+    out_rows = torch.empty(((2 if cfg["tracker"] == "strongsort" else 1) * pipe.rows_cap, cols), dtype=torch.float64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(src, n_steps, read_back, time_kernels=False):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(n_steps):
+            res = pipe.run_video(src, out_rows=out_rows, time_kernels=time_kernels)
+            if read_back:
+                last = pipe.results_to_host(res)      # D2H read of the step's result rows
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), res, last
+
+    timed(frames, warmup, False)
+    if sampler is not None:
+        sampler.rows.clear()          # keep only samples taken during the timed steps
+    pipe.launches = 0
+    pipe.kernel_events = []
+    ranged = os.environ.get("TK_PROFILE_RANGE") == "1" and config == args.config   # ncu --profile-from-start off
+    if ranged:
+        torch.cuda.cudart().cudaProfilerStart()
+    ms, res, _ = timed(frames, steps, False, time_kernels=True)
+    if ranged:
+        torch.cuda.cudart().cudaProfilerStop()
+    launches = pipe.launches
+    clocks = sampler.stop() if sampler is not None else None
+    pipe.check_status()
+    host = pipe.results_to_host(res, with_detections=True)
+    stage_ms = {}
+    for name, a, b, n in pipe.kernel_events:
+        d = stage_ms.setdefault(name, [0.0, 0, 0])
+        d[0] += a.elapsed_time(b); d[1] += 1; d[2] += n
+    kernels = profile_repo_kernels(pipe, frames, batch)
+    ms_e2e, h2d, d2h = None, 0, 0
+    if want_e2e:
+        host_frames = torch.empty(frames.shape, dtype=torch.uint8, pin_memory=True)    # first touch under the NUMA binding
+        host_frames.copy_(frames)
+        timed(host_frames, min(warmup, 2), True)
+        ms_e2e, _, last = timed(host_frames, steps, True)
+        h2d = int(host_frames.nbytes)
+        d2h = int(last.rows.nbytes + F * 4 + 4 + 8)
+        del host_frames
+    return dict(config=config, cfg=cfg, video=video, pipe=pipe, frames=frames, ms=ms, ms_e2e=ms_e2e, h2d=h2d, d2h=d2h, host=host,
+                launches=launches, clocks=clocks, stage_ms=stage_ms, kernels=kernels, steps=steps, warmup=warmup, batch=batch)
+
+
+def gather_and_reduce(r, dev, world):
+    """The single collective of the multi-GPU path: per-video metrics incl. every rank's OWN device-timed step times."""
+    import numpy as np
+    import torch
+
+    from tracklab_b200 import dist as tdist
+    F = r["video"].n_frames
+    n_ids = float(len(np.unique(r["host"].rows[:, 4 if r["cfg"]["tracker"] != "bpbreid" else 0]))) if len(r["host"].rows) else 0.0
+    m = torch.tensor([[F, r["host"].det_rows, len(r["host"].rows), n_ids, r["ms"] / r["steps"],
+                       (r["ms_e2e"] or 0.0) / r["steps"]]], dtype=torch.float64, device=dev)
+    allm = tdist.gather_video_metrics(m)[:, 0].cpu().numpy()        # [world, 6]
+    return allm
+
+
+def roofline_blocks(r, peak_hbm, peak_tf, peak_src):
+    """`roofline` of the dominant kernel of THIS repo in the step + the whole-step tensor figure."""
+    k = r["kernels"]
+    B, crops = max(1, k.pop("_frames")), k.pop("_crops")
+    cand = {n: v for n, v in k.items() if v["total_ms"] > 0}
+    if not cand:
+        return None, None, k
+    top = max(cand, key=lambda n: cand[n]["total_ms"])
+    v = cand[top]
+    gbs = v["bytes"] / (v["total_ms"] * 1e-3) / 1e9
+    tfs = v["flops"] / (v["total_ms"] * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(top)
+    hbm_frac, tens_frac = gbs / peak_hbm, tfs / peak_tf
+    bound = "hbm" if hbm_frac >= tens_frac else "tensor"
+    roof = {"kernel": top, "bound": bound, "achieved": gbs if bound == "hbm" else tfs, "peak": peak_hbm if bound == "hbm" else peak_tf,
+            "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": max(hbm_frac, tens_frac), "peak_source": peak_src,
+            "traffic": (traffic or {}).get("dram_bytes_per_launch") if isinstance(traffic, dict) else None,
+            "traffic_source": (traffic or {}).get("source") if isinstance(traffic, dict) else "no ncu --set full capture of this kernel committed yet",
+            "bytes_per_launch": v["bytes"] / v["launches"], "flops_per_launch": v["flops"] / v["launches"],
+            "avg_launch_ms": v["total_ms"] / v["launches"], "launches_timed": v["launches"],
+            "hbm_GBps": gbs, "hbm_frac": hbm_frac, "tensor_TFLOPs": tfs, "tensor_frac": tens_frac,
+            "how": "CUDA events around every launch of one eager detector forward (batch %d) + one eager ReID forward (%d crops), sums" % (B, crops)}
+    F = r["video"].n_frames
+    variant = r["cfg"]["variant"]
+    flops_step = F * FLOPS_PER_FRAME[variant] + (r["host"].det_rows * RESNET50_FLOPS_PER_CROP if r["cfg"]["reid"] else 0.0)
+    tens = {"bound": "tensor", "achieved": flops_step / (r["ms"] / r["steps"] * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+            "peak_source": peak_src + " (sustained bf16 GEMM)",
+            "flops_per_step": flops_step, "note": "whole step: nominal network FLOPs (YOLOX %s %.1f GFLOP/frame%s) / device step time" % (
+                variant, FLOPS_PER_FRAME[variant] / 1e9, ", ResNet-50 5.4 GFLOP/crop" if r["cfg"]["reid"] else "")}
+    tens["frac"] = tens["achieved"] / peak_tf
+    return roof, tens, k
+
+
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
     from tracklab_b200 import _lib
-    from tracklab_b200 import dist as tdist
-    from tracklab_b200.detector import YoloxDetectorDevice
-    from tracklab_b200.device_trackers import ByteTrackDevice
-    from tracklab_b200.synth import make_frames, make_video
-    from tracklab_b200.video_pipeline import DetectTrackPipeline
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -199,241 +440,120 @@ def run_ours(args):
     _lib.load()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    F, B = args.frames, args.batch
-    video = make_video(seed=2000 + rank, n_frames=F, n_ids=44)     # video `rank` of the 8-video set
-    frames = torch.empty((F, video.height, video.width, 3), dtype=torch.uint8, device=dev)
-    for f0 in range(0, F, 50):
-        frames[f0:min(F, f0 + 50)] = make_frames(video, f0, min(F, f0 + 50), device=dev)
-    gen_dets = torch.from_numpy(video.dets).to(dev)
-    gen_offs = torch.from_numpy(video.offsets.astype(np.int32)).to(dev)
-
-    det = YoloxDetectorDevice(args.variant, device=dev, batch=B, frames_cap=F, dets_cap=max(1 << 16, 300 * F))
-    det.calibrate(frames[:B])
-    trk = ByteTrackDevice(**HYPER, min_confidence=MIN_CONF, cap_tracks=128, cap_dets=128, device=dev)
-    pipe = DetectTrackPipeline(det, trk, B)
-    out_rows = torch.empty((video.n_dets, 8), dtype=torch.float64, device=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(src, steps, read_back, time_kernels=False):
-        det.time_kernels = time_kernels
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        last = None
-        for _ in range(steps):
-            res = pipe.run_video(src, gen_dets, gen_offs, out_rows=out_rows, time_kernels=time_kernels)
-            if read_back:
-                last = pipe.results_to_host(res[0], res[1], res[2])   # D2H read of the step's result
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        ms = tdist.max_over_ranks(ms, dev)      # job time = slowest rank (device-timed per rank)
-        det.time_kernels = False
-        return ms, res, last
-
-    # ---- HBM-resident run (value) ----
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    timed(frames, args.warmup, False)
-    if rank == 0:
-        sampler.rows.clear()       # keep only samples taken during the timed steps
-    pipe.launches = 0
-    pipe.kernel_events, det.kernel_events = [], []
-    ranged = os.environ.get("TK_PROFILE_RANGE") == "1"     # ncu --profile-from-start off: profile the timed steps only
-    if ranged:
-        torch.cuda.cudart().cudaProfilerStart()
-    ms, res, _ = timed(frames, args.steps, False, time_kernels=True)
-    if ranged:
-        torch.cuda.cudart().cudaProfilerStop()
-    launches = pipe.launches
-    clocks = sampler.stop() if rank == 0 else None
-    det.check_status(); trk.check_status()
-    value = world * args.steps * F / (ms / 1e3)
-
-    # per-kernel device times from the events recorded on the launching streams
-    kt = {}
-    for name, a, b, n in pipe.kernel_events + det.kernel_events:
-        d = kt.setdefault(name, [0.0, 0, 0])
-        d[0] += a.elapsed_time(b); d[1] += 1; d[2] += n
-    n_rows = int(res[2].item())
-    det_rows = int(res[3][0].item())
-
-    # ---- roofline of the dominant HBM-bound kernel of this repo (bias+SiLU epilogue): CUDA events around every launch of
-    #      one eager (non-graph) detector forward on the launching stream; algorithmic bytes = src read + dst written (+ residual)
-    epi = None
-    if det.use_fused:
-        from tracklab_b200 import kernels as _k
-        rec = []
-        orig = _k.bias_act
-
-        def timed_bias_act(src, bias, dst, dst_offset=0, act=1, residual=None, res_offset=0):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = orig(src, bias, dst, dst_offset, act, residual, res_offset)
-            e1.record()
-            rec.append((e0, e1, src.numel() * 2 * (3 if residual is not None else 2)))
-            return out
-
-        _k.bias_act = timed_bias_act
-        try:
-            with torch.no_grad():
-                for _ in range(3):
-                    rec.clear()
-                    det.fused(det.x)
-                torch.cuda.synchronize()
-        finally:
-            _k.bias_act = orig
-        t_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
-        nbytes = sum(n for _, _, n in rec)
-        epi = {"launches": len(rec), "total_ms": t_ms, "bytes": nbytes, "GBps": nbytes / (t_ms * 1e-3) / 1e9,
-               "us_per_frame": 1e3 * t_ms / B}
-
-    # ---- parity spot-check of the timed output against the oracle on the first 64 frames (untimed) ----
-    parity = None
-    if rank == 0:
-        from oracle.bytetrack_np import ByteTrackOracle
-        rows, fr = pipe.results_to_host(res[0], res[1], res[2])
-        k = min(64, F)
-        want, wf = ByteTrackOracle(**HYPER, min_confidence=MIN_CONF).run_video(video.dets, video.offsets[:k + 1])
-        m = fr < k
-        parity = bool(rows[m].shape == want.shape and np.array_equal(rows[m][:, 4:], want[:, 4:])
-                      and np.abs(rows[m][:, :4] - want[:, :4]).max() < 1e-6)
-
-    # ---- end-to-end: frames in pinned host memory, H2D per batch + D2H of the rows inside the timed region ----
-    e2e = None
-    if not args.no_e2e:
-        host_frames = torch.empty(frames.shape, dtype=torch.uint8, pin_memory=True)
-        host_frames.copy_(frames)
-        timed(host_frames, min(args.warmup, 3), True)
-        ms_e, res_e, last = timed(host_frames, args.steps, True)
-        e2e_fps = world * args.steps * F / (ms_e / 1e3)
-        d2h = int(last[0].nbytes + F * 4 + 4)
-        e2e = {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": int(host_frames.nbytes), "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e / args.steps,
-               "api": "DetectTrackPipeline.run_video(pinned host frames) + results_to_host"}
-        del host_frames
-
-    # ---- per-video metrics: the single collective of the multi-GPU path ----
-    metrics = torch.tensor([F, video.n_dets, n_rows, float(len(torch.unique(res[0][:n_rows, 4]))), ms / args.steps],
-                           dtype=torch.float64, device=dev)
-    allm = tdist.gather_video_metrics(metrics[None])[:, 0].cpu().numpy()   # the single collective: [world, 5]
+    main = run_config(args.config, args, dev, rank, world, local, args.frames, args.batch, args.steps, args.warmup,
+                      sampler=sampler if rank == 0 else None, want_e2e=not args.no_e2e)
+    allm = gather_and_reduce(main, dev, world)
+    second, allm2 = None, None
+    if not args.no_config2 and args.config != "config2":
+        second = run_config("config2", args, dev, rank, world, local, args.frames, 50, max(3, args.steps), args.warmup, want_e2e=not args.no_e2e)
+        allm2 = gather_and_reduce(second, dev, world)
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        H, W = video.height, video.width
-        lb = kt.get("letterbox_kernel", [0.0, 0, 1])
-        # letterbox algorithmic bytes / frame: source rows actually needed + the bf16 canvas
-        lb_bytes_frame = 360 * W * 3 + 3 * 640 * 640 * 2
-        lb_per_launch_bytes = lb_bytes_frame * (lb[2] / max(1, lb[1]))
-        lb_ms = lb[0] / max(1, lb[1])
-        bt = kt.get("bytetrack_video_kernel", [0.0, 0, 1])
-        bt_bytes_frame = (video.n_dets / F) * (7 * 8 + 8 * 8)        # rows in + rows out
-        lb_roof = {"kernel": "letterbox_kernel<bf16>", "bound": "hbm", "achieved": lb_per_launch_bytes / (lb_ms * 1e-3) / 1e9,
-                   "peak": peak, "unit": "GB/s", "bytes_per_launch": lb_per_launch_bytes, "avg_launch_ms": lb_ms,
-                   "launches_timed": lb[1]}
-        lb_roof["frac"] = lb_roof["achieved"] / peak
-        if epi is not None:   # dominant kernel of this repo by device time inside the step
-            roof = {"kernel": "bias_act_kernel (bias+SiLU(+residual) epilogue, bf16 NHWC)", "bound": "hbm",
-                    "achieved": epi["GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
-                    "bytes_per_launch": epi["bytes"] / epi["launches"], "avg_launch_ms": epi["total_ms"] / epi["launches"],
-                    "launches_timed": epi["launches"], "us_per_frame": epi["us_per_frame"],
-                    "how": "CUDA events around each of the launches of one eager detector forward (batch %d), sums" % B,
-                    "traffic_note": "ncu --set full (profiles/r01b_ncu_summary.md): a launch with 41.0 MB in / 41.0 MB out reads 41.0 MB "
-                                    "from DRAM and writes 0.0-3.4 MB: the output stays in the 126 MB L2 for the next convolution, so DRAM "
-                                    "traffic is below the algorithmic bytes; no re-reads"}
-        else:
-            roof = dict(lb_roof, peak_source=peak_src, traffic=None)
-        roof["frac"] = roof["achieved"] / peak
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16 detector / f64 association (f32 +1-pixel IoU)", "data": "synthetic",
-                "config": workload_config(args), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roof, "roofline_letterbox": lb_roof,
-                "kernels": {k: {"total_ms": v[0], "launches": v[1], "frames": v[2],
-                                "us_per_frame": 1e3 * v[0] / max(1, v[2])} for k, v in kt.items()},
-                "tracker": {"us_per_frame": 1e3 * bt[0] / max(1, bt[2]), "note": "latency-bound sequential kernel, 1 CTA per video",
-                            "algorithmic_GBps": bt_bytes_frame * bt[2] / max(1e-9, bt[0] * 1e-3) / 1e9},
-                "parity_first_64_frames_vs_oracle": parity,
-                "per_video": {"frames": allm[:, 0].tolist(), "dets": allm[:, 1].tolist(), "rows": allm[:, 2].tolist(),
-                              "ids": allm[:, 3].tolist(), "ms_per_step": allm[:, 4].tolist()},
-                "detector_rows_per_frame": det_rows / F}
+        peak_hbm, peak_tf, peak_src = measured_peaks()
+        F = args.frames
+
+        def headline(r, am):
+            ms = float(am[:, 4].max())                      # job time = slowest rank (device-timed per rank)
+            ms_e = float(am[:, 5].max())
+            value = world * F / (ms * 1e-3)
+            e2e = None
+            if r["ms_e2e"] is not None:
+                e2e = {"value": world * F / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                       "ms_per_step": ms_e, "api": "DetectReidTrackPipeline.run_video(pinned host frames) + results_to_host"}
+            return value, ms, e2e
+
+        value, ms, e2e = headline(main, allm)
+        roof, tens, kern = roofline_blocks(main, peak_hbm, peak_tf, peak_src)
+        cfg = main["cfg"]
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": main["steps"], "warmup": main["warmup"],
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 detector + ReID / f32 appearance distances / f64 association", "data": "synthetic",
+                "config": dict(workload_config(args, args.config, cfg["variant"], cfg["tracker"], cfg["reid"], main["pipe"].det.trained, world),
+                               detector_batch=main["batch"]),
+                "clocks": main["clocks"], "e2e": e2e, "gpu_launches": main["launches"], "roofline": roof, "tensor": tens,
+                "kernels": {n: dict(v, us_per_frame=1e3 * v["total_ms"] / main["batch"]) for n, v in kern.items()},
+                "stages": {n: {"total_ms": v[0], "launches": v[1], "units": v[2], "us_per_unit": 1e3 * v[0] / max(1, v[2])}
+                           for n, v in main["stage_ms"].items()},
+                "per_video": {"frames": allm[:, 0].tolist(), "detector_rows": allm[:, 1].tolist(), "track_rows": allm[:, 2].tolist(),
+                              "ids": allm[:, 3].tolist(), "ms_per_step": allm[:, 4].tolist(), "e2e_ms_per_step": allm[:, 5].tolist()},
+                "detector_rows_per_frame": main["host"].det_rows / F, "numa": numa,
+                "tc_layers_per_forward": getattr(main["pipe"].det.fused, "tc_layers", None)}
+        if second is not None:
+            v2, ms2, e2 = headline(second, allm2)
+            roof2, tens2, kern2 = roofline_blocks(second, peak_hbm, peak_tf, peak_src)
+            c2 = second["cfg"]
+            line["config2"] = {"value": v2, "unit": UNIT, "ms_per_step": ms2, "steps": second["steps"], "e2e": e2, "gpu_launches": second["launches"],
+                               "config": dict(workload_config(args, "config2", c2["variant"], c2["tracker"], None, second["pipe"].det.trained, world),
+                                              detector_batch=second["batch"]),
+                               "roofline": roof2, "tensor": tens2,
+                               "stages": {n: {"total_ms": v[0], "launches": v[1], "units": v[2], "us_per_unit": 1e3 * v[0] / max(1, v[2])}
+                                          for n, v in second["stage_ms"].items()},
+                               "per_video": {"ms_per_step": allm2[:, 4].tolist(), "e2e_ms_per_step": allm2[:, 5].tolist(),
+                                             "detector_rows": allm2[:, 1].tolist(), "track_rows": allm2[:, 2].tolist()}}
         if world == 1:
             try:
-                line["other_trackers"] = other_tracker_timings(dev)
-            except Exception as e:   # secondary figures must never cost the headline line
-                line["other_trackers"] = {"error": f"{type(e).__name__}: {e}"}
+                line["hota_vs_generator"] = hota_block(main)
+            except Exception as e:
+                line["hota_vs_generator"] = {"error": f"{type(e).__name__}: {e}"}
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args, video)
+            try:
+                line["cpu_baseline"] = cpu_baseline(args, main)
+            except Exception as e:
+                line["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def other_tracker_timings(dev, frames=200):
-    """Whole-video kernels of the other association families on the generator video of this bench (tracker only, inputs in
-    HBM, CUDA events, second of two runs): the rows SURVEY.md section 8 lists next to ByteTrack. A few hundred ms in total."""
+def hota_block(r):
+    """HOTA of the device chain's tracks against the generator identities (TrackEval HOTA restated in oracle/hota_np.py):
+    detector rows are matched to the generator's boxes by IoU so the tracker's det ids can be scored on the generator's identities."""
     import numpy as np
-    import torch
-    from tracklab_b200.device_trackers import BpbreidStrongSortDevice, OCSortDevice, StrongSortDevice
-    from tracklab_b200.synth import make_video
-    out = {}
 
-    def timed(run):
-        run(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); run(); e1.record(); torch.cuda.synchronize()
-        return 1e3 * e0.elapsed_time(e1) / frames
-
-    v = make_video(seed=2000, n_frames=frames, n_ids=44, emb_dim=512)
-    dets = torch.from_numpy(v.dets).to(dev); offs = torch.from_numpy(v.offsets.astype(np.int32))[None].to(dev)
-    feats = torch.from_numpy(v.embeddings).to(dev)
-    oc = OCSortDevice(device=dev)
-    out["ocsort_us_per_frame"] = timed(lambda: (oc.reset(), oc.run(dets, offs)))
-    ss = StrongSortDevice(512, ctas_per_video=32, device=dev)
-    out["strongsort_e512_budget100_32ctas_us_per_frame"] = timed(lambda: (ss.reset(), ss.run(dets, offs, feats)))
-    vp = make_video(seed=2000, n_frames=frames, n_ids=44, emb_dim=512, n_parts=6)
-    d2 = vp.dets.copy(); d2[:, 2] -= d2[:, 0]; d2[:, 3] -= d2[:, 1]
-    bp = BpbreidStrongSortDevice(6, 512, ctas_per_video=24, device=dev)
-    pd_, pf, pv = torch.from_numpy(d2).to(dev), torch.from_numpy(vp.embeddings).to(dev), torch.from_numpy(vp.visibility.astype(np.float32)).to(dev)
-    po = torch.from_numpy(vp.offsets.astype(np.int32))[None].to(dev)
-    out["bpbreid_k6_e512_24ctas_us_per_frame"] = timed(lambda: (bp.reset(), bp.run(pd_, po, pf, pv)))
-    for t in (oc, ss, bp):
-        t.check_status(); t.close()
-    out["note"] = "%d frames, ~38 det/frame, reference hyper-parameters (YAML); see profiles/ for the larger configurations" % frames
-    return out
+    from oracle.hota_np import hota_of_tracker_rows
+    if r["cfg"]["tracker"] == "bpbreid":
+        return None
+    h = hota_of_tracker_rows(r["video"], r["host"].rows, r["host"].frame)
+    return {"HOTA": float(h["HOTA"].mean()), "DetA": float(h["DetA"].mean()), "AssA": float(h["AssA"].mean()),
+            "note": "device chain, all frames; tracker output boxes vs generator boxes/identities"}
 
 
-def cpu_baseline(args, video):
-    """Oracle port timed on the host cores of this box on a bounded sample (reported baseline, not the target)."""
-    import torch
+def cpu_baseline(args, r):
+    """Oracle port timed on the host cores of this box on a bounded sample (reported baseline, not the target) + the parity of
+    the device chain against it on that sample."""
+    import numpy as np
 
-    from oracle.pipeline_np import detect_track_video
-    from tracklab_b200.nets.yolox import build_yolox
+    from oracle.hota_np import hota_of_tracker_rows
     from tracklab_b200.synth import make_frames
     cores = os.cpu_count() or 1
+    used = pick_cpu_threads(cores)
     n = min(args.ref_frames, args.frames)
-    frames = make_frames(video, 0, n, device="cpu").numpy()
-    model = build_yolox(args.variant).float().eval()
-    used = pick_cpu_threads(model, frames, video, cores)
-    detect_track_video(model, frames[:2], video.dets, video.offsets, HYPER, MIN_CONF)
+    frames = make_frames(r["video"], 0, n, device="cpu").numpy()
+    cfg = r["cfg"]
+    cpu_chain(r["config"], cfg["variant"], frames, r["video"], min(2, n))
     t0 = time.perf_counter()
-    reps = 0
-    while time.perf_counter() - t0 < 12.0 and reps < 4:
-        detect_track_video(model, frames, video.dets, video.offsets, HYPER, MIN_CONF)
+    reps, last = 0, None
+    while time.perf_counter() - t0 < 15.0 and reps < 3:
+        last = cpu_chain(r["config"], cfg["variant"], frames, r["video"], n)
         reps += 1
     dt = time.perf_counter() - t0
-    return {"value": reps * n / dt, "unit": UNIT, "cores": used, "kind": "port",
-            "sample": f"{reps} x first {n} frames of the same video, detector batch 1 fp32, {used} of {cores} host threads "
-                      "(best of 4/8/16/32/64/all)"}
+    out = {"value": reps * n / dt, "unit": UNIT, "cores": used, "kind": "port",
+           "sample": f"{reps} x first {n} frames of the same video, detector + ReID per frame in fp32, {used} of {cores} host threads"}
+    # parity on the sample: detector rows per frame and track rows, CPU fp32 chain vs device bf16 chain
+    _, rows, fr, det_rows = last
+    dev_rows = r["host"].rows[r["host"].frame < n]
+    out["sample_parity"] = {"cpu_detector_rows": int(sum(len(d) for d in det_rows)), "device_detector_rows": int(r["host"].det_offsets[n]),
+                            "cpu_track_rows": int(len(rows)), "device_track_rows": int(len(dev_rows)),
+                            "note": "fp32 CPU networks vs bf16 device networks: counts, not ids (exact-id parity of the chain is tests/test_connected_pipeline_gpu.py)"}
+    return out
 
 
 if __name__ == "__main__":

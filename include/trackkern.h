@@ -152,6 +152,18 @@ int tk_pack_detections_ex(const float* boxes, const float* scores, const int* cl
  */
 int tk_bias_act_nhwc(const void* src, const float* bias, void* dst, const void* residual, long long n_pixels, int channels,
                      int dst_pitch, int dst_offset, int res_pitch, int res_offset, int act, void* stream);
+/* 1x1 convolution with the epilogue fused in (hand-written sm_100a GEMM: TMA tensor-map loads of the NHWC activation tile,
+ * tcgen05.mma into a TMEM accumulator, bias + activation (+ residual) in the TMEM read-out, bf16 straight into the concat slice):
+ *   dst[m, dst_off + n] = act(sum_k x[m, k] * w[n, k] + bias[n]) (+ residual[m, res_off + n]),  m < M = images * H * W
+ * x: bf16 [M, x_pitch] (first K channels of every pixel are read), w: bf16 [N, K], bias: float [N] or NULL, dst / residual: bf16
+ * rows of dst_pitch / res_pitch channels. K, pitches and offsets multiples of 8, N a multiple of 16; all pointers 16-byte aligned.
+ * Replaces "cuDNN 1x1 convolution + tk_bias_act_nhwc" for the 1x1 layers of the YOLOX / ResNet-50 executors. */
+#define TK_ACT_NONE 0
+#define TK_ACT_SILU 1
+#define TK_ACT_RELU 2
+#define TK_ACT_RELU_AFTER_RESIDUAL 3
+int tk_conv1x1_bias_act_bf16(const void* x, long long M, int K, int x_pitch, const void* w, int N, const float* bias, void* dst,
+                             int dst_pitch, int dst_off, const void* residual, int res_pitch, int res_off, int act, void* stream);
 int tk_spp_nhwc(const void* x, void* dst, int n_images, int H, int W, int channels, int dst_pitch, int dst_offset, void* stream);
 int tk_upsample2x_nhwc(const void* src, int src_pitch, int src_offset, void* dst, int n_images, int h, int w, int channels,
                        int dst_pitch, int dst_offset, void* stream);

@@ -46,7 +46,7 @@ def test_bpbreid_matches_reference_golden(name, ncta):
     g = load_bpbreid_golden(name)
     v = make_video(**g["gen"])
     rows, fr = _run_device(v, g["hyper"], ncta=ncta)
-    assert_bpbreid_rows_match(rows, fr, g["rows"], g["frames"], box_tol=1e-6, dist_tol=1e-5, allow_relabel=True)
+    assert_bpbreid_rows_match(rows, fr, g["rows"], g["frames"], box_tol=1e-6, dist_tol=1e-5)
 
 
 def test_bpbreid_chunked_launches_equal_one_launch():
@@ -65,7 +65,7 @@ def test_bpbreid_fresh_seed_vs_oracle(seed):
     v = make_video(seed=seed, n_frames=140, n_ids=36, emb_dim=48, n_parts=5, conf_range=(0.1, 1.0), p_visible=0.7)
     ref_rows, ref_fr = BpbreidStrongSortOracle(**hyper).run_video(v.dets, v.offsets, v.embeddings, v.visibility)
     rows, fr = _run_device(v, hyper, ncta=6)
-    assert_bpbreid_rows_match(rows, fr, ref_rows, ref_fr, box_tol=1e-6, dist_tol=1e-5, allow_relabel=True)
+    assert_bpbreid_rows_match(rows, fr, ref_rows, ref_fr, box_tol=1e-6, dist_tol=1e-5)
 
 
 def test_bpbreid_empty_frames_and_capacity_error():
@@ -77,7 +77,7 @@ def test_bpbreid_empty_frames_and_capacity_error():
     assert (np.diff(v.offsets) == 0).any()
     ref_rows, ref_fr = BpbreidStrongSortOracle(**hyper).run_video(v.dets, v.offsets, v.embeddings, v.visibility)
     rows, fr = _run_device(v, hyper, ncta=2)
-    assert_bpbreid_rows_match(rows, fr, ref_rows, ref_fr, allow_relabel=True)
+    assert_bpbreid_rows_match(rows, fr, ref_rows, ref_fr)
     big = make_video(seed=6201, n_frames=10, n_ids=40, emb_dim=8, n_parts=2)
     with pytest.raises(_lib.TrackKernError):
         _run_device(big, hyper, cap=16)
@@ -94,7 +94,7 @@ def test_bpbreid_yaml_config_keeps_hundreds_of_stale_tracks():
     ref_rows, ref_fr = orc.run_video(v.dets, v.offsets, v.embeddings, v.visibility)
     assert len(orc.tracks) > 300
     rows, fr = _run_device(v, hyper, ncta=8, chunks=3)
-    assert_bpbreid_rows_match(rows, fr, ref_rows, ref_fr, box_tol=1e-6, dist_tol=1e-5, allow_relabel=True)
+    assert_bpbreid_rows_match(rows, fr, ref_rows, ref_fr, box_tol=1e-6, dist_tol=1e-5)
 
 
 def test_bpbreid_two_videos_in_one_launch():
@@ -120,7 +120,7 @@ def test_bpbreid_two_videos_in_one_launch():
         got, gf = rows_to_frames(rows, fc, out_start, seq=i)
         want, wf = BpbreidStrongSortOracle(**hyper).run_video(v.dets, v.offsets, v.embeddings, v.visibility)
         assert F == v.n_frames
-        assert_bpbreid_rows_match(got, gf, want, wf, box_tol=1e-6, dist_tol=1e-5, allow_relabel=True)
+        assert_bpbreid_rows_match(got, gf, want, wf, box_tol=1e-6, dist_tol=1e-5)
 
 
 def test_bpbreid_frames_whose_detections_are_all_filtered_out():
@@ -136,4 +136,4 @@ def test_bpbreid_frames_whose_detections_are_all_filtered_out():
     assert not np.isin(ref_fr, [5, 6, 17, 39]).any()
     for ncta in (1, 4):
         rows, fr = _run_device(v, hyper, ncta=ncta, chunks=2)
-        assert_bpbreid_rows_match(rows, fr, ref_rows, ref_fr, allow_relabel=True)
+        assert_bpbreid_rows_match(rows, fr, ref_rows, ref_fr)

@@ -26,9 +26,9 @@ def test_strongsort_matches_reference_golden(name, ncta):
     g = load_golden(name)
     video = make_video(**g["gen"])
     rows, frames = _run_device(video, g["hyper"], g["min_conf"], ncta)
-    # boxes are int()-truncated: an ulp-level difference in the filter state can move a value across an integer
-    # boundary, so boxes get a 1-pixel tolerance; ids are exact up to the solver-tie relabelling of tests/util.py
-    assert_rows_match(rows, frames, g["rows"], g["frames"], box_tol=1.0, allow_relabel=True)
+    # strict: track ids, detection ids and the int()-truncated boxes are bit-equal to the UNMODIFIED plugin's (the device solver
+    # is scipy's algorithm including its tie-breaking, csrc/lsap_scipy.cuh, and unmatched detections keep the reference's order)
+    assert_rows_match(rows, frames, g["rows"], g["frames"], box_tol=0.0)
 
 
 def test_strongsort_matches_oracle_fresh_seed():
@@ -39,17 +39,20 @@ def test_strongsort_matches_oracle_fresh_seed():
     ref_rows, ref_frames = StrongSortOracle(**hyper, min_confidence=0.4, image_size=(video.width, video.height)).run_video(
         video.dets, video.offsets, video.embeddings)
     rows, frames = _run_device(video, hyper, 0.4)
-    assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1.0, allow_relabel=True)
+    assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=0.0)
 
 
+@pytest.mark.parametrize("golden", ["strongsort_e2e_s5000", "strongsort_e2e_s5001"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_strongsort_end_to_end_with_reid_matches_reference_plugin(precision):
+def test_strongsort_end_to_end_with_reid_matches_reference_plugin(precision, golden):
     """frames -> crop kernel -> ResNet-50 -> StrongSORT kernel vs the UNMODIFIED plugin incl. its in-tracker ReID on the
-    same synthetic frames (tests/golden/strongsort_e2e_s5000.npz, make_golden.py: run_strongsort_end_to_end)."""
+    same synthetic frames (tests/golden/strongsort_e2e_s500{0,1}.npz, make_golden.py: run_strongsort_end_to_end; s5001 = 200
+    frames / 44 identities / 8115 rows). Ids and boxes bit-equal for the fp32 AND the bf16 backbone; the cosine distances of the
+    two differ by < 1e-4 (printed), inside north_star's tolerance, which is why bf16 is the default of the ReID stage."""
     from tracklab_b200.device_trackers import StrongSortDevice, rows_to_frames
     from tracklab_b200.reid import ReidStageDevice
     from tracklab_b200.synth import make_frames
-    g = load_golden("strongsort_e2e_s5000")
+    g = load_golden(golden)
     video = make_video(**g["gen"])
     frames = make_frames(video, 0, video.n_frames, device="cuda")
     dets = torch.from_numpy(video.dets).cuda()
@@ -60,4 +63,4 @@ def test_strongsort_end_to_end_with_reid_matches_reference_plugin(precision):
     rows, fc, cnt = trk.run(dets, offs, feats)
     trk.check_status()
     got, gf = rows_to_frames(rows, fc, torch.zeros(1, dtype=torch.int32))
-    assert_rows_match(got, gf, g["rows"], g["frames"], box_tol=1.0, allow_relabel=True)
+    assert_rows_match(got, gf, g["rows"], g["frames"], box_tol=0.0)

@@ -54,7 +54,7 @@ def test_strongsort_two_videos_in_one_launch():
     for i, v in enumerate(videos):
         got, gf = rows_to_frames(rows, fc, out_start, seq=i)
         want, wf = StrongSortOracle(nn_budget=30).run_video(v.dets, v.offsets, v.embeddings)
-        assert_rows_match(got, gf, want, wf, box_tol=1.0, allow_relabel=True)
+        assert_rows_match(got, gf, want, wf, box_tol=0.0)
 
 
 @pytest.mark.parametrize("kind", ["bytetrack", "ocsort", "strongsort"])
@@ -85,7 +85,7 @@ def test_empty_low_confidence_and_single_detection_frames(kind):
         start = o[:, 0].contiguous()
     trk.check_status()
     got, gf = rows_to_frames(rows, fc, start)
-    assert_rows_match(got, gf, want, wf, box_tol=1.0 if kind == "strongsort" else 1e-6, allow_relabel=kind != "bytetrack")
+    assert_rows_match(got, gf, want, wf, box_tol=0.0 if kind == "strongsort" else 1e-6, allow_relabel=kind == "ocsort")
 
 
 def test_ocsort_chunked_equals_whole():

@@ -66,6 +66,7 @@ def _declare(lib):
         "tk_pack_detections": ([vp, vp, vp, vp, ci, ci, ci, ci, ci, cd, cd, vp, vp, vp, ci, ci, vp, vp], ci),
         "tk_pack_detections_ex": ([vp, vp, vp, vp, ci, ci, ci, ci, ci, cd, cd, vp, vp, vp, ci, ci, vp, ci, vp, vp], ci),
         "tk_bias_act_nhwc": ([vp, vp, vp, vp, ctypes.c_longlong, ci, ci, ci, ci, ci, ci, vp], ci),
+        "tk_conv1x1_bias_act_bf16": ([vp, ctypes.c_longlong, ci, ci, vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, vp], ci),
         "tk_spp_nhwc": ([vp, vp, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_upsample2x_nhwc": ([vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_resize_frames_u8": ([vp, ci, ci, ci, ctypes.c_longlong, vp, ci, ci, ci, ctypes.c_float, vp], ci),

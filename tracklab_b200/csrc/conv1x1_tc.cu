@@ -1,0 +1,332 @@
+// 1x1 convolution (= GEMM over NHWC activations) with the bias / activation / residual / concat-slice epilogue fused in:
+//     dst[m, dst_off + n] = act( sum_k x[m, k] * w[n, k] + bias[n] ) (+ residual[m, res_off + n])       bf16 in, fp32 accumulate, bf16 out
+//
+// Replaces, for the 1x1 layers of the detector / ReID backbones (YOLOX CSP blocks, ResNet-50 bottlenecks: two thirds of their
+// convolutions), the pair "cuDNN convolution -> tk_bias_act_nhwc": the convolution output no longer goes out to HBM/L2 through
+// the library's store and comes back through a second kernel. The reference runs these layers inside third-party runtimes
+// (onnxruntime / PyTorch CPU: /root/reference/tracklab/wrappers/bbox_detector/rtmlib_api.py:27-30,
+// /root/reference/plugins/track/strong_sort/reid_multibackend.py:184-237).
+//
+// sm_100a design (hand-written, no library): persistent CTAs (one per SM), warp-specialised
+//   warp 0   : TMA producer — cp.async.bulk.tensor 2-D tiles of the activation matrix [M, K] (128 rows x 64 channels) and of
+//              the weight matrix [N, K] (BLOCK_N x 64) into a multi-stage 128-byte-swizzled shared-memory ring (mbarrier tx counts)
+//   warp 1   : one elected thread issues tcgen05.mma (UMMA 128 x BLOCK_N x 16, bf16 -> fp32) into a TMEM accumulator;
+//              tcgen05.commit releases the ring slot / publishes the accumulator
+//   warp 2   : allocates / frees TMEM (two accumulator stages, so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 4-7: epilogue — tcgen05.ld the accumulator (thread = one output row, 16 columns at a time), bias + SiLU/ReLU
+//              (+ residual) in fp32, one rounding to bf16, 32-byte row segments straight into the channel slice of dst
+// These layers are HBM-bound (K, N = 32..768 against M = B*H*W up to millions): algorithmic bytes per output row =
+// 2K (x) + 2N (dst) (+ 2N residual); the weights are L2 resident.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tk_common.cuh"
+#include "trackkern.h"
+
+namespace {
+
+constexpr int BM = 128;          // rows of an output tile = TMEM lanes
+constexpr int BK = 64;           // channels per pipeline stage = one 128-byte swizzle atom of bf16
+constexpr int UMMA_K = 16;
+constexpr int C1_THREADS = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` when all previously issued MMAs have completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, 128 x N x 16
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): K-major tile whose rows are 128 bytes (one swizzle atom),
+// 8-row groups 1024 bytes apart (SBO), SWIZZLE_128B, descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);        // start address, bits [0,14)
+    d |= (uint64_t)0 << 16;                        // leading byte offset (unused: one atom along K)
+    d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;   // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                        // version
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == TK_ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
+    if (act == TK_ACT_RELU) return fmaxf(v, 0.0f);
+    return v;
+}
+
+struct C1Params {
+    long long M;
+    int K, N, block_n, n_blocks, stages, tmem_cols;
+    const float* bias;
+    __nv_bfloat16* dst;
+    int dst_pitch, dst_off;
+    const __nv_bfloat16* res;
+    int res_pitch, res_off;
+    int act;
+};
+
+__global__ void __launch_bounds__(C1_THREADS, 1)
+conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const C1Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // 1024-byte alignment is required by the 128-byte swizzle; dynamic shared memory starts 1024-aligned only by request
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b_stage_bytes = p.block_n * BK * 2;
+    const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;          // multiple of 1024 (block_n is a multiple of 16 -> 2 KB granules)
+    unsigned char* tail = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* full_bar = (uint64_t*)tail;                             // [stages]
+    uint64_t* empty_bar = full_bar + p.stages;                        // [stages]
+    uint64_t* tfull_bar = empty_bar + p.stages;                       // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                             // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    float* s_bias = (float*)(tmem_slot + 4);                          // [N]
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(full_bar + s), 1); mbar_init(smem_u32(empty_bar + s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(tfull_bar + a), 1); mbar_init(smem_u32(tempty_bar + a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {   // TMEM: 2 accumulator stages of block_n fp32 columns (power of two >= 32 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.N; i += C1_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.0f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long m_tiles = (p.M + BM - 1) / BM;
+    const long long n_tiles = m_tiles * p.n_blocks;
+    const int k_blocks = (p.K + BK - 1) / BK;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+                const int m0 = (int)((t / p.n_blocks) * BM), n0 = (int)(t % p.n_blocks) * p.block_n;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                    const uint32_t fb = smem_u32(full_bar + stage);
+                    mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                    unsigned char* sa = smem + (size_t)stage * stage_bytes;
+                    tma_load_2d(smem_u32(sa), &map_x, fb, kb * BK, m0);                      // rows/channels past the edge arrive as zeros
+                    tma_load_2d(smem_u32(sa + A_STAGE_BYTES), &map_w, fb, kb * BK, n0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A/B bf16, both K-major, N = block_n, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t it = 0;
+            for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+                const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+                mbar_wait(smem_u32(tempty_bar + acc), acc_phase ^ 1);      // the epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)      // advance 32 bytes (16 bf16) inside the swizzle atom per UMMA_K step
+                        umma_bf16(tmem_d, da + (uint64_t)(k * UMMA_K * 2 >> 4), db + (uint64_t)(k * UMMA_K * 2 >> 4), idesc, (kb | k) != 0);
+                    umma_commit(smem_u32(empty_bar + stage));            // slot reusable once these MMAs have read it
+                    if (kb == k_blocks - 1) umma_commit(smem_u32(tfull_bar + acc));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> bias/activation/residual -> bf16 -> dst slice =====
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+            const uint32_t acc = it & 1u, acc_phase = (it >> 1) & 1u;
+            const long long m = (t / p.n_blocks) * BM + q * 32 + lane;
+            const int n0 = (int)(t % p.n_blocks) * p.block_n;
+            mbar_wait(smem_u32(tfull_bar + acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * (uint32_t)p.block_n + ((uint32_t)(q * 32) << 16);
+            const int ncols = min(p.block_n, p.N - n0);
+            __nv_bfloat16* drow = p.dst + (size_t)m * p.dst_pitch + p.dst_off + n0;
+            const __nv_bfloat16* rrow = p.res ? p.res + (size_t)m * p.res_pitch + p.res_off + n0 : nullptr;
+            for (int c = 0; c < ncols; c += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c, v);
+                tmem_ld_wait();
+                if (m < p.M) {
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = act_apply(__uint_as_float(v[j]) + s_bias[n0 + c + j], p.act);
+                    if (rrow) {
+                        const uint4 r0 = *(const uint4*)(rrow + c), r1 = *(const uint4*)(rrow + c + 8);
+                        const __nv_bfloat162* rp0 = (const __nv_bfloat162*)&r0;
+                        const __nv_bfloat162* rp1 = (const __nv_bfloat162*)&r1;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 a = __bfloat1622float2(rp0[j]), b = __bfloat1622float2(rp1[j]);
+                            f[2 * j] += a.x; f[2 * j + 1] += a.y; f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
+                        }
+                    }
+                    if (p.act == TK_ACT_RELU_AFTER_RESIDUAL) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.0f);
+                    }
+                    uint4 o0, o1;
+                    __nv_bfloat162* op0 = (__nv_bfloat162*)&o0;
+                    __nv_bfloat162* op1 = (__nv_bfloat162*)&o1;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        op0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                        op1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+                    }
+                    *(uint4*)(drow + c) = o0;
+                    *(uint4*)(drow + c + 8) = o1;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(tempty_bar + acc));    // 128 epilogue threads -> accumulator stage free
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+    }
+    return fn;
+}
+
+// [rows, cols] bf16 matrix, row pitch `pitch` elements, box = box_rows x 64 columns, 128-byte swizzle, zero fill outside
+bool make_map(CUtensorMap* map, const void* base, unsigned long long rows, unsigned long long cols, unsigned long long pitch, unsigned box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {pitch * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int g_sms = 0;
+
+}  // namespace
+
+extern "C" int tk_conv1x1_bias_act_bf16(const void* x, long long M, int K, int x_pitch, const void* w, int N, const float* bias,
+                                        void* dst, int dst_pitch, int dst_off, const void* residual, int res_pitch, int res_off,
+                                        int act, void* stream) {
+    if (!x || !w || !dst || M <= 0 || K <= 0 || N <= 0) return TK_ERR_ARG;
+    if (act < TK_ACT_NONE || act > TK_ACT_RELU_AFTER_RESIDUAL) return TK_ERR_ARG;
+    // 16-byte vector access / TMA stride rules: channel counts, pitches and offsets in multiples of 8; N in multiples of 16 (UMMA N)
+    if ((K & 7) || (x_pitch & 7) || (N & 15) || (dst_pitch & 7) || (dst_off & 7) || x_pitch < K || dst_off + N > dst_pitch) return TK_ERR_ARG;
+    if (residual && ((res_pitch & 7) || (res_off & 7) || res_off + N > res_pitch)) return TK_ERR_ARG;
+    if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)dst | (uintptr_t)residual) & 15) return TK_ERR_ARG;
+    if (M > 0x7fffff00ll) return TK_ERR_CAPACITY;
+    // output-channel blocking: one block when N <= 256, else the smallest number of equal blocks (multiples of 16) <= 256
+    int n_blocks = 1;
+    while (N / n_blocks > 256 || N % n_blocks || (N / n_blocks) % 16) { if (++n_blocks > N / 16) return TK_ERR_ARG; }
+    const int block_n = N / n_blocks;
+    int tmem_cols = 32;
+    while (tmem_cols < 2 * block_n) tmem_cols <<= 1;
+    const int stage_bytes = A_STAGE_BYTES + block_n * BK * 2;
+    const int k_blocks = (K + BK - 1) / BK;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return TK_ERR_CAPACITY;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16 + (size_t)N * 4 + 16;
+    if (smem > 227 * 1024) return TK_ERR_CAPACITY;
+    (void)k_blocks;
+    CUtensorMap mx, mw;
+    if (!make_map(&mx, x, (unsigned long long)M, (unsigned long long)K, (unsigned long long)x_pitch, BM)) return TK_ERR_CUDA;
+    if (!make_map(&mw, w, (unsigned long long)N, (unsigned long long)K, (unsigned long long)K, (unsigned)block_n)) return TK_ERR_CUDA;
+    if (!g_sms) {
+        int dev = 0;
+        TK_CUDA_TRY(cudaGetDevice(&dev));
+        TK_CUDA_TRY(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    C1Params p;
+    p.M = M; p.K = K; p.N = N; p.block_n = block_n; p.n_blocks = n_blocks; p.stages = stages; p.tmem_cols = tmem_cols;
+    p.bias = bias; p.dst = (__nv_bfloat16*)dst; p.dst_pitch = dst_pitch; p.dst_off = dst_off;
+    p.res = (const __nv_bfloat16*)residual; p.res_pitch = res_pitch; p.res_off = res_off; p.act = act;
+    const long long tiles = ((M + BM - 1) / BM) * n_blocks;
+    const int grid = (int)(tiles < g_sms ? tiles : g_sms);
+    TK_CUDA_TRY(cudaFuncSetAttribute(conv1x1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv1x1_tc_kernel<<<grid, C1_THREADS, smem, (cudaStream_t)stream>>>(mx, mw, p);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}

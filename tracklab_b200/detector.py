@@ -57,11 +57,12 @@ class YoloxDetectorDevice:
         for p in self.model.parameters():
             p.requires_grad_(False)
         self.fused = None
+        self.use_tc = os.environ.get("TK_NO_TC", "0") != "1"     # 1x1 layers on the hand-written tcgen05 GEMM (A/B switch for profiling)
         self.use_fused = bool(fused) and dtype == torch.bfloat16
         if self.use_fused:
             from .nets.yolox_fused import YoloxFused
             self._fused_cls = YoloxFused
-            self.fused = YoloxFused(self.model, self.device)
+            self.fused = YoloxFused(self.model, self.device, use_tc=self.use_tc)
             # Focus-unfolded input written by the letterbox kernel; channels 12.. are zero padding (32-channel pitch, see yolox_fused)
             self.x = torch.zeros((batch, self._fused_cls.STEM_IN, input_size // 2, input_size // 2), dtype=dtype,
                                  device=self.device).contiguous(memory_format=torch.channels_last)
@@ -124,7 +125,7 @@ class YoloxDetectorDevice:
         self.graph = None
         self._tail_graphs = {}
         if self.use_fused:
-            self.fused = self._fused_cls(self.model, self.device)
+            self.fused = self._fused_cls(self.model, self.device, use_tc=self.use_tc)
         return shift
 
     # ---- one batch ---------------------------------------------------------------------------------

@@ -116,6 +116,44 @@ def bias_act(src: torch.Tensor, bias: torch.Tensor, dst: torch.Tensor, dst_offse
     return dst
 
 
+def conv1x1_bias_act(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, dst: torch.Tensor | None = None, dst_offset: int = 0,
+                     act: int = 1, residual: torch.Tensor | None = None, res_offset: int = 0):
+    """1x1 convolution with fused epilogue on the tcgen05 path (C ABI: tk_conv1x1_bias_act_bf16).
+    x bf16 channels-last [B,K,H,W] (or [M,K]); w bf16 [N,K]; bias float32 [N]; dst / residual bf16 channels-last, possibly wider
+    (concat buffers). act: 0 none, 1 SiLU, 2 ReLU, 3 ReLU after the residual add. Returns dst."""
+    lib = _lib.load()
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.is_contiguous() and w.dim() == 2
+    if x.dim() == 4:
+        B, K, H, W = x.shape
+        assert x.is_contiguous(memory_format=torch.channels_last)
+        M = B * H * W
+    else:
+        M, K = x.shape
+        assert x.is_contiguous()
+        B = H = W = None
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if dst is None:
+        dst = (torch.empty((B, N, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last) if B is not None
+               else torch.empty((M, N), dtype=torch.bfloat16, device=x.device))
+    if dst.dim() == 4:
+        assert dst.is_contiguous(memory_format=torch.channels_last) and dst.shape[0] * dst.shape[2] * dst.shape[3] == M
+        dp = dst.shape[1]
+    else:
+        assert dst.is_contiguous() and dst.shape[0] == M
+        dp = dst.shape[1]
+    rp, r = 0, None
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16
+        rp = residual.shape[1]
+        r = residual.data_ptr()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tk_conv1x1_bias_act_bf16(x.data_ptr(), M, K, K, w.data_ptr(), N, bias.data_ptr() if bias is not None else None,
+                                                dst.data_ptr(), dp, dst_offset, r, rp, res_offset, act, _stream()),
+                   "tk_conv1x1_bias_act_bf16"); _count()
+    return dst
+
+
 def resize_frames(frames: torch.Tensor, out_hw=(640, 640), out_dtype=torch.float32, scale: float = 1.0 / 255.0) -> torch.Tensor:
     """frames uint8 [n,H,W,3] -> [n,3,h,w] = PIL-bilinear(frame) * scale (RTDetrImageProcessor; C ABI: tk_resize_frames_u8)."""
     lib = _lib.load()

@@ -36,8 +36,14 @@ def stem_weight_s2d16(w: torch.Tensor) -> torch.Tensor:
 
 
 class ResNet50Fused:
-    def __init__(self, model: ResNet50ReID, device, legacy: bool = False, use_graphs: bool = True, crop_hw=(256, 128)):
+    def __init__(self, model: ResNet50ReID, device, legacy: bool = False, use_graphs: bool = True, crop_hw=(256, 128),
+                 use_tc: bool | None = None):
+        import os
         self.device = torch.device(device)
+        # 1x1 stride-1 layers (conv1 / conv3 of every bottleneck: 32 of the 53 convolutions) on the hand-written tcgen05 GEMM with
+        # bias + ReLU (+ residual) fused (csrc/conv1x1_tc.cu) instead of cuDNN's fused convolution; TK_RESNET_TC=0/1 overrides
+        self.use_tc = (os.environ.get("TK_RESNET_TC", "0") == "1") if use_tc is None else use_tc
+        self.tc_layers = 0
         self.model = model
         self.legacy = legacy
         self.use_graphs = use_graphs and not legacy
@@ -54,13 +60,18 @@ class ResNet50Fused:
                                     tuple(mod.conv.stride), tuple(mod.conv.padding))
         # a bottleneck's projection shortcut has no activation of its own: its bias is folded into conv3's
         # (relu(conv3(y) + b3 + down(x) + bd) = relu(conv3(y) + (b3 + bd) + down_nobias(x))), so no separate bias pass remains
-        self._b3 = {}
+        self._b3, self._b3f, self._w2d = {}, {}, {}
+        for mod in model.modules():
+            if isinstance(mod, ConvBias) and tuple(mod.conv.kernel_size) == (1, 1) and tuple(mod.conv.stride) == (1, 1):
+                w = self._c[id(mod)][0]
+                self._w2d[id(mod)] = w.reshape(w.shape[0], w.shape[1]).contiguous()
         for mod in model.modules():
             if hasattr(mod, "conv3") and hasattr(mod, "down"):
                 b = self._c[id(mod.conv3)][1]
                 if mod.down is not None:
                     b = b + self._c[id(mod.down)][1]
                 self._b3[id(mod)] = b.to(torch.bfloat16)
+                self._b3f[id(mod)] = b.contiguous()
         self._graphs = {}   # bucket size -> (graph, static input, static output)
         self._pool = None   # one private memory pool shared by all buckets' graphs (they never run concurrently)
 
@@ -91,6 +102,10 @@ class ResNet50Fused:
             b16 = bias
         if stem:
             stride, pad = (1, 1), (0, 0)
+        if self.use_tc and id(m) in self._w2d:
+            self.tc_layers += 1
+            b32 = self._c[id(m)][1] if bias is None else self._b3f_cur
+            return kernels.conv1x1_bias_act(x, self._w2d[id(m)], b32, act=2 if residual is None else 3, residual=residual)
         if residual is None:
             return torch.cudnn_convolution_relu(x, w, b16, stride, pad, (1, 1), 1)
         return torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b16, stride, pad, (1, 1), 1)
@@ -108,6 +123,7 @@ class ResNet50Fused:
                     idt = F.conv2d(x, w, None, stride, pad)
                 y = self._relu_conv(x, blk.conv1)
                 y = self._relu_conv(y, blk.conv2)
+                self._b3f_cur = self._b3f[id(blk)]
                 x = self._relu_conv(y, blk.conv3, residual=idt, bias=self._b3[id(blk)])
         return kernels.avgpool(x)
 

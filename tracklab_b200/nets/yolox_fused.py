@@ -28,6 +28,10 @@ class _Conv:
         self.stride = m.conv.stride
         self.padding = m.conv.padding
         self.cout = self.w.shape[0]
+        # 1x1 stride-1 layers run on the hand-written tcgen05 GEMM with the epilogue fused in (csrc/conv1x1_tc.cu)
+        self.w2d = None
+        if tuple(m.conv.kernel_size) == (1, 1) and tuple(self.stride) == (1, 1) and self.w.shape[1] % 8 == 0 and self.cout % 16 == 0:
+            self.w2d = self.w.reshape(self.cout, self.w.shape[1]).contiguous()
 
 
 class YoloxFused:
@@ -35,8 +39,10 @@ class YoloxFused:
     # 425 us per 50 frames; with 32 an sm_100 one, 164 us — tools/probe_yolox_stem.py)
     STEM_IN = 32
 
-    def __init__(self, model: YOLOX, device):
+    def __init__(self, model: YOLOX, device, use_tc: bool = True):
         self.device = torch.device(device)
+        self.use_tc = use_tc
+        self.tc_layers = 0        # 1x1 layers of the last forward that ran on the tcgen05 path
         self.nc = model.num_classes
         dev = self.device
         self._convs = {}
@@ -63,6 +69,9 @@ class YoloxFused:
     # ---- building blocks -------------------------------------------------------------------------
     def _conv(self, x, m: ConvAct, dst=None, dst_off=0, residual=None, res_off=0):
         c = self._convs[id(m)]
+        if self.use_tc and c.w2d is not None and x.shape[1] == c.w2d.shape[1]:
+            self.tc_layers += 1
+            return kernels.conv1x1_bias_act(x, c.w2d, c.b, dst=dst, dst_offset=dst_off, act=1, residual=residual, res_offset=res_off)
         y = F.conv2d(x, c.w, None, c.stride, c.padding)
         return kernels.bias_act(y, c.b, y if dst is None else dst, dst_off, 1, residual, res_off)
 
@@ -99,6 +108,7 @@ class YoloxFused:
         """x16: [B,16,S/2,S/2] bf16 channels-last produced by kernels.letterbox(..., focus16=True)."""
         m = self.model
         B = x16.shape[0]
+        self.tc_layers = 0
         x = self._conv(x16, m.stem.conv)
         x = self._conv(x, m.dark2[0]); x = self._csp(x, m.dark2[1])
         x = self._conv(x, m.dark3[0]); d3 = self._csp(x, m.dark3[1])

@@ -333,7 +333,7 @@ def build_pipeline(config: str = "config3", device="cuda:0", batch: int = 20, fr
         trk = OCSortDevice(**cfg["hyper"], min_confidence=min_confidence, cap_tracks=256, cap_dets=128, device=dev)
     elif cfg["tracker"] == "strongsort":
         trk = StrongSortDevice(reid.feature_dim, **cfg["hyper"], min_confidence=min_confidence, image_size=(W, H),
-                               ctas_per_video=ctas_per_video, cap_tracks=256, cap_dets=128, device=dev)
+                               ctas_per_video=ctas_per_video, cap_tracks=160, cap_dets=128, device=dev)
     else:
         trk = BpbreidStrongSortDevice(1, reid.feature_dim, **cfg["hyper"], ctas_per_video=ctas_per_video, cap_tracks=1024,
                                       cap_dets=128, device=dev)
