@@ -140,26 +140,56 @@ def workload_config(args, config, variant, tracker, reid, trained, world):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_chain(config, variant, frames_np, video, n, threads=None):
-    """One pass of the CPU restatement over the first n frames; returns (seconds, tracker rows, frame index, detector rows)."""
+def cpu_chain(config, variant, frames_np, video, n, state={}):
+    """One pass of the CPU arm over the first n frames; returns (seconds, tracker rows, frame index, detector rows, kind).
+    Detector: the restated YOLOX in fp32 on the host threads (the reference's rtmlib + onnxruntime back-end is not installable
+    offline). ReID + association of configs[2]: the UNMODIFIED StrongSORT plugin (its own PIL crops, vendored ResNet-50, NumPy /
+    scipy association) when the reference is present (/root/reference, or oracle/_ref/ staged by build()), else the NumPy port."""
+    import numpy as np
     import torch
 
-    from oracle import pipeline_np
+    from oracle import pipeline_np, ref_env
     from tracklab_b200.detector import load_yolox_weights, synth_weights_path
     from tracklab_b200.nets.yolox import build_yolox
     from tracklab_b200.video_pipeline import CONFIGS
-    wp = synth_weights_path(variant)
-    det = (load_yolox_weights(variant, wp) if wp else build_yolox(variant, 1, 1234, prior_prob=0.01)).float().eval()
+    if "det" not in state:
+        wp = synth_weights_path(variant)
+        state["det"] = (load_yolox_weights(variant, wp) if wp else build_yolox(variant, 1, 1234, prior_prob=0.01)).float().eval()
+    det = state["det"]
     hyper = CONFIGS[config]["hyper"]
     if CONFIGS[config]["reid"] is None:
         t0 = time.perf_counter()
         rows, fr, det_rows = pipeline_np.detect_track_video(det, frames_np[:n], None, None, hyper, MIN_CONF)
-        return time.perf_counter() - t0, rows, fr, det_rows
+        return time.perf_counter() - t0, rows, fr, det_rows, "port"
+    if CONFIGS[config]["tracker"] == "strongsort" and ref_env.available():
+        from oracle.ref_models import reference_strongsort
+        ref_env.install()
+        t0 = time.perf_counter()
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):           # the plugin prints while loading weights; stdout carries the JSON line only
+            model = reference_strongsort(hyper)                # re-created per video like the wrapper's reset() (strong_sort_api.py:36-41)
+        out, fr, det_rows, next_id = [], [], [], 0
+        with torch.no_grad():                                  # strong_sort_api.py:59
+            for f in range(n):
+                rows = pipeline_np.detect_frame(det, frames_np[f], first_id=next_id)
+                next_id += len(rows)
+                det_rows.append(rows)
+                keep = rows[rows[:, 4] > MIN_CONF] if len(rows) else rows
+                if len(keep) == 0:
+                    continue
+                res = np.asarray(model.update(torch.from_numpy(keep.copy()), frames_np[f]))
+                if res.size:
+                    out.append(res[:, [0, 1, 2, 3, 4, 5, 6, 8]].astype(np.float64))
+                    fr.append(np.full(len(res), f, dtype=np.int32))
+        dt = time.perf_counter() - t0
+        rows = np.concatenate(out) if out else np.zeros((0, 8))
+        return dt, rows, (np.concatenate(fr) if fr else np.zeros((0,), np.int32)), det_rows, "reference"
     from tracklab_b200.nets.resnet_reid import build_resnet50_reid
-    reid = build_resnet50_reid(1234).float().eval()
+    if "reid" not in state:
+        state["reid"] = build_resnet50_reid(1234).float().eval()
     t0 = time.perf_counter()
-    rows, fr, det_rows, _ = pipeline_np.detect_reid_track_video(det, reid, frames_np[:n], hyper, MIN_CONF)
-    return time.perf_counter() - t0, rows, fr, det_rows
+    rows, fr, det_rows, _ = pipeline_np.detect_reid_track_video(det, state["reid"], frames_np[:n], hyper, MIN_CONF)
+    return time.perf_counter() - t0, rows, fr, det_rows, "port"
 
 
 def pick_cpu_threads(cores):
@@ -185,6 +215,11 @@ def pick_cpu_threads(cores):
     return best
 
 
+KIND_NOTE = {"reference": "ReID + association = the UNMODIFIED StrongSORT plugin (staged reference); detector = the restated YOLOX in fp32 "
+                          "(rtmlib/onnxruntime are not installable offline)",
+             "port": "NumPy/PyTorch-CPU restatement (oracle/): the reference is not present on this machine"}
+
+
 def run_reference(args):
     """CPU arm: bounded sample of the same workload per step, all host threads torch/BLAS will use."""
     import numpy as np
@@ -201,7 +236,8 @@ def run_reference(args):
     n = min(args.ref_frames, args.frames)
     frames = make_frames(video, 0, n, device="cpu").numpy()
     cpu_chain(args.config, cfg["variant"], frames, video, min(2, n))
-    times = [cpu_chain(args.config, cfg["variant"], frames, video, n)[0] for _ in range(max(1, min(args.steps, 3)))]
+    runs = [cpu_chain(args.config, cfg["variant"], frames, video, n) for _ in range(max(1, min(args.steps, 3)))]
+    times, kind = [r[0] for r in runs], runs[-1][4]
     total = sum(times)
     fps = len(times) * n / total
     from tracklab_b200.detector import synth_weights_path
@@ -211,7 +247,8 @@ def run_reference(args):
             "warmup": 1, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 detector + ReID / f64 association", "data": "synthetic",
             "config": workload_config(args, args.config, cfg["variant"], cfg["tracker"], cfg["reid"], synth_weights_path(cfg["variant"]) is not None, args.gpus),
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": used, "kind": kind, "sample": sample,
+                             "what": KIND_NOTE[kind]},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -545,10 +582,10 @@ def cpu_baseline(args, r):
         last = cpu_chain(r["config"], cfg["variant"], frames, r["video"], n)
         reps += 1
     dt = time.perf_counter() - t0
-    out = {"value": reps * n / dt, "unit": UNIT, "cores": used, "kind": "port",
+    out = {"value": reps * n / dt, "unit": UNIT, "cores": used, "kind": last[4], "what": KIND_NOTE[last[4]],
            "sample": f"{reps} x first {n} frames of the same video, detector + ReID per frame in fp32, {used} of {cores} host threads"}
     # parity on the sample: detector rows per frame and track rows, CPU fp32 chain vs device bf16 chain
-    _, rows, fr, det_rows = last
+    _, rows, fr, det_rows, _ = last
     dev_rows = r["host"].rows[r["host"].frame < n]
     out["sample_parity"] = {"cpu_detector_rows": int(sum(len(d) for d in det_rows)), "device_detector_rows": int(r["host"].det_offsets[n]),
                             "cpu_track_rows": int(len(rows)), "device_track_rows": int(len(dev_rows)),

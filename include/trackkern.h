@@ -292,7 +292,15 @@ typedef struct tk_bpbreid_params {
     int n_parts;
     int feature_dim;
     int ctas_per_video;         /* 0 = default */
+    int matching_strategy;      /* TK_BPBREID_STRONG_SORT_MATCHING (two stages, the YAML) or TK_BPBREID_BOT_SORT_MATCHING: one stage over all
+                                   tracks on (w_kfgd * pos + w_reid * app + w_st * st) / sum(w), sort/tracker.py:335-363,169-240 */
+    double gating_thres_factor; /* 1.0 */
+    double w_kfgd;              /* 1.0 (must be > 0 on device: the position gate prunes the pairs) */
+    double w_reid;              /* 1.0 */
+    double w_st;                /* 1.0 */
 } tk_bpbreid_params;
+#define TK_BPBREID_STRONG_SORT_MATCHING 0
+#define TK_BPBREID_BOT_SORT_MATCHING 1
 
 int tk_bpbreid_create(const tk_bpbreid_params* p, int n_seq, int cap_tracks, int cap_dets, void** handle);
 int tk_bpbreid_reset(void* handle, int keep_id_counter, void* stream);

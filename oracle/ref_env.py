@@ -13,8 +13,14 @@ import os
 import sys
 import types
 
-REF = "/root/reference"
 HERE = os.path.dirname(os.path.abspath(__file__))
+# the build container has the reference itself; the GPU box has the copy oracle/stage_ref.py staged (git-ignored oracle/_ref/)
+REF = "/root/reference" if os.path.isdir("/root/reference/tracklab") else os.path.join(HERE, "_ref")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF, "tracklab")) and os.path.isdir(os.path.join(REF, "plugins", "track"))
+
 STUBS = ("omegaconf", "hydra", "yt_dlp", "trackeval", "SoccerNet", "matplotlib", "distinctipy", "skimage", "yacs",
          "rtmlib", "accelerate", "torchreid", "huggingface_hub", "mim", "mmcv", "mmdet", "mmpose", "mmengine",
          "openpifpaf", "posetrack21", "posetrack21_mot", "poseval", "torchmetrics", "wandb", "rich", "sn_trackeval",
@@ -56,8 +62,8 @@ def install():
     global _installed
     if _installed:
         return
-    if not os.path.isdir(REF):
-        raise RuntimeError("/root/reference is not present: reference-backed goldens can only be generated in the build container")
+    if not available():
+        raise RuntimeError("neither /root/reference nor the staged copy oracle/_ref/ is present (run oracle/stage_ref.py in the build container)")
     sys.path[:0] = [os.path.join(HERE, "ref_shims"), os.path.join(REF, "plugins", "track"), REF]
     present = set()
     for name in STUBS:

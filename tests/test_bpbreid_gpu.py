@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import BPB_KEYS, assert_bpbreid_rows_match, load_bpbreid_golden
+from tests.util import BPB_KEYS, BPB_ORACLE_KEYS, assert_bpbreid_rows_match, load_bpbreid_golden
 from tracklab_b200.synth import make_video
 
 pytestmark = pytest.mark.gpu
@@ -20,7 +20,7 @@ def _run_device(v, hyper, ncta=8, chunks=1, cap=128):
     from tracklab_b200.device_trackers import BpbreidStrongSortDevice, rows_to_frames
     dev = torch.device("cuda:0")
     K, E = v.embeddings.shape[1:]
-    trk = BpbreidStrongSortDevice(K, E, **{k: hyper[k] for k in BPB_KEYS}, ctas_per_video=ncta, cap_tracks=(8 * cap if cap >= 128 else cap), cap_dets=cap)
+    trk = BpbreidStrongSortDevice(K, E, **{k: hyper[k] for k in BPB_ORACLE_KEYS if k in hyper}, ctas_per_video=ncta, cap_tracks=(8 * cap if cap >= 128 else cap), cap_dets=cap)
     dets = torch.from_numpy(_ltwh_rows(v)).to(dev)
     feats = torch.from_numpy(v.embeddings).to(dev)
     vis = torch.from_numpy(v.visibility.astype(np.float32)).to(dev)
@@ -44,6 +44,17 @@ def _run_device(v, hyper, ncta=8, chunks=1, cap=128):
 @pytest.mark.parametrize("name,ncta", [("bpbreid_yaml_s6000", 8), ("bpbreid_tight_s6001", 1), ("bpbreid_tight_s6001", 24)])
 def test_bpbreid_matches_reference_golden(name, ncta):
     g = load_bpbreid_golden(name)
+    v = make_video(**g["gen"])
+    rows, fr = _run_device(v, g["hyper"], ncta=ncta)
+    assert_bpbreid_rows_match(rows, fr, g["rows"], g["frames"], box_tol=1e-6, dist_tol=1e-5)
+
+
+@pytest.mark.parametrize("ncta", [1, 8])
+def test_bpbreid_bot_sort_matching_matches_reference_golden(ncta):
+    """matching_strategy: bot_sort_matching (one stage over all tracks on the weighted sum of the Kalman position distance, the
+    part-based appearance distance and 1 - IoU, sort/tracker.py:335-363,169-240, incl. the np.logical_or(.., .., out) quirk that
+    leaves the spatio-temporal gate unapplied) vs the UNMODIFIED plugin (tests/golden/bpbreid_botsort_s6002.npz): exact ids."""
+    g = load_bpbreid_golden("bpbreid_botsort_s6002")
     v = make_video(**g["gen"])
     rows, fr = _run_device(v, g["hyper"], ncta=ncta)
     assert_bpbreid_rows_match(rows, fr, g["rows"], g["frames"], box_tol=1e-6, dist_tol=1e-5)

@@ -45,7 +45,8 @@ class BpbreidParams(ctypes.Structure):
     _fields_ = [("max_dist", ctypes.c_double), ("max_iou_distance", ctypes.c_double), ("mc_lambda", ctypes.c_double),
                 ("ema_alpha", ctypes.c_double), ("min_bbox_confidence", ctypes.c_double), ("max_age", ctypes.c_int),
                 ("n_init", ctypes.c_int), ("max_kalman_prediction_without_update", ctypes.c_int), ("n_parts", ctypes.c_int),
-                ("feature_dim", ctypes.c_int), ("ctas_per_video", ctypes.c_int)]
+                ("feature_dim", ctypes.c_int), ("ctas_per_video", ctypes.c_int), ("matching_strategy", ctypes.c_int),
+                ("gating_thres_factor", ctypes.c_double), ("w_kfgd", ctypes.c_double), ("w_reid", ctypes.c_double), ("w_st", ctypes.c_double)]
 
 
 ASSO_CODES = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3, "ct_dist": 4}

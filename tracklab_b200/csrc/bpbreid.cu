@@ -59,6 +59,8 @@ struct BpParams {
     double max_dist, max_iou_dist, mc_lambda, min_conf;
     float ema_alpha, ema_beta;   // np.float32(alpha), np.float32(1 - alpha) (track.py:155-158)
     int max_age, n_init, max_pred, K, E;
+    int bot_sort;                 // matching_strategy: 0 strong_sort_matching (two stages), 1 bot_sort_matching (one weighted stage)
+    double gtf, w_k, w_r, w_s;    // gating_thres_factor, w_kfgd, w_reid, w_st (tracker.py:169-240)
 };
 
 struct BpDev {
@@ -346,7 +348,8 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
                 const int nd_ = warp_compact(nraw, 0, [&](int i) { return D[i * 7 + 4] > prm.min_conf; }, [&](int i, int p) { S.det_rows[p] = i; });
                 if (lane_id() == 0) { sh->nd = nd_; S.hdr[6] = nd_; sh->ncp = 0; sh->nap = 0; }
             } else if (warp_id() == 2) {
-                const int nc = warp_compact(nt, 0, [&](int k) { return state_m[list_m[k]] == BP_CONFIRMED; },
+                // bot_sort_matching associates ALL tracks in its single stage (tracker.py:343), strong_sort_matching the confirmed ones
+                const int nc = warp_compact(nt, 0, [&](int k) { return prm.bot_sort || state_m[list_m[k]] == BP_CONFIRMED; },
                                             [&](int k, int p) { S.conf_list[p] = list_m[k]; conf_m[p] = list_m[k]; });
                 if (lane_id() == 0) sh->nconf = nc;
             }
@@ -392,12 +395,14 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
             // The exact test of the hits is done by all CTAs after the barrier.
             {
                 const int total = nd > 0 ? nconf * nd : 0;
+                // bot_sort_matching gates on sqrt(d2) / (sqrt(chi2) * gating_thres_factor) > 1: the rectangle grows by that factor
+                const float rect_scale = prm.bot_sort ? __double2float_ru(prm.gtf) * 1.0001f : 1.0f;
                 auto hit_at = [&](int r, int d, int& pk) {
                     const int slot = conf_m[r];
                     const float4 g = gate_f[slot];
                     const float2 z = dz_f[d];
                     pk = (slot << 8) | d;
-                    return fabsf(z.x - g.x) <= g.z && fabsf(z.y - g.y) <= g.w;
+                    return fabsf(z.x - g.x) <= g.z * rect_scale && fabsf(z.y - g.y) <= g.w * rect_scale;
                 };
                 const int per = (total + BP_THREADS - 1) / BP_THREADS, e_lo = min(total, tid * per), e_hi = min(total, e_lo + per);
                 const int r_lo = nd > 0 ? e_lo / nd : 0, d_lo = e_lo - r_lo * nd;
@@ -438,7 +443,9 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
                     pk_l = S.cpack[hi];
                     const double* c = S.chol + (size_t)(pk_l >> 8) * 24;
                     g_l = kf8_maha(c, c + 4, c + 20, S.dz + 4 * (pk_l & 255));
-                    pass = !(g_l > CHI2_4);
+                    // strong_sort_matching: d2 > chi2inv95[4] (linear_assignment.py:166-175); bot_sort_matching: pos > 1 with
+                    // pos = sqrt(d2) / (sqrt(chi2) * gating_thres_factor) (tracker.py:194-199,222)
+                    pass = prm.bot_sort ? !(sqrt(g_l) / (sqrt(CHI2_4) * prm.gtf) > 1.0) : !(g_l > CHI2_4);
                 }
                 unsigned todo = __ballot_sync(0xffffffffu, pass);
                 if (todo == 0u) continue;
@@ -520,7 +527,29 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
         for (int i = tid; i < nap; i += BP_THREADS) {
             const double a = (double)S.pa[i];
             if (!(a == a)) atomicOr(status, TK_DEV_NAN_COST);   // no commonly visible part: the reference's solver raises on NaN
-            const double fused = __dadd_rn(__dmul_rn(prm.mc_lambda, a), __dmul_rn(1.0 - prm.mc_lambda, S.pg[i]));
+            double fused;
+            if (prm.bot_sort) {
+                // _full_cost_metric (tracker.py:169-240): (w_kfgd * pos + w_reid * app + st * w_st) / sum(w); voided where the position
+                // gate OR the appearance gate fails (the st gate never applies: np.logical_or(pos_gate, app_gate, st_gate) takes its
+                // third argument as the output array). Pairs outside the position gate never reach this point.
+                const int pk = S.ppack[i], sl = pk >> 8, d = pk & 255;
+                const double pos = sqrt(S.pg[i]) / (sqrt(CHI2_4) * prm.gtf);
+                const double* m = S.mean + (size_t)sl * 8;
+                const double w = m[2] * m[3];
+                const double bx = m[0] - w / 2, by = m[1] - m[3] / 2;                 // Track.to_ltwh (track.py:97-100)
+                const double* cb = d_ltwh + 4 * d;
+                const double x0 = fmax(bx, cb[0]), y0 = fmax(by, cb[1]);
+                const double x1 = fmin(bx + w, cb[0] + cb[2]), y1 = fmin(by + m[3], cb[1] + cb[3]);
+                const double iw = fmax(0.0, x1 - x0), ih = fmax(0.0, y1 - y0);
+                const double inter = __dmul_rn(iw, ih);
+                const double uni = __dsub_rn(__dadd_rn(__dmul_rn(w, m[3]), __dmul_rn(cb[2], cb[3])), inter);
+                const double st = 1.0 - inter / uni;
+                const double c = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn(prm.w_k, pos), __dmul_rn(prm.w_r, a)), __dmul_rn(st, prm.w_s)),
+                                           prm.w_k + prm.w_r + prm.w_s);
+                fused = (prm.w_r > 0 && a > prm.max_dist) ? 1e5 : c;
+            } else {
+                fused = __dadd_rn(__dmul_rn(prm.mc_lambda, a), __dmul_rn(1.0 - prm.mc_lambda, S.pg[i]));
+            }
             S.pf[i] = fused;
             if (!(fused > prm.max_dist)) t_live[S.ppack[i] >> 8] = 1;   // by slot
         }
@@ -590,8 +619,9 @@ bpbreid_video_kernel(BpParams prm, char* state_base, size_t state_stride, int ca
         PH(9);
         // stage-B candidates: unconfirmed + unmatched confirmed with tsu == 1 (tracker.py:303-309)
         if (warp_id() == 0) {
-            int nc = warp_compact(nt, 0, [&](int k) { return state_m[list_m[k]] != BP_CONFIRMED; }, [&](int k, int p) { if (p < capl) cand[p] = list_m[k]; });
-            nc = warp_compact(nconf, nc, [&](int r) { const int s = conf_m[r]; return !t_flag[s] && tick - last_m[s] == 1; },
+            // bot_sort_matching has no second stage (tracker.py:335-363): no candidates, every unmatched detection is born below
+            int nc = warp_compact(nt, 0, [&](int k) { return !prm.bot_sort && state_m[list_m[k]] != BP_CONFIRMED; }, [&](int k, int p) { if (p < capl) cand[p] = list_m[k]; });
+            nc = warp_compact(nconf, nc, [&](int r) { const int s = conf_m[r]; return !prm.bot_sort && !t_flag[s] && tick - last_m[s] == 1; },
                               [&](int r, int p) { if (p < capl) cand[p] = conf_m[r]; });
             // unmatched_detections_a in the reference's order (linear_assignment.py:57-68): untouched columns in detection order,
             // then the detections of the rejected pairs in confirmed-track order
@@ -835,6 +865,12 @@ int tk_bpbreid_create(const tk_bpbreid_params* p, int n_seq, int cap_tracks, int
     h->prm.min_conf = p->min_bbox_confidence; h->prm.ema_alpha = (float)p->ema_alpha; h->prm.ema_beta = (float)(1 - p->ema_alpha);
     h->prm.max_age = p->max_age; h->prm.n_init = p->n_init; h->prm.max_pred = p->max_kalman_prediction_without_update;
     h->prm.K = p->n_parts; h->prm.E = p->feature_dim;
+    h->prm.bot_sort = p->matching_strategy == TK_BPBREID_BOT_SORT_MATCHING ? 1 : 0;
+    h->prm.gtf = p->gating_thres_factor > 0 ? p->gating_thres_factor : 1.0;
+    h->prm.w_k = p->w_kfgd; h->prm.w_r = p->w_reid; h->prm.w_s = p->w_st;
+    if (p->matching_strategy != TK_BPBREID_STRONG_SORT_MATCHING && p->matching_strategy != TK_BPBREID_BOT_SORT_MATCHING) { delete h; return TK_ERR_ARG; }
+    // the single-stage strategy is evaluated gate-first: it needs the Kalman position gate (w_kfgd > 0, the reference default)
+    if (h->prm.bot_sort && !(p->w_kfgd > 0 && p->w_reid >= 0 && p->w_st >= 0)) { delete h; return TK_ERR_ARG; }
     h->n_seq = n_seq; h->cap = cap_tracks; h->capd = cap_dets;
     h->capl = cap_tracks < cap_dets ? cap_tracks : cap_dets;   // side of the compacted assignment problems
     h->ncta = p->ctas_per_video > 0 ? p->ctas_per_video : 8;

@@ -177,10 +177,16 @@ class BpbreidStrongSortDevice(_VideoTrackerDevice):
 
     def __init__(self, n_parts, feature_dim, ema_alpha=0.9, mc_lambda=0.995, max_dist=0.5, max_iou_distance=0.8, max_age=300,
                  n_init=0, min_bbox_confidence=0.0, max_kalman_prediction_without_update=7, ctas_per_video=8, n_seq=1,
-                 cap_tracks=1024, cap_dets=128, device="cuda:0"):
+                 cap_tracks=1024, cap_dets=128, device="cuda:0", matching_strategy="strong_sort_matching", gating_thres_factor=1.0,
+                 w_kfgd=1.0, w_reid=1.0, w_st=1.0):
         self.n_parts, self.feature_dim = n_parts, feature_dim
+        if matching_strategy not in ("strong_sort_matching", "bot_sort_matching"):
+            raise _lib.TrackKernError(f"matching_strategy {matching_strategy!r} unknown (strong_sort_matching / bot_sort_matching)")
+        if matching_strategy == "bot_sort_matching" and not w_kfgd > 0:
+            raise _lib.TrackKernError("bot_sort_matching on device needs w_kfgd > 0 (the Kalman position gate prunes the pair list)")
         self._create(_lib.BpbreidParams(max_dist, max_iou_distance, mc_lambda, ema_alpha, min_bbox_confidence, max_age, n_init,
-                                        max_kalman_prediction_without_update, n_parts, feature_dim, ctas_per_video),
+                                        max_kalman_prediction_without_update, n_parts, feature_dim, ctas_per_video,
+                                        int(matching_strategy == "bot_sort_matching"), gating_thres_factor, w_kfgd, w_reid, w_st),
                      n_seq, cap_tracks, cap_dets, device)
 
     def run(self, dets: torch.Tensor, offsets: torch.Tensor, features: torch.Tensor, visibility: torch.Tensor,

@@ -25,7 +25,7 @@ import torch
 
 from . import _lib
 from .device_trackers import ByteTrackDevice, OCSortDevice
-from .pipeline import ImageLevelModule
+from .pipeline import DetectionLevelModule, ImageLevelModule
 
 
 def _cfg_get(cfg, key, default=None):
@@ -218,6 +218,9 @@ class _StrongSortImpl:
         name = os.path.basename(str(weights)) if weights is not None else ""
         arch = _cfg_get(cfg, "reid_arch", None) or next((a for a in ("osnet_ibn_x1_0", "osnet_x1_0", "resnet50") if a in name), "resnet50")
         model = None
+        if weights is not None and not os.path.isfile(str(weights)) and not bool(_cfg_get(cfg, "synthetic_weights", False)):
+            # the reference loads or downloads real weights or fails; a typo must not produce plausible tracks from random weights
+            raise _lib.TrackKernError(f"ReID weights {weights!r} not found (pass synthetic_weights=True to run on seeded random weights)")
         if weights is not None and os.path.isfile(str(weights)):   # a reference-format state_dict (conv + BN), folded on load
             from .reid import build_reid_model
             sd = torch.load(str(weights), map_location="cpu")
@@ -345,9 +348,8 @@ class _BpbreidImpl:
             raise _lib.TrackKernError(f"{type(self).__name__} needs a CUDA device: tracklab_b200 has no CPU path")
         if bool(_cfg_get(cfg, "ecc", False)):
             raise _lib.TrackKernError("ecc=True (cv2.findTransformECC camera compensation) is not implemented on device")
-        if _cfg_get(cfg, "matching_strategy", "strong_sort_matching") != "strong_sort_matching" or \
-                _cfg_get(cfg, "motion_criterium", "iou") != "iou":
-            raise _lib.TrackKernError("only matching_strategy=strong_sort_matching with motion_criterium=iou is implemented on device")
+        if _cfg_get(cfg, "motion_criterium", "iou") != "iou":
+            raise _lib.TrackKernError("only motion_criterium=iou is implemented on device (oks needs the pose module's keypoints)")
         self.cfg = cfg
         self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
         self.cap_tracks = int(_cfg_get(cfg, "cap_tracks", 1024))
@@ -358,7 +360,10 @@ class _BpbreidImpl:
                           max_dist=float(_cfg_get(cfg, "max_dist", 0.5)), max_iou_distance=float(_cfg_get(cfg, "max_iou_distance", 0.8)),
                           max_age=int(_cfg_get(cfg, "max_age", 300)), n_init=int(_cfg_get(cfg, "n_init", 0)),
                           min_bbox_confidence=float(_cfg_get(cfg, "min_bbox_confidence", 0.0)),
-                          max_kalman_prediction_without_update=int(_cfg_get(cfg, "max_kalman_prediction_without_update", 7)))
+                          max_kalman_prediction_without_update=int(_cfg_get(cfg, "max_kalman_prediction_without_update", 7)),
+                          matching_strategy=str(_cfg_get(cfg, "matching_strategy", "strong_sort_matching")),
+                          gating_thres_factor=float(_cfg_get(cfg, "gating_thres_factor", 1.0)), w_kfgd=float(_cfg_get(cfg, "w_kfgd", 1.0)),
+                          w_reid=float(_cfg_get(cfg, "w_reid", 1.0)), w_st=float(_cfg_get(cfg, "w_st", 1.0)))
         self.tracker = None
         self._pipe = _TrackerDatapipe(self, self.frames_per_batch)
         self._result = None
@@ -465,7 +470,9 @@ class RTDetr(ImageLevelModule):
         from .nets.rtdetr import build_rtdetr
         from .rtdetr_detector import RTDetrDetectorDevice
         self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
-        sd = torch.load(str(weights), map_location="cpu") if weights is not None and os.path.isfile(str(weights)) else None
+        if weights is not None and not os.path.isfile(str(weights)):
+            raise _lib.TrackKernError(f"RT-DETR weights {weights!r} not found (omit `weights` to run on seeded random weights)")
+        sd = torch.load(str(weights), map_location="cpu") if weights is not None else None
         self.detector = RTDetrDetectorDevice(self.device, min_confidence, precision, model=build_rtdetr(seed, state_dict=sd))
         self._calibrate = sd is None     # seeded weights: the person bias is set on the first batch (nets/rtdetr.py)
         self.min_confidence = min_confidence
@@ -493,3 +500,215 @@ class RTDetr(ImageLevelModule):
                                           video_id=metadatas["video_id"].values[i], category_id=1), name=self.id))
                 self.id += 1
         return out
+
+
+# ---- YOLOX detector (rtmlib flavour of the bbox_detector step) -----------------------------------------------------------
+class _ImageBatches:
+    """Iterable the engine treats as a DataLoader: yields ``(image_ids, {"image_ids": ids})`` chunks of ``batch`` images."""
+
+    def __init__(self, pipe, batch):
+        self.pipe, self.batch = pipe, max(1, int(batch))
+
+    def __iter__(self):
+        ids = self.pipe.image_ids
+        for i in range(0, len(ids), self.batch):
+            yield ids[i:i + self.batch], {"image_ids": ids[i:i + self.batch]}
+
+    def __len__(self):
+        return (len(self.pipe.image_ids) + self.batch - 1) // self.batch
+
+
+class _PathsDatapipe:
+    """Stands in for EngineDatapipe (datastruct/datapipe.py:5-48) without per-sample decoding in worker processes: ``update``
+    just remembers the video's image paths; ``process`` decodes the images of its batch once."""
+
+    def __init__(self):
+        self.image_ids, self.paths = [], {}
+
+    def update(self, image_filepaths, img_metadatas, detections):
+        self.image_ids = list(img_metadatas.index)
+        self.paths = dict(image_filepaths) if image_filepaths else {i: p for i, p in img_metadatas["file_path"].items()}
+
+    def __len__(self):
+        return len(self.image_ids)
+
+
+def _decode_rgb(paths):
+    import cv2
+    return np.stack([cv2.cvtColor(cv2.imread(str(p)), cv2.COLOR_BGR2RGB) for p in paths])     # cv2_load_image (utils/cv2.py:54-66)
+
+
+class RTMLibDetector(ImageLevelModule):
+    """Drop-in for tracklab.wrappers.bbox_detector.rtmlib_api.RTMLibDetector (same name, columns, running detection id,
+    ``bbox_conf = 1.0``, float32 clipped ``bbox_ltwh``, /root/reference/tracklab/wrappers/bbox_detector/rtmlib_api.py:12-46).
+    The reference instantiates ``rtmlib.YOLOX(onnx_model=<url>, model_input_size=[640, 640])`` on onnxruntime and calls it once
+    per image; here the YOLOX variant is read from the same config node (``yolox_s`` / ``yolox_m`` in ``model.onnx_model``) and a
+    batch of images goes through letterbox -> YOLOX (bf16, CUDA graph) -> decode + NMS -> tk_pack_detections_ex on the device.
+    Weights: ``weights`` (a tracklab_b200 YOLOX state_dict; "auto" = weights/yolox_<v>_synth.pt); a missing file is an error."""
+    input_columns = []
+    output_columns = ["image_id", "video_id", "category_id", "bbox_ltwh", "bbox_conf"]
+    collate_fn = None
+
+    def __init__(self, device, model=None, batch_size=16, weights="auto", score_thr=0.7, nms_thr=0.45, synthetic_weights=False, **kwargs):
+        super().__init__(batch_size=1)
+        if not torch.cuda.is_available():
+            raise _lib.TrackKernError("RTMLibDetector needs a CUDA device: tracklab_b200 has no CPU path")
+        import re
+
+        from .detector import YoloxDetectorDevice, synth_weights_path
+        self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
+        url = str(_cfg_get(model, "onnx_model", "") or "") if model is not None else ""
+        mt = re.search(r"yolox[_-](tiny|s|m|l)(?![a-z])", url)
+        self.variant = str(_cfg_get(model, "variant", None) or (mt.group(1) if mt else "s"))
+        size = _cfg_get(model, "model_input_size", [640, 640]) if model is not None else [640, 640]
+        if weights == "auto":
+            weights = synth_weights_path(self.variant)
+            if weights is None and not synthetic_weights:
+                raise _lib.TrackKernError(f"no weights for YOLOX-{self.variant} under weights/ (pass weights=<state_dict file>, or "
+                                          "synthetic_weights=True to run on seeded random weights)")
+        self.frames_per_batch = int(batch_size)
+        self.detector = YoloxDetectorDevice(self.variant, device=self.device, batch=self.frames_per_batch, input_size=int(size[0]),
+                                            score_thr=score_thr, nms_thr=nms_thr, frames_cap=self.frames_per_batch,
+                                            dets_cap=self.frames_per_batch * 256, weights=weights, rows_ltwh=True)
+        self._needs_calibration = weights is None
+        self._pipe = _PathsDatapipe()
+        self.id = 0
+
+    @property
+    def datapipe(self):
+        return self._pipe
+
+    def dataloader(self, engine=None):
+        return _ImageBatches(self._pipe, self.frames_per_batch)
+
+    def preprocess(self, image, detections: pd.DataFrame, metadata: pd.Series):
+        return {}
+
+    @torch.no_grad()
+    def process(self, batch, detections: pd.DataFrame, metadatas: pd.DataFrame):
+        ids = list(metadatas.index)
+        paths = [self._pipe.paths[i] if i in self._pipe.paths else metadatas.loc[i, "file_path"] for i in ids]
+        frames = torch.from_numpy(_decode_rgb(paths)).to(self.device)
+        det = self.detector
+        if self._needs_calibration:
+            det.calibrate(frames, target_per_image=60.0)
+            self._needs_calibration = False
+        n = det.detect_into(frames)                             # one synchronisation per batch of images
+        rows = det.dets[:n].cpu().numpy()
+        offs = det.offsets[:len(ids) + 1].cpu().numpy()
+        frame_of_row = np.repeat(np.arange(len(ids)), np.diff(offs))
+        image_ids = np.asarray(ids)[frame_of_row]
+        video_ids = metadatas["video_id"].to_numpy()[frame_of_row]
+        out = pd.DataFrame({"image_id": image_ids, "bbox_ltwh": list(rows[:, :4].astype(np.float32)), "bbox_conf": rows[:, 4],
+                            "video_id": video_ids, "category_id": np.ones(n, dtype=int)},
+                           index=pd.RangeIndex(self.id, self.id + n))
+        self.id += n
+        return out
+
+
+# ---- ReID embeddings of the detections (DetectionLevelModule) ---------------------------------------------------------
+class _DetectionBatches:
+    def __init__(self, pipe, batch):
+        self.pipe, self.batch = pipe, max(1, int(batch))
+
+    def __iter__(self):
+        ids = self.pipe.det_ids
+        for i in range(0, len(ids), self.batch):
+            yield ids[i:i + self.batch], {"detection_ids": ids[i:i + self.batch]}
+
+    def __len__(self):
+        return (len(self.pipe.det_ids) + self.batch - 1) // self.batch
+
+
+class _ReidDatapipe:
+    def __init__(self, module):
+        self.module, self.det_ids = module, []
+
+    def update(self, image_filepaths, img_metadatas, detections):
+        self.det_ids = list(detections.index) if detections is not None else []
+        self.module._embed_video(image_filepaths, img_metadatas, detections)
+
+    def __len__(self):
+        return len(self.det_ids)
+
+
+class KPReId(DetectionLevelModule):
+    """Drop-in for the ReID step of the pipeline (tracklab.wrappers.reid.kpreid_api.KPReId: DetectionLevelModule,
+    input ``bbox_ltwh``, output ``embeddings`` [K, E] / ``visibility_scores`` [K], /root/reference/tracklab/wrappers/reid/
+    kpreid_api.py:20-24,115-182). The crop rule is the wrapper's (``detection.bbox.ltrb(image_shape, rounded=True)``: sanitise in
+    float32, round half to even, ``image[t:b, l:r]`` — tk_crop_resize_norm_ex / TK_CROP_RULE_LTWH_ROUNDED); the backbone is one of
+    the architectures vendored in the reference (ResNet-50 -> K = 1, E = 2048, the configs[2] shape of SURVEY.md 8d; OSNet -> E =
+    512), because KPR itself lives in the un-vendored torchreid fork. All detections of a video are embedded when the engine
+    hands them to the datapipe (images decoded once, crops batched through the CUDA-graphed backbone); ``process`` returns the
+    rows of its batch of detection ids."""
+    input_columns = ["bbox_ltwh"]
+    output_columns = ["embeddings", "visibility_scores"]
+    collate_fn = None
+
+    def __init__(self, cfg=None, device="cuda:0", save_path=None, training_enabled=False, batch_size=4096, job_id=0, *args, **kwargs):
+        super().__init__(batch_size)
+        if not torch.cuda.is_available():
+            raise _lib.TrackKernError("KPReId needs a CUDA device: tracklab_b200 has no CPU path")
+        from .reid import ReidStageDevice, build_reid_model
+        self.cfg = cfg
+        self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
+        arch = _cfg_get(cfg, "reid_arch", "resnet50") if cfg is not None else "resnet50"
+        weights = _cfg_get(cfg, "model_weights", None) if cfg is not None else None
+        model = None
+        if weights is not None:
+            if not os.path.isfile(str(weights)):
+                raise _lib.TrackKernError(f"ReID weights {weights!r} not found")
+            sd = torch.load(str(weights), map_location="cpu")
+            model = build_reid_model(arch).from_reference_state_dict(sd.get("state_dict", sd))
+        self.reid = ReidStageDevice(device=self.device, model=model, arch=arch,
+                                    precision=(_cfg_get(cfg, "reid_precision", "bf16") if cfg is not None else "bf16"))
+        self.decode_batch = int(_cfg_get(cfg, "decode_batch", 16)) if cfg is not None else 16
+        self.frames_per_batch = int(batch_size)
+        self._pipe = _ReidDatapipe(self)
+        self._result = None
+
+    @property
+    def datapipe(self):
+        return self._pipe
+
+    def dataloader(self, engine=None):
+        return _DetectionBatches(self._pipe, self.frames_per_batch)
+
+    def preprocess(self, image, detection: pd.Series, metadata: pd.Series):   # never called: the datapipe is overridden
+        return {}
+
+    @torch.no_grad()
+    def _embed_video(self, image_filepaths, img_metadatas, detections):
+        if detections is None or len(detections) == 0:
+            self._result = pd.DataFrame(columns=self.output_columns)
+            return
+        image_ids = np.asarray(img_metadatas.index)
+        pos = {int(i): k for k, i in enumerate(image_ids)}
+        frame = np.fromiter((pos[int(i)] for i in detections["image_id"].to_numpy()), dtype=np.int64, count=len(detections))
+        order = np.argsort(frame, kind="stable")
+        ltwh = np.stack(detections["bbox_ltwh"].to_numpy()).astype(np.float32).reshape(-1, 4)[order]
+        rows = np.zeros((len(order), 7), dtype=np.float64)
+        rows[:, :4] = ltwh
+        counts = np.bincount(frame, minlength=len(image_ids))
+        offsets = np.zeros(len(image_ids) + 1, dtype=np.int64)
+        np.cumsum(counts, out=offsets[1:])
+        paths = [image_filepaths[i] if image_filepaths and i in image_filepaths else img_metadatas.loc[i, "file_path"] for i in image_ids]
+        d_dev = torch.from_numpy(rows).to(self.device)
+        feats = torch.empty((len(rows), self.reid.feature_dim), dtype=torch.float32, device=self.device)
+        for f0 in range(0, len(paths), self.decode_batch):
+            f1 = min(len(paths), f0 + self.decode_batch)
+            r0, r1 = int(offsets[f0]), int(offsets[f1])
+            if r1 == r0:
+                continue
+            fr = torch.from_numpy(_decode_rgb(paths[f0:f1])).to(self.device)
+            det_frame = torch.from_numpy(np.repeat(np.arange(f1 - f0), counts[f0:f1]).astype(np.int32)).to(self.device)
+            feats[r0:r1] = self.reid.features(fr, d_dev[r0:r1], det_frame, ltwh_rows=True)
+        emb = feats.cpu().numpy()
+        idx = np.asarray(detections.index)[order]
+        self._result = pd.DataFrame({"embeddings": list(emb[:, None, :]), "visibility_scores": list(np.ones((len(emb), 1), dtype=np.float32))},
+                                    index=pd.Index(idx))
+
+    def process(self, batch, detections: pd.DataFrame, metadatas: pd.DataFrame):
+        if self._result is None or len(detections) == 0:
+            return []
+        return self._result.loc[detections.index, ["embeddings", "visibility_scores"]]
