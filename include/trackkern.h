@@ -164,6 +164,13 @@ int tk_bias_act_nhwc(const void* src, const float* bias, void* dst, const void* 
 #define TK_ACT_RELU_AFTER_RESIDUAL 3
 int tk_conv1x1_bias_act_bf16(const void* x, long long M, int K, int x_pitch, const void* w, int N, const float* bias, void* dst,
                              int dst_pitch, int dst_off, const void* residual, int res_pitch, int res_off, int act, void* stream);
+/* 3x3 convolution, stride 1, padding 1, same fused epilogue (hand-written sm_100a implicit GEMM: the im2col gather is done by the
+ * TMA engine — one 4-D tensor-map box per tap, out-of-image rows arrive as zeros — tcgen05.mma into TMEM, TMA store of the tile):
+ *   dst[b, y, x, dst_off + n] = act(sum_{ky,kx,c} x[b, y+ky-1, x+kx-1, c] * w[n, ky, kx, c] + bias[n]) (+ residual[b, y, x, res_off + n])
+ * x: bf16 NHWC [n_images, H, W, Cin] contiguous; w: bf16 [N][3][3][Cin] (a channels-last PyTorch weight); Cin and N multiples of 16.
+ * Replaces "cuDNN 3x3 convolution + tk_bias_act_nhwc" in the YOLOX executor. */
+int tk_conv3x3_bias_act_bf16(const void* x, int n_images, int H, int W, int Cin, const void* w, int N, const float* bias, void* dst,
+                             int dst_pitch, int dst_off, const void* residual, int res_pitch, int res_off, int act, void* stream);
 int tk_spp_nhwc(const void* x, void* dst, int n_images, int H, int W, int channels, int dst_pitch, int dst_offset, void* stream);
 int tk_upsample2x_nhwc(const void* src, int src_pitch, int src_offset, void* dst, int n_images, int h, int w, int channels,
                        int dst_pitch, int dst_offset, void* stream);
@@ -262,6 +269,26 @@ int tk_strongsort_create(const tk_strongsort_params* p, int n_seq, int cap_track
 int tk_strongsort_reset(void* handle, int keep_id_counter, void* stream);
 int tk_strongsort_run(void* handle, const double* dets, const float* features, const int* offsets, int n_frames, double* out_rows,
                       const int* out_start, int* out_frame_count, int* out_count, int out_capacity_rows, void* stream);
+/* Same with camera-motion compensation (cfg.ecc of /root/reference/tracklab/wrappers/track/strong_sort_api.py:62-65 ->
+ * Tracker.camera_update -> Track.camera_update, sort/track.py:224-239): warps = float [n_seq][n_frames][6], the 2x3 matrix of every
+ * frame of this call (tk_ecc_euclidean); it is applied to the box of EVERY track before the frame is processed (also on frames
+ * without detections). A NaN first entry means "no previous frame / ECC failed": tracks are left alone. NULL = tk_strongsort_run. */
+int tk_strongsort_run_cmc(void* handle, const double* dets, const float* features, const int* offsets, int n_frames, const float* warps,
+                          double* out_rows, const int* out_start, int* out_frame_count, int* out_count, int out_capacity_rows, void* stream);
+
+/* ---- ECC camera-motion estimation (sort/track.py:129-214: gray, x0.1 bilinear, cv2.findTransformECC MOTION_EUCLIDEAN) -------------
+ *   tk_ecc_small_size  (H, W, scale) -> size of the down-scaled gray image (cv2.resize with fx = fy = scale: cvRound)
+ *   tk_ecc_gray_small  frames uint8 [n,H,W,3] (the RGB frames the wrapper loads; the plugin runs COLOR_BGR2GRAY on them as they
+ *                      are) -> uint8 [n,h,w]: OpenCV's fixed-point gray conversion + INTER_LINEAR resize, bit-equal to cv2
+ *   tk_ecc_euclidean   small uint8 [n,h,w]: for every consecutive pair (i-1, i) the forward-additive ECC iteration of OpenCV
+ *                      (max_iter, eps on the change of the correlation coefficient) -> warps_out float [n][6] (row 0 = NaN: the first
+ *                      image has no predecessor; translation already divided by `scale` like track.py:196-198), rho_out double [n],
+ *                      ok_out int [n] (0: did not converge / singular -> the caller stores NaN in the warp, "ecc transform failed") */
+int tk_ecc_small_size(int H, int W, double scale, int* h_out, int* w_out);
+int tk_ecc_gray_small(const unsigned char* frames, int n_frames, int H, int W, long long frame_stride_bytes, double scale,
+                      unsigned char* out, void* stream);
+int tk_ecc_euclidean(const unsigned char* small_images, int n_images, int h, int w, int max_iter, double eps, double scale,
+                     float* warps_out, double* rho_out, int* ok_out, void* stream);
 int tk_strongsort_status(void* handle, int* status_host, void* stream);
 int tk_strongsort_destroy(void* handle);
 

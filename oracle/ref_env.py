@@ -94,6 +94,11 @@ def install():
         new_index = set(appended_piece.index).difference(main_df.index)
         for index in new_index:
             main_df.loc[index] = np.nan
+        # pandas 3 re-infers float64 for an all-NaN object column when rows are added to an EMPTY frame (a detector module filling
+        # the table from scratch); the pinned pandas 2.2.3 keeps object. Restore it so that update() can store ndarray cells.
+        for c in appended_piece.columns:
+            if c in main_df.columns and appended_piece[c].dtype == object and main_df[c].dtype != object:
+                main_df[c] = main_df[c].astype(object)
         main_df.update(appended_piece)
         return main_df
 

@@ -97,6 +97,11 @@ class _Trk:  # sort/track.py
         r[:2] -= r[2:] / 2
         return r
 
+    def tlbr(self):  # track.py:114-126
+        r = self.tlwh()
+        r[2:] = r[:2] + r[2:]
+        return r
+
 
 def _min_cost(cost, max_distance, t_idx, d_idx):  # linear_assignment.py:11-72 (cost already built)
     cost[cost > max_distance] = max_distance + 1e-5
@@ -132,6 +137,24 @@ class StrongSortOracle:
             a = x / np.linalg.norm(x, axis=1, keepdims=True)
             cost[r, :] = (1.0 - np.dot(a, b.T)).min(axis=0)
         return cost
+
+    # ---- camera motion compensation (tracker.py:66-68, track.py:216-239) ------------------------------
+    def camera_update(self, warp):
+        """warp: the 2x3 float32 matrix Track.ECC returned for (previous frame, this frame), or None ("ecc transform failed" /
+        no previous frame). The reference recomputes it per track; it only depends on the frame pair."""
+        if warp is None or not np.all(np.isfinite(warp)):
+            return
+        a, b = np.asarray(warp, dtype=np.float32).reshape(2, 3)
+        matrix = np.array([a, b, [0, 0, 1]]).tolist()
+        eye = np.eye(3)
+        matrix = matrix if np.linalg.norm(eye - matrix) < 100 else eye
+        for t in self.tracks:
+            x1, y1, x2, y2 = t.tlbr()
+            x1_, y1_, _ = matrix @ np.array([x1, y1, 1]).T
+            x2_, y2_, _ = matrix @ np.array([x2, y2, 1]).T
+            w, h = x2_ - x1_, y2_ - y1_
+            cx, cy = x1_ + w / 2, y1_ + h / 2
+            t.mean[:4] = [cx, cy, w / h, h]
 
     # ---- one frame (strong_sort.py:41-85) -----------------------------------------------------------
     def update(self, dets7, feats):
@@ -225,10 +248,13 @@ class StrongSortOracle:
             rows.append([x1, y1, x2, y2, t.id, t.cls, t.conf, t.det_id])
         return np.asarray(rows, dtype=np.float64).reshape(-1, 8)
 
-    def run_video(self, dets, offsets, feats):
-        """Wrapper semantics of strong_sort_api.py:66-93; ``feats`` float32 [N,E] aligned with ``dets`` rows."""
+    def run_video(self, dets, offsets, feats, warps=None):
+        """Wrapper semantics of strong_sort_api.py:59-93; ``feats`` float32 [N,E] aligned with ``dets`` rows; ``warps`` [F,6]
+        (cfg.ecc): the ECC matrix of (frame f-1, frame f), NaN rows = none."""
         out, fr = [], []
         for f in range(len(offsets) - 1):
+            if warps is not None:
+                self.camera_update(warps[f])
             d = dets[offsets[f]:offsets[f + 1]]
             if len(d) == 0:
                 continue

@@ -157,6 +157,57 @@ def run_strongsort_end_to_end(name="strongsort_e2e_s5000", gen=None):
     print(f"{name}: {video.n_dets} dets -> {rows.shape[0]} rows, {len(np.unique(rows[:, 4]))} ids")
 
 
+def run_strongsort_ecc(name="strongsort_ecc_s4002"):
+    """The UNMODIFIED StrongSORT tracker with camera compensation (strong_sort_api.py:59-65: tracker.camera_update(prev, img) before
+    update) on a camera_drift video with externally supplied features. Every track runs cv2.findTransformECC itself (track.py:129-214);
+    the matrix of each frame pair is recorded too (it is the same for all tracks) so that the tests can feed it to the device tracker."""
+    import cv2
+
+    from strong_sort.sort.nn_matching import NearestNeighborDistanceMetric
+    from strong_sort.sort.track import Track
+    from strong_sort.sort.tracker import Tracker
+    from strong_sort.strong_sort import StrongSORT
+
+    from tracklab_b200.synth import make_frames
+    gen = dict(seed=4002, n_frames=90, n_ids=24, emb_dim=64, camera_drift=True)
+    hyper = dict(max_dist=0.1594374041012136, max_iou_dist=0.5431835667667874, max_age=40, max_unmatched_preds=0,
+                 n_init=3, nn_budget=100, mc_lambda=0.995, ema_alpha=0.8962157769329083)
+    video = make_video(**gen)
+    model = object.__new__(StrongSORT)
+    model.max_dist = hyper["max_dist"]
+    metric = NearestNeighborDistanceMetric("cosine", hyper["max_dist"], hyper["nn_budget"])
+    model.tracker = Tracker(metric, max_iou_dist=hyper["max_iou_dist"], max_age=hyper["max_age"], n_init=hyper["n_init"],
+                            max_unmatched_preds=hyper["max_unmatched_preds"], mc_lambda=hyper["mc_lambda"], ema_alpha=hyper["ema_alpha"])
+    rows, frames, warps = [], [], np.full((video.n_frames, 6), np.nan, dtype=np.float32)
+    prev = None
+    probe = object.__new__(Track)
+    for f in range(video.n_frames):
+        img = make_frames(video, f, f + 1, device="cpu")[0].numpy()
+        if prev is not None:
+            wm, _ = probe.ECC(prev, img)
+            if wm is not None:
+                warps[f] = np.asarray(wm, dtype=np.float32).reshape(-1)
+            model.tracker.camera_update(prev, img)
+        prev = img
+        d = video.frame(f)
+        if len(d) == 0:
+            continue
+        keep = d[:, 4] > MIN_CONF
+        d = d[keep]
+        feats = video.embeddings[video.offsets[f]:video.offsets[f + 1]][keep]
+        model._get_features = lambda xywhs, im, _f=feats: torch.from_numpy(_f.copy())
+        with torch.no_grad():
+            res = np.asarray(model.update(torch.from_numpy(d.copy()), img))
+        if res.size:
+            res = res[:, [0, 1, 2, 3, 4, 5, 6, 8]].astype(np.float64)
+            rows.append(res); frames.append(np.full(len(res), f, dtype=np.int32))
+    rows, frames = np.concatenate(rows), np.concatenate(frames)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), rows=rows, frames=frames, warps=warps,
+                        dets_sha=np.frombuffer(__import__("hashlib").sha256(video.dets.tobytes()).digest(), dtype=np.uint8),
+                        tracker="strongsort_ecc", gen=repr(gen), hyper=repr(hyper), min_conf=MIN_CONF)
+    print(f"{name}: {video.n_dets} dets -> {rows.shape[0]} rows, {len(np.unique(rows[:, 4]))} ids; warps finite in {int(np.isfinite(warps[:, 0]).sum())} frames")
+
+
 def main(names):
     for name in names:
         tracker, gen, hyper = CASES[name]
@@ -174,6 +225,11 @@ if __name__ == "__main__":
     if "strongsort_e2e" in args:
         run_strongsort_end_to_end()
         args.remove("strongsort_e2e")
+        if not args:
+            sys.exit(0)
+    if "strongsort_ecc" in args:
+        run_strongsort_ecc()
+        args.remove("strongsort_ecc")
         if not args:
             sys.exit(0)
     if "strongsort_e2e_long" in args:   # 200 frames / 44 identities (~7.5k crops through the plugin's CPU ResNet-50: minutes)

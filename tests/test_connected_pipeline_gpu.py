@@ -49,7 +49,8 @@ def test_config2_connected_chain_equals_oracle_on_the_detector_rows(config, orac
     Orc = ByteTrackOracle if oracle == "bytetrack" else OCSortOracle
     want, wf = Orc(**CONFIGS[config]["hyper"], min_confidence=0.4).run_video(h.det_table, h.det_offsets)
     assert len(want) > 0
-    assert_rows_match(h.rows, h.frame, want, wf, box_tol=1e-9)
+    # OC-SORT's lap.lapjv is un-vendored: ids up to the documented relabelling where the stand-in solver ties (tests/util.py)
+    assert_rows_match(h.rows, h.frame, want, wf, box_tol=1e-9, allow_relabel=(oracle == "ocsort"))
     # pinned-host streaming gives the same rows (same graphs per batch)
     res2 = pipe.run_video(frames.cpu().pin_memory())
     torch.cuda.synchronize()

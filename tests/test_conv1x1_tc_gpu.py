@@ -76,3 +76,52 @@ def test_yolox_fused_executor_with_tcgen05_1x1_layers_matches_module():
     assert ex.tc_layers > 20
     denom = ref.abs().max().item()
     assert (got - ref).abs().max().item() <= 0.05 * denom, ((got - ref).abs().max().item(), denom)
+
+
+def _ref3(x, w, b, act, res):
+    y = torch.nn.functional.conv2d(x.float(), w.float(), b, 1, 1)
+    if act == 1:
+        y = y * torch.sigmoid(y)
+    elif act == 2:
+        y = torch.relu(y)
+    if res is not None:
+        y = y + res.float()
+    if act == 3:
+        y = torch.relu(y)
+    return y
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N", [(2, 16, 16, 64, 64), (3, 20, 20, 128, 128), (2, 40, 40, 96, 96), (1, 80, 80, 48, 48), (2, 33, 47, 32, 16),
+                                         (1, 160, 160, 32, 64), (2, 20, 20, 384, 384), (1, 24, 24, 192, 320), (5, 8, 8, 16, 48)])
+@pytest.mark.parametrize("act", [1, 0])
+def test_conv3x3_matches_fp32_reference(B, H, W, Cin, N, act):
+    """csrc/conv3x3_tc.cu (TMA im2col boxes, BK 64 / 32 / 16, clipped patches at the borders) vs F.conv2d in float32 on the same bf16 data."""
+    from tracklab_b200 import kernels
+    g = torch.Generator(device="cuda").manual_seed(B * H + W + Cin + N)
+    x = torch.randn((B, Cin, H, W), device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((N, Cin, 3, 3), device="cuda", generator=g) / (9 * Cin) ** 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn((N,), device="cuda", generator=g)
+    out = kernels.conv3x3_bias_act(x, w, b, act=act)
+    torch.cuda.synchronize()
+    ref = _ref3(x, w, b, act, None)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2.0 ** -7 * max(1.0, ref.abs().max().item()), err
+    assert (out.float() - ref).abs().mean().item() < 3e-3 * max(1.0, ref.abs().mean().item())
+
+
+@pytest.mark.parametrize("act", [1, 3])
+def test_conv3x3_residual_and_concat_slice(act):
+    from tracklab_b200 import kernels
+    B, H, W, Cin, N, P = 2, 40, 40, 64, 64, 160
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn((B, Cin, H, W), device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = (torch.randn((N, Cin, 3, 3), device="cuda", generator=g) / 24).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    b = torch.randn((N,), device="cuda", generator=g)
+    res = torch.randn((B, 2 * N, H, W), device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    dst = torch.full((B, P, H, W), 7.0, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    kernels.conv3x3_bias_act(x, w, b, dst=dst, dst_offset=64, act=act, residual=res, res_offset=N)
+    torch.cuda.synchronize()
+    ref = _ref3(x, w, b, act, res[:, N:])
+    got = dst[:, 64:128].float()
+    assert (got - ref).abs().max().item() <= 2.0 ** -7 * max(1.0, ref.abs().max().item())
+    assert torch.all(dst[:, :64] == 7.0) and torch.all(dst[:, 128:] == 7.0)

@@ -22,7 +22,17 @@ def rec(x, w, bias, dst=None, dst_offset=0, act=1, residual=None, res_offset=0):
     return orig(x, w, bias, dst=dst, dst_offset=dst_offset, act=act, residual=residual, res_offset=res_offset)
 
 
+orig3 = kernels.conv3x3_bias_act
+
+
+def rec3(x, w, bias, dst=None, dst_offset=0, act=1, residual=None, res_offset=0):
+    M = x.numel() // x.shape[1]
+    shapes.append((M, w.shape[1], w.shape[0], act, residual is not None, x.shape[2], x.shape[3], 3))
+    return orig3(x, w, bias, dst=dst, dst_offset=dst_offset, act=act, residual=residual, res_offset=res_offset)
+
+
 kernels.conv1x1_bias_act = rec
+kernels.conv3x3_bias_act = rec3
 with torch.no_grad():
     if a.net.startswith("yolox"):
         from tracklab_b200.nets.yolox import build_yolox
@@ -37,6 +47,7 @@ with torch.no_grad():
         ex = ResNet50Fused(build_resnet50_reid(1234), dev, use_graphs=False, use_tc=True)
         ex(ex.input_buffer(a.batch))
 kernels.conv1x1_bias_act = orig
+kernels.conv3x3_bias_act = orig3
 torch.cuda.synchronize()
 
 
@@ -57,19 +68,26 @@ rows = []
 uniq = {}
 for s in shapes:
     uniq[s] = uniq.get(s, 0) + 1
-for (M, K, N, act, has_res, H, W), cnt in uniq.items():
+for key, cnt in uniq.items():
+    M, K, N, act, has_res, H, W = key[:7]
+    ks = key[7] if len(key) > 7 else 1
     B = M // (H * W)
     nbuf = max(2, min(6, int(300e6 // max(1, M * (K + N) * 2)) + 1))
     xs = [torch.randn((B, K, H, W), device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for _ in range(nbuf)]
     ds = [torch.empty((B, N, H, W), dtype=torch.bfloat16, device=dev).contiguous(memory_format=torch.channels_last) for _ in range(nbuf)]
     rs = [torch.randn((B, N, H, W), device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) for _ in range(nbuf)] if has_res else None
-    w = (torch.randn((N, K), device=dev) / K ** 0.5).to(torch.bfloat16)
-    w4 = w.reshape(N, K, 1, 1).contiguous(memory_format=torch.channels_last)
+    if ks == 3:
+        w4 = (torch.randn((N, K, 3, 3), device=dev) / (9 * K) ** 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        w = w4
+    else:
+        w = (torch.randn((N, K), device=dev) / K ** 0.5).to(torch.bfloat16)
+        w4 = w.reshape(N, K, 1, 1).contiguous(memory_format=torch.channels_last)
+    tcfn = kernels.conv3x3_bias_act if ks == 3 else kernels.conv1x1_bias_act
     bias = torch.randn((N,), device=dev); b16 = bias.to(torch.bfloat16)
-    t_tc = timeit(lambda i: kernels.conv1x1_bias_act(xs[i % nbuf], w, bias, dst=ds[i % nbuf], act=act, residual=rs[i % nbuf] if rs else None), a.reps)
+    t_tc = timeit(lambda i: tcfn(xs[i % nbuf], w, bias, dst=ds[i % nbuf], act=act, residual=rs[i % nbuf] if rs else None), a.reps)
     if a.net.startswith("yolox"):
         def lib(i):
-            y = F.conv2d(xs[i % nbuf], w4)
+            y = F.conv2d(xs[i % nbuf], w4, None, 1, ks // 2)
             kernels.bias_act(y, bias, ds[i % nbuf], 0, act, rs[i % nbuf] if rs else None)
     else:
         def lib(i):
@@ -79,8 +97,8 @@ for (M, K, N, act, has_res, H, W), cnt in uniq.items():
                 torch.cudnn_convolution_relu(xs[i % nbuf], w4, b16, (1, 1), (0, 0), (1, 1), 1)
     t_lib = timeit(lib, a.reps)
     nbytes = M * (2 * K + 2 * N + (2 * N if has_res else 0))
-    flops = 2.0 * M * K * N
-    rows.append(dict(M=M, K=K, N=N, act=act, res=has_res, count=cnt, tc_us=round(t_tc, 1), lib_us=round(t_lib, 1), tc_GBps=round(nbytes / t_tc / 1e3, 0),
+    flops = 2.0 * M * K * N * ks * ks
+    rows.append(dict(k=ks, HW=f"{H}x{W}", M=M, K=K, N=N, act=act, res=has_res, count=cnt, tc_us=round(t_tc, 1), lib_us=round(t_lib, 1), tc_GBps=round(nbytes / t_tc / 1e3, 0),
                      tc_TFLOPs=round(flops / t_tc / 1e6, 1), lib_GBps=round(nbytes / t_lib / 1e3, 0)))
     tot_tc += t_tc * cnt; tot_lib += t_lib * cnt; tot_bytes += nbytes * cnt
 for r in sorted(rows, key=lambda r: -r["tc_us"] * r["count"]):

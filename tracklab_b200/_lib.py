@@ -68,6 +68,7 @@ def _declare(lib):
         "tk_pack_detections_ex": ([vp, vp, vp, vp, ci, ci, ci, ci, ci, cd, cd, vp, vp, vp, ci, ci, vp, ci, vp, vp], ci),
         "tk_bias_act_nhwc": ([vp, vp, vp, vp, ctypes.c_longlong, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_conv1x1_bias_act_bf16": ([vp, ctypes.c_longlong, ci, ci, vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, vp], ci),
+        "tk_conv3x3_bias_act_bf16": ([vp, ci, ci, ci, ci, vp, ci, vp, vp, ci, ci, vp, ci, ci, ci, vp], ci),
         "tk_spp_nhwc": ([vp, vp, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_upsample2x_nhwc": ([vp, ci, ci, vp, ci, ci, ci, ci, ci, ci, vp], ci),
         "tk_resize_frames_u8": ([vp, ci, ci, ci, ctypes.c_longlong, vp, ci, ci, ci, ctypes.c_float, vp], ci),
@@ -94,6 +95,10 @@ def _declare(lib):
         "tk_strongsort_create": ([P(StrongsortParams), ci, ci, ci, P(vp)], ci),
         "tk_strongsort_reset": ([vp, ci, vp], ci),
         "tk_strongsort_run": ([vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp], ci),
+        "tk_strongsort_run_cmc": ([vp, vp, vp, vp, ci, vp, vp, vp, vp, vp, ci, vp], ci),
+        "tk_ecc_small_size": ([ci, ci, cd, P(ci), P(ci)], ci),
+        "tk_ecc_gray_small": ([vp, ci, ci, ci, ctypes.c_longlong, cd, vp, vp], ci),
+        "tk_ecc_euclidean": ([vp, ci, ci, ci, ci, cd, cd, vp, vp, vp, vp], ci),
         "tk_strongsort_status": ([vp, P(ci), vp], ci),
         "tk_strongsort_destroy": ([vp], ci),
         "tk_bpbreid_create": ([P(BpbreidParams), ci, ci, ci, P(vp)], ci),

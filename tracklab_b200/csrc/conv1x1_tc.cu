@@ -23,10 +23,13 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "tc_gemm.cuh"
 #include "tk_common.cuh"
 #include "trackkern.h"
 
 namespace {
+
+using namespace tcg;
 
 constexpr int BM = 128;          // rows of an output tile = TMEM lanes
 constexpr int BK = 64;           // channels per pipeline stage = one 128-byte swizzle atom of bf16
@@ -34,69 +37,6 @@ constexpr int UMMA_K = 16;
 constexpr int C1_MAX_THREADS = 128 + 32 * 12;   // 4 control warps + up to 12 epilogue warps
 constexpr int STG_SUB_BYTES = BM * 128;         // one 64-column group of the staged output tile
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` when all previously issued MMAs have completed
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, 128 x N x 16
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): K-major tile whose rows are 128 bytes (one swizzle atom),
-// 8-row groups 1024 bytes apart (SBO), SWIZZLE_128B, descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3fff);        // start address, bits [0,14)
-    d |= (uint64_t)0 << 16;                        // leading byte offset (unused: one atom along K)
-    d |= (uint64_t)((1024 >> 4) & 0x3fff) << 32;   // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                        // version
-    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
 
 struct C1Params {
     long long M;
@@ -106,23 +46,6 @@ struct C1Params {
     int res_pitch, res_off;
     int act;
 };
-
-// SiLU with ONE transcendental: x * sigmoid(x) = 0.5 x (1 + tanh(x / 2)). The epilogue runs on a handful of warps per SM, so
-// the 2 MUFU operations of the exp + divide form (16 MUFU results / clock / SM) would eat most of a tile's time budget.
-__device__ __forceinline__ float silu_fast(float v) {
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * v));
-    return 0.5f * v * (1.0f + t);
-}
-__device__ __forceinline__ float act_apply(float v, int act) {
-    if (act == TK_ACT_SILU) return silu_fast(v);
-    if (act == TK_ACT_RELU) return fmaxf(v, 0.0f);
-    return v;
-}
-
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
 
 __global__ void __launch_bounds__(C1_MAX_THREADS, 1)
 conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
@@ -295,21 +218,6 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)f;
-    }
-    return fn;
 }
 
 // [rows, cols] bf16 matrix, row pitch `pitch` elements, box = box_rows x 64 columns, 128-byte swizzle, zero fill outside

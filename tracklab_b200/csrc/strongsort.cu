@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(SS_THREADS)
 strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int cap, int capd, int ncta,
                         const double* __restrict__ dets, const float* __restrict__ feats, const int* __restrict__ offsets,
                         int n_frames, double* __restrict__ out_rows, const int* __restrict__ out_start,
-                        int* __restrict__ out_frame_count, int* __restrict__ out_count, int out_cap) {
+                        int* __restrict__ out_frame_count, int* __restrict__ out_count, int out_cap, const float* __restrict__ warps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int seq = blockIdx.x / ncta, cta = blockIdx.x % ncta, tid = threadIdx.x;
     const bool master = cta == 0;
@@ -240,6 +240,40 @@ strongsort_video_kernel(SsParams prm, char* state_base, size_t state_stride, int
     for (int f = 0; f < n_frames; ++f) {
         const int r0 = offsets[seq * F1 + f], r1 = offsets[seq * F1 + f + 1];
         const int nraw = r1 - r0;
+        // ---- camera motion compensation (strong_sort_api.py:62-65 -> tracker.camera_update -> track.py:224-239): every track's
+        // box corners go through the frame pair's warp (tk_ecc_euclidean) before anything else, also on frames without detections.
+        // A NaN first entry = no previous frame / ECC failed: the reference leaves the tracks alone.
+        if (master && warps != nullptr) {
+            const float* wm = warps + ((size_t)seq * n_frames + f) * 6;
+            if (wm[0] == wm[0]) {
+                double a[6];
+                for (int i = 0; i < 6; ++i) a[i] = (double)wm[i];
+                const double dist = sqrt((1 - a[0]) * (1 - a[0]) + a[1] * a[1] + a[2] * a[2] + a[3] * a[3] + (1 - a[4]) * (1 - a[4]) + a[5] * a[5]);
+                if (!(dist < 100)) { a[0] = 1; a[1] = 0; a[2] = 0; a[3] = 0; a[4] = 1; a[5] = 0; }   // get_matrix (track.py:216-222)
+                const int ntk = S.hdr[1];
+                for (int k = tid; k < ntk; k += SS_THREADS) {
+                    const int s = S.list[k];
+                    double* m = S.mean + (size_t)s * 8;
+                    double x1, y1, x2, y2;
+                    if (S.fresh[s]) {   // mean is a float32 array until the first predict (kalman_filter.py:47-78): float32 box arithmetic
+                        const float cx = (float)m[0], cy = (float)m[1], w = __fmul_rn((float)m[2], (float)m[3]), hh = (float)m[3];
+                        const float l = __fsub_rn(cx, __fdiv_rn(w, 2.0f)), t = __fsub_rn(cy, __fdiv_rn(hh, 2.0f));
+                        x1 = (double)l; y1 = (double)t; x2 = (double)__fadd_rn(l, w); y2 = (double)__fadd_rn(t, hh);
+                    } else {
+                        const double w = m[2] * m[3];
+                        const double l = m[0] - w / 2, t = m[1] - m[3] / 2;   // to_tlwh (track.py:97-101), to_tlbr (:114-126)
+                        x1 = l; y1 = t; x2 = l + w; y2 = t + m[3];
+                    }
+                    const double x1_ = a[0] * x1 + a[1] * y1 + a[2], y1_ = a[3] * x1 + a[4] * y1 + a[5];
+                    const double x2_ = a[0] * x2 + a[1] * y2 + a[2], y2_ = a[3] * x2 + a[4] * y2 + a[5];
+                    const double w = x2_ - x1_, hh = y2_ - y1_;
+                    double o0 = x1_ + w / 2, o1 = y1_ + hh / 2, o2 = w / hh, o3 = hh;
+                    if (S.fresh[s]) { o0 = (double)(float)o0; o1 = (double)(float)o1; o2 = (double)(float)o2; o3 = (double)(float)o3; }
+                    m[0] = o0; m[1] = o1; m[2] = o2; m[3] = o3;
+                }
+            }
+            __syncthreads();
+        }
         if (nraw == 0) { if (master && tid == 0) out_frame_count[seq * n_frames + f] = 0; continue; }   // strong_sort_api.py:66-67
         if (nraw > capd) { if (master && tid == 0) atomicOr(status, TK_DEV_OVERFLOW_DETS); break; }
         const double* D = dets + (size_t)r0 * 7;
@@ -662,12 +696,18 @@ int tk_strongsort_reset(void* handle, int keep_id_counter, void* stream) {
 
 int tk_strongsort_run(void* handle, const double* dets, const float* features, const int* offsets, int n_frames, double* out_rows,
                       const int* out_start, int* out_frame_count, int* out_count, int out_capacity_rows, void* stream) {
+    return tk_strongsort_run_cmc(handle, dets, features, offsets, n_frames, nullptr, out_rows, out_start, out_frame_count, out_count,
+                                 out_capacity_rows, stream);
+}
+
+int tk_strongsort_run_cmc(void* handle, const double* dets, const float* features, const int* offsets, int n_frames, const float* warps,
+                          double* out_rows, const int* out_start, int* out_frame_count, int* out_count, int out_capacity_rows, void* stream) {
     if (!handle || !offsets || !out_rows || !out_start || !out_frame_count || !out_count || n_frames < 0) return TK_ERR_ARG;
     SsHandle* h = (SsHandle*)handle;
     if (n_frames == 0) return TK_OK;
     int cap = h->cap, capd = h->capd, ncta = h->ncta;
     void* args[] = {&h->prm, &h->state, &h->state_stride, &cap, &capd, &ncta, &dets, &features, &offsets, &n_frames,
-                    &out_rows, &out_start, &out_frame_count, &out_count, &out_capacity_rows};
+                    &out_rows, &out_start, &out_frame_count, &out_count, &out_capacity_rows, &warps};
     // cooperative launch: every CTA of a video group must be co-resident for the group barrier
     TK_CUDA_TRY(cudaFuncSetAttribute(strongsort_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));   // per function, not per handle
     TK_CUDA_TRY(cudaLaunchCooperativeKernel((void*)strongsort_video_kernel, dim3(h->n_seq * ncta), dim3(SS_THREADS), args,

@@ -140,8 +140,10 @@ class StrongSortDevice(_VideoTrackerDevice):
                                            ctas_per_video), n_seq, cap_tracks, cap_dets, device)
 
     def run(self, dets: torch.Tensor, offsets: torch.Tensor, features: torch.Tensor, out_rows: torch.Tensor | None = None,
-            out_start: torch.Tensor | None = None, out_count: torch.Tensor | None = None):
-        """features float32 [N, E] aligned with dets rows. Output capacity: 2 rows per detection per video by default."""
+            out_start: torch.Tensor | None = None, out_count: torch.Tensor | None = None, warps: torch.Tensor | None = None):
+        """features float32 [N, E] aligned with dets rows. Output capacity: 2 rows per detection per video by default.
+        warps float32 [n_seq, F, 6] (optional): per-frame camera motion (kernels.ecc_euclidean), applied to every track before
+        the frame is processed (cfg.ecc of the reference wrapper, C ABI: tk_strongsort_run_cmc)."""
         _require_cuda(dets, "dets"); _require_cuda(offsets, "offsets"); _require_cuda(features, "features")
         assert dets.dtype == torch.float64 and dets.is_contiguous() and features.dtype == torch.float32 and features.is_contiguous()
         assert features.shape == (dets.shape[0], self.feature_dim)
@@ -158,10 +160,15 @@ class StrongSortDevice(_VideoTrackerDevice):
         if out_count is None:
             out_count = torch.zeros(self.n_seq, dtype=torch.int32, device=dets.device)
         out_fc = torch.empty((self.n_seq, n_frames), dtype=torch.int32, device=dets.device)
+        wp = None
+        if warps is not None:
+            _require_cuda(warps, "warps")
+            assert warps.dtype == torch.float32 and warps.is_contiguous() and warps.numel() == self.n_seq * n_frames * 6
+            wp = warps.data_ptr()
         with torch.cuda.device(self.device):
-            _lib.check(self._fn["run"](self.handle, dets.data_ptr(), features.data_ptr(), offsets.data_ptr(), n_frames,
-                                       out_rows.data_ptr(), out_start.data_ptr(), out_fc.data_ptr(), out_count.data_ptr(),
-                                       cap_rows, _stream_ptr()), "tk_strongsort_run")
+            _lib.check(self.lib.tk_strongsort_run_cmc(self.handle, dets.data_ptr(), features.data_ptr(), offsets.data_ptr(), n_frames, wp,
+                                                      out_rows.data_ptr(), out_start.data_ptr(), out_fc.data_ptr(), out_count.data_ptr(),
+                                                      cap_rows, _stream_ptr()), "tk_strongsort_run_cmc")
         return out_rows, out_fc, out_count
 
 

@@ -154,6 +154,60 @@ def conv1x1_bias_act(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None
     return dst
 
 
+def conv3x3_bias_act(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None, dst: torch.Tensor | None = None, dst_offset: int = 0,
+                     act: int = 1, residual: torch.Tensor | None = None, res_offset: int = 0):
+    """3x3 / stride 1 / padding 1 convolution with fused epilogue on the tcgen05 path (C ABI: tk_conv3x3_bias_act_bf16).
+    x bf16 channels-last [B,Cin,H,W]; w bf16 channels-last [N,Cin,3,3]; bias float32 [N]; dst / residual bf16 channels-last [B,*,H,W]."""
+    lib = _lib.load()
+    B, Cin, H, W = x.shape
+    N = w.shape[0]
+    assert x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last)
+    assert w.dtype == torch.bfloat16 and tuple(w.shape[1:]) == (Cin, 3, 3) and w.is_contiguous(memory_format=torch.channels_last)
+    if dst is None:
+        dst = torch.empty((B, N, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    assert dst.is_contiguous(memory_format=torch.channels_last) and dst.shape[0] == B and tuple(dst.shape[2:]) == (H, W)
+    rp, r = 0, None
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.is_contiguous(memory_format=torch.channels_last) and tuple(residual.shape[2:]) == (H, W)
+        rp, r = residual.shape[1], residual.data_ptr()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.tk_conv3x3_bias_act_bf16(x.data_ptr(), B, H, W, Cin, w.data_ptr(), N, bias.data_ptr() if bias is not None else None,
+                                                dst.data_ptr(), dst.shape[1], dst_offset, r, rp, res_offset, act, _stream()),
+                   "tk_conv3x3_bias_act_bf16"); _count()
+    return dst
+
+
+def ecc_gray_small(frames: torch.Tensor, scale: float = 0.1) -> torch.Tensor:
+    """frames uint8 [n,H,W,3] (RGB, as the StrongSORT wrapper loads them) -> uint8 [n,h,w]: cv2.cvtColor(COLOR_BGR2GRAY) on the
+    array as it is + cv2.resize(fx=fy=scale, INTER_LINEAR), bit-equal to OpenCV (C ABI: tk_ecc_gray_small)."""
+    lib = _lib.load()
+    _cuda(frames, "frames")
+    n, H, W, _ = frames.shape
+    h, w = ctypes.c_int(), ctypes.c_int()
+    _lib.check(lib.tk_ecc_small_size(H, W, float(scale), ctypes.byref(h), ctypes.byref(w)), "tk_ecc_small_size")
+    out = torch.empty((n, h.value, w.value), dtype=torch.uint8, device=frames.device)
+    with torch.cuda.device(frames.device):
+        _lib.check(lib.tk_ecc_gray_small(frames.data_ptr(), n, H, W, frames.stride(0), float(scale), out.data_ptr(), _stream()),
+                   "tk_ecc_gray_small"); _count()
+    return out
+
+
+def ecc_euclidean(small: torch.Tensor, max_iter: int = 100, eps: float = 1e-5, scale: float = 0.1):
+    """small uint8 [n,h,w] -> (warps float32 [n,6] (row i: frame i-1 -> i; row 0 and failed pairs NaN), rho float64 [n], ok int32 [n]):
+    cv2.findTransformECC(MOTION_EUCLIDEAN) of every consecutive pair, translation divided by ``scale`` (C ABI: tk_ecc_euclidean)."""
+    lib = _lib.load()
+    _cuda(small, "small")
+    n, h, w = small.shape
+    warps = torch.full((n, 6), float("nan"), dtype=torch.float32, device=small.device)
+    rho = torch.zeros((n,), dtype=torch.float64, device=small.device)
+    ok = torch.zeros((n,), dtype=torch.int32, device=small.device)
+    with torch.cuda.device(small.device):
+        _lib.check(lib.tk_ecc_euclidean(small.data_ptr(), n, h, w, max_iter, float(eps), float(scale), warps.data_ptr(), rho.data_ptr(),
+                                        ok.data_ptr(), _stream()), "tk_ecc_euclidean"); _count()
+    warps[ok == 0] = float("nan")      # "ecc transform failed": camera_update leaves the tracks alone (track.py:190-193,226-227)
+    return warps, rho, ok
+
+
 def resize_frames(frames: torch.Tensor, out_hw=(640, 640), out_dtype=torch.float32, scale: float = 1.0 / 255.0) -> torch.Tensor:
     """frames uint8 [n,H,W,3] -> [n,3,h,w] = PIL-bilinear(frame) * scale (RTDetrImageProcessor; C ABI: tk_resize_frames_u8)."""
     lib = _lib.load()

@@ -195,14 +195,15 @@ class _StrongSortImpl:
     /root/reference/tracklab/wrappers/track/strong_sort_api.py:16-93: the reference decodes the frame in ``process``, crops
     and runs the ReID network inside the tracker for every frame; here the video's frames are decoded once per batch of
     images, all crops of the batch go through the crop-gather kernel + backbone together, and the whole video is
-    associated by one tk_strongsort_run launch. ``cfg.ecc`` must be false (camera compensation is out of scope)."""
+    associated by one tk_strongsort_run_cmc launch. ``cfg.ecc`` (the YAML default, strong_sort.yaml:13): the camera motion of every
+    consecutive frame pair is estimated on the device (tk_ecc_gray_small + tk_ecc_euclidean = cv2.findTransformECC, once per pair
+    instead of once per track and pair) and applied to every track's box before the frame is processed (sort/track.py:224-239)."""
 
     def __init__(self, cfg, device, **kwargs):
         ImageLevelModule.__init__(self, batch_size=1)
         if not torch.cuda.is_available():
             raise _lib.TrackKernError(f"{type(self).__name__} needs a CUDA device: tracklab_b200 has no CPU path")
-        if bool(_cfg_get(cfg, "ecc", False)):
-            raise _lib.TrackKernError("ecc=True (cv2.findTransformECC camera compensation) is not implemented on device")
+        self.ecc = bool(_cfg_get(cfg, "ecc", False))
         from .device_trackers import StrongSortDevice
         from .reid import ReidStageDevice
         self.cfg = cfg
@@ -260,16 +261,25 @@ class _StrongSortImpl:
                                          image_size=(W, H), cap_tracks=self.cap_tracks, cap_dets=self.cap_dets, device=self.device)
         d_dev = torch.from_numpy(rows).to(self.device)
         feats = torch.empty((len(rows), self.reid.feature_dim), dtype=torch.float32, device=self.device)
+        small = []
         for f0 in range(0, len(paths), self.decode_batch):   # decode once per image (cv2_load_image: BGR -> RGB, utils/cv2.py:54-66)
             f1 = min(len(paths), f0 + self.decode_batch)
             batch = np.stack([cv2.cvtColor(cv2.imread(p), cv2.COLOR_BGR2RGB) for p in paths[f0:f1]])
             fr = torch.from_numpy(batch).to(self.device)
+            if self.ecc:
+                from . import kernels
+                small.append(kernels.ecc_gray_small(fr, 0.1))
             r0, r1 = int(offsets[f0]), int(offsets[f1])
             if r1 > r0:
                 det_frame = torch.from_numpy(np.repeat(np.arange(f1 - f0), np.diff(offsets[f0:f1 + 1])).astype(np.int32)).to(self.device)
                 feats[r0:r1] = self.reid.features(fr, d_dev[r0:r1], det_frame)
         o_dev = torch.from_numpy(offsets)[None].to(self.device)
-        out_rows, out_fc, out_cnt = self.tracker.run(d_dev, o_dev, feats)
+        warps = None
+        if self.ecc:
+            from . import kernels
+            warps, _, _ = kernels.ecc_euclidean(torch.cat(small), 100, 1e-5, 0.1)   # row f: frame f-1 -> f, row 0 NaN (no previous frame)
+            warps = warps[None].contiguous()
+        out_rows, out_fc, out_cnt = self.tracker.run(d_dev, o_dev, feats, warps=warps)
         self.tracker.check_status()
         n = int(out_cnt[0].item())
         res = out_rows[:n].cpu().numpy()
@@ -325,7 +335,7 @@ def _bind_from(cls, impl):
 
 
 class StrongSORT(ImageLevelModule):
-    """Drop-in for tracklab.wrappers.track.strong_sort_api.StrongSORT (ReID + association on device, ecc off)."""
+    """Drop-in for tracklab.wrappers.track.strong_sort_api.StrongSORT (ReID + ECC camera compensation + association on device)."""
     input_columns = list(_IN_COLS)
     output_columns = list(_OUT_COLS)
     collate_fn = None

@@ -32,6 +32,9 @@ class _Conv:
         self.w2d = None
         if tuple(m.conv.kernel_size) == (1, 1) and tuple(self.stride) == (1, 1) and self.w.shape[1] % 8 == 0 and self.cout % 16 == 0:
             self.w2d = self.w.reshape(self.cout, self.w.shape[1]).contiguous()
+        # 3x3 stride-1 layers: the implicit-GEMM tcgen05 kernel (csrc/conv3x3_tc.cu); stride-2 layers stay in cuDNN
+        self.tc3 = (tuple(m.conv.kernel_size) == (3, 3) and tuple(self.stride) == (1, 1) and tuple(self.padding) == (1, 1)
+                    and self.w.shape[1] % 16 == 0 and self.cout % 16 == 0)
 
 
 class YoloxFused:
@@ -39,9 +42,11 @@ class YoloxFused:
     # 425 us per 50 frames; with 32 an sm_100 one, 164 us — tools/probe_yolox_stem.py)
     STEM_IN = 32
 
-    def __init__(self, model: YOLOX, device, use_tc: bool = True):
+    def __init__(self, model: YOLOX, device, use_tc: bool = True, use_tc3: bool | None = None):
+        import os
         self.device = torch.device(device)
         self.use_tc = use_tc
+        self.use_tc3 = (use_tc and os.environ.get("TK_NO_TC3", "0") != "1") if use_tc3 is None else use_tc3
         self.tc_layers = 0        # 1x1 layers of the last forward that ran on the tcgen05 path
         self.nc = model.num_classes
         dev = self.device
@@ -72,6 +77,9 @@ class YoloxFused:
         if self.use_tc and c.w2d is not None and x.shape[1] == c.w2d.shape[1]:
             self.tc_layers += 1
             return kernels.conv1x1_bias_act(x, c.w2d, c.b, dst=dst, dst_offset=dst_off, act=1, residual=residual, res_offset=res_off)
+        if self.use_tc3 and c.tc3 and x.shape[1] == c.w.shape[1]:
+            self.tc_layers += 1
+            return kernels.conv3x3_bias_act(x, c.w, c.b, dst=dst, dst_offset=dst_off, act=1, residual=residual, res_offset=res_off)
         y = F.conv2d(x, c.w, None, c.stride, c.padding)
         return kernels.bias_act(y, c.b, y if dst is None else dst, dst_off, 1, residual, res_off)
 

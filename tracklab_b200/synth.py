@@ -43,7 +43,9 @@ class SyntheticVideo:
 def make_video(seed: int, n_frames: int = 64, n_ids: int = 20, width: int = 1920, height: int = 1080,
                p_detect: float = 0.9, fp_rate: float = 0.02, occlusion: bool = True,
                conf_range=(0.45, 1.0), emb_dim: int | None = None, n_parts: int | None = None,
-               first_det_id: int = 0, p_visible: float = 0.85) -> SyntheticVideo:
+               first_det_id: int = 0, p_visible: float = 0.85, camera_drift: bool = False) -> SyntheticVideo:
+    """camera_drift: the whole scene (boxes here, background in make_frames) is displaced by an integer offset per frame,
+    (round(12 sin(t / 8)), round(8 cos(t / 11))) px — exercises the ECC camera compensation of StrongSORT (cfg.ecc)."""
     rng = np.random.default_rng(seed)
     W, H = float(width), float(height)
     c = rng.uniform([0.05 * W, 0.1 * H], [0.95 * W, 0.9 * H], size=(n_ids, 2))
@@ -92,6 +94,9 @@ def make_video(seed: int, n_frames: int = 64, n_ids: int = 20, width: int = 1920
             fx = rng.uniform(0.0, W - fw)
             fy = rng.uniform(0.0, max(1.0, H - fh))
             frame_rows.append((fx, fy, fx + fw, fy + fh, rng.uniform(0.1, 0.6), 1.0, -1))
+        if camera_drift:
+            ddx, ddy = camera_offset(f)
+            frame_rows = [(l + ddx, t + ddy, r + ddx, b + ddy, s, k, p) for (l, t, r, b, s, k, p) in frame_rows]
         for (l, t, r, b, s, k, p) in frame_rows:
             # clip like the detector wrappers do (coordinates.py:270-295) so boxes stay in the image
             l = min(max(l, 0.0), W - 2.0)
@@ -118,8 +123,13 @@ def make_video(seed: int, n_frames: int = 64, n_ids: int = 20, width: int = 1920
         offsets=np.asarray(offsets, dtype=np.int32), gt_identity=np.asarray(gt, dtype=np.int32),
         embeddings=(np.stack(embs) if embs else None),
         visibility=(np.stack(viss) if viss else None), seed=seed,
-        meta=dict(n_ids=n_ids, p_detect=p_detect, fp_rate=fp_rate, occlusion=occlusion),
+        meta=dict(n_ids=n_ids, p_detect=p_detect, fp_rate=fp_rate, occlusion=occlusion, camera_drift=camera_drift),
     )
+
+
+def camera_offset(f: int):
+    """Integer scene displacement of frame ``f`` of a camera_drift video."""
+    return int(np.rint(12.0 * np.sin(f / 8.0))), int(np.rint(8.0 * np.cos(f / 11.0)))
 
 
 def make_frames(video: SyntheticVideo, f0: int, f1: int, device="cpu"):
@@ -139,10 +149,20 @@ def make_frames(video: SyntheticVideo, f0: int, f1: int, device="cpu"):
     ys = torch.arange(H, device=dev)
     xs = torch.arange(W, device=dev)
     # bilinear-free integer blend: nearest coarse cell + position hash
-    bg = coarse_t[(ys // 120)[:, None], (xs // 120)[None, :]]
-    bg = (bg + ((ys[:, None] * 7 + xs[None, :] * 13) % 32)[..., None]).clamp(0, 255).to(torch.uint8)
-    tex_t = torch.from_numpy(tex).to(dev).to(torch.uint8)
-    out = bg.unsqueeze(0).repeat(f1 - f0, 1, 1, 1)
+    drift = bool(video.meta.get("camera_drift", False))
+    if drift:   # background on a canvas with a 32-px margin; every frame is a window displaced by the camera offset
+        ye = torch.arange(H + 64, device=dev)
+        xe = torch.arange(W + 64, device=dev)
+        big = coarse_t[(ye // 120).clamp(max=coarse.shape[0] - 1)[:, None], (xe // 120).clamp(max=coarse.shape[1] - 1)[None, :]]
+        big = (big + ((ye[:, None] * 7 + xe[None, :] * 13) % 32)[..., None]).clamp(0, 255).to(torch.uint8)
+        out = torch.stack([big[32 - camera_offset(f)[1]:32 - camera_offset(f)[1] + H, 32 - camera_offset(f)[0]:32 - camera_offset(f)[0] + W]
+                           for f in range(f0, f1)]).contiguous()
+        tex_t = torch.from_numpy(tex).to(dev).to(torch.uint8)
+    else:
+        bg = coarse_t[(ys // 120)[:, None], (xs // 120)[None, :]]
+        bg = (bg + ((ys[:, None] * 7 + xs[None, :] * 13) % 32)[..., None]).clamp(0, 255).to(torch.uint8)
+        tex_t = torch.from_numpy(tex).to(dev).to(torch.uint8)
+        out = bg.unsqueeze(0).repeat(f1 - f0, 1, 1, 1)
     for i, f in enumerate(range(f0, f1)):
         rows = video.frame(f)
         ids = video.gt_identity[video.offsets[f]:video.offsets[f + 1]]
