@@ -21,7 +21,7 @@ def _ref(x, w, b, act, res):
 
 
 @pytest.mark.parametrize("M,K,N", [(128, 64, 32), (1000, 64, 32), (128 * 148 * 2 + 77, 32, 16), (5000, 96, 48), (3001, 192, 96),
-                                   (4096, 128, 256), (2500, 384, 384), (777, 1536, 768), (20000, 256, 64), (300, 48, 48)])
+                                   (4096, 128, 256), (2500, 384, 384), (777, 1536, 768), (20000, 256, 64), (300, 48, 48), (1000, 64, 320), (513, 128, 160)])
 @pytest.mark.parametrize("act", [1, 0])
 def test_conv1x1_matches_fp32_reference(M, K, N, act):
     from tracklab_b200 import kernels
@@ -65,7 +65,7 @@ def test_yolox_fused_executor_with_tcgen05_1x1_layers_matches_module():
     from tracklab_b200.nets.yolox_fused import YoloxFused
     torch.manual_seed(0)
     model = build_yolox("s", 1, 1234, prior_prob=0.01).cuda().eval()
-    ex = YoloxFused(model.to(torch.bfloat16).to(memory_format=torch.channels_last), "cuda")
+    ex = YoloxFused(model.to(torch.bfloat16).to(memory_format=torch.channels_last), "cuda", use_tc3=True)   # 1x1 and 3x3 layers on tcgen05
     x = torch.rand((2, 3, 640, 640), device="cuda") * 255.0
     with torch.no_grad():
         ref = model.float()(x).float()

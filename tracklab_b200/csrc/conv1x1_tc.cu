@@ -32,15 +32,13 @@ namespace {
 using namespace tcg;
 
 constexpr int BM = 128;          // rows of an output tile = TMEM lanes
-constexpr int BK = 64;           // channels per pipeline stage = one 128-byte swizzle atom of bf16
 constexpr int UMMA_K = 16;
 constexpr int C1_MAX_THREADS = 128 + 32 * 12;   // 4 control warps + up to 12 epilogue warps
 constexpr int STG_SUB_BYTES = BM * 128;         // one 64-column group of the staged output tile
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 
 struct C1Params {
     long long M;
-    int K, N, block_n, n_blocks, stages, tmem_cols, epi_warps, stg_bufs;
+    int K, N, bk, block_n, n_blocks, stages, tmem_cols, epi_warps, stg_bufs;
     const float* bias;
     const __nv_bfloat16* res;
     int res_pitch, res_off;
@@ -54,8 +52,10 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // 1024-byte alignment is required by the 128-byte swizzle; dynamic shared memory starts 1024-aligned only by request
     unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b_stage_bytes = p.block_n * BK * 2;
-    const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;          // multiple of 1024 (block_n is a multiple of 16 -> 2 KB granules)
+    const int row_bytes = p.bk * 2;
+    const int A_STAGE_BYTES = BM * row_bytes;                         // 16 / 8 / 4 KB
+    const int b_stage_bytes = p.block_n * row_bytes;
+    const int stage_bytes = A_STAGE_BYTES + ((b_stage_bytes + 1023) & ~1023);   // every stage base stays 1024-aligned
     const int sub_tiles = (p.block_n + 63) / 64;                      // 64-column (128-byte) groups of the output tile
     const int stg_bytes = sub_tiles * STG_SUB_BYTES;                  // one staging buffer: sub_tiles x [128 rows][128 B], 128B-swizzled
     unsigned char* stg = smem + (size_t)p.stages * stage_bytes;       // [stg_bufs][stg_bytes], 1024-aligned
@@ -90,6 +90,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 
     const long long m_tiles = (p.M + BM - 1) / BM;
     const long long n_tiles = m_tiles * p.n_blocks;
+    const int BK = p.bk;
     const int k_blocks = (p.K + BK - 1) / BK;
 
     if (warp == 0) {
@@ -102,7 +103,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                     const uint32_t fb = smem_u32(full_bar + stage);
-                    mbar_expect_tx(fb, (uint32_t)stage_bytes);
+                    mbar_expect_tx(fb, (uint32_t)(A_STAGE_BYTES + b_stage_bytes));
                     unsigned char* sa = smem + (size_t)stage * stage_bytes;
                     tma_load_2d(smem_u32(sa), &map_x, fb, kb * BK, m0);                      // rows/channels past the edge arrive as zeros
                     tma_load_2d(smem_u32(sa + A_STAGE_BYTES), &map_w, fb, kb * BK, n0);
@@ -127,8 +128,7 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     mbar_wait(smem_u32(full_bar + stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t da = make_desc_sw128(sa), db = make_desc_sw128(sa + A_STAGE_BYTES);
-#pragma unroll
+                    const uint64_t da = make_desc_kmajor(sa, row_bytes), db = make_desc_kmajor(sa + A_STAGE_BYTES, row_bytes);
                     for (int k = 0; k < BK / UMMA_K; ++k)      // advance 32 bytes (16 bf16) inside the swizzle atom per UMMA_K step
                         umma_bf16(tmem_d, da + (uint64_t)(k * UMMA_K * 2 >> 4), db + (uint64_t)(k * UMMA_K * 2 >> 4), idesc, (kb | k) != 0);
                     umma_commit(smem_u32(empty_bar + stage));            // slot reusable once these MMAs have read it
@@ -220,16 +220,13 @@ conv1x1_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
 }
 
-// [rows, cols] bf16 matrix, row pitch `pitch` elements, box = box_rows x 64 columns, 128-byte swizzle, zero fill outside
-bool make_map(CUtensorMap* map, const void* base, unsigned long long rows, unsigned long long cols, unsigned long long pitch, unsigned box_rows) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
+// [rows, cols] bf16 matrix, row pitch `pitch` elements, box = box_rows x box_cols columns (swizzle span = box_cols * 2 bytes), zero fill outside
+bool make_map(CUtensorMap* map, const void* base, unsigned long long rows, unsigned long long cols, unsigned long long pitch, unsigned box_rows,
+              unsigned box_cols) {
     const cuuint64_t dims[2] = {cols, rows};
     const cuuint64_t strides[1] = {pitch * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    return make_map_nd(map, base, 2, dims, strides, box);
 }
 
 int g_sms = 0;
@@ -257,16 +254,22 @@ extern "C" int tk_conv1x1_bias_act_bf16(const void* x, long long M, int K, int x
         g_force_one_cta = o ? atoi(o) : 0;
     }
     // output-channel blocking: one block when N <= 256, else the smallest number of equal blocks (multiples of 16) <= 256
+    // several blocks only in multiples of 64 channels: the store boxes are 64 channels wide and are clipped by the tensor extent, not
+    // by the block, so a narrower last box of block k would spill into block k+1's channels (N = 320 -> 5 x 64, not 2 x 160)
     int n_blocks = 1;
-    while (N / n_blocks > 256 || N % n_blocks || (N / n_blocks) % 16) { if (++n_blocks > N / 16) return TK_ERR_ARG; }
+    while (N / n_blocks > 256 || N % n_blocks || (N / n_blocks) % 16 || (n_blocks > 1 && (N / n_blocks) % 64)) {
+        if (++n_blocks > N / 16) return TK_ERR_ARG;
+    }
     const int block_n = N / n_blocks;
     int tmem_cols = 32;
     while (tmem_cols < 2 * block_n) tmem_cols <<= 1;
-    const int stage_bytes = A_STAGE_BYTES + block_n * BK * 2;
+    // channels per stage: no partially out-of-bounds boxes for K = 32 / 48 / 96 ... (they ran at 2.2-3.9 TB/s against 5+ for K = 64)
+    const int bk = (K % 64 == 0) ? 64 : ((K % 32 == 0) ? 32 : ((K % 16 == 0) ? 16 : 64));
+    const int stage_bytes = BM * bk * 2 + ((block_n * bk * 2 + 1023) & ~1023);
     const int sub_tiles = (block_n + 63) / 64;
     const int stg_bufs = block_n <= 128 ? 2 : 1;
     const size_t stg_total = (size_t)stg_bufs * sub_tiles * STG_SUB_BYTES;
-    const int k_blocks = (K + BK - 1) / BK;
+    const int k_blocks = (K + bk - 1) / bk;
     auto smem_for = [&](int st) { return (size_t)1024 + (size_t)st * stage_bytes + stg_total + (2 * st + 4) * 8 + 16 + (size_t)N * 4 + 16; };
     // two CTAs per SM (two independent pipelines, twice the epilogue warps) when 3 stages + staging fit in half an SM and the
     // accumulators fit in half the TMEM; otherwise one CTA with as many stages as fit
@@ -274,24 +277,26 @@ extern "C" int tk_conv1x1_bias_act_bf16(const void* x, long long M, int K, int x
     if (!g_force_one_cta && tmem_cols <= 256 && smem_for(k_blocks >= 3 ? 3 : 2) <= 110 * 1024) {
         ctas_per_sm = 2;
         stages = k_blocks >= 3 ? 3 : 2;
-        while (stages < 6 && smem_for(stages + 1) <= 110 * 1024) ++stages;
+        const int cap2 = 6 * (64 / bk) < 12 ? 6 * (64 / bk) : 12;      // smaller stages -> a deeper ring for the same bytes in flight
+        while (stages < cap2 && smem_for(stages + 1) <= 110 * 1024) ++stages;
     } else {
         stages = 2;
-        while (stages < 8 && smem_for(stages + 1) <= 220 * 1024) ++stages;
+        const int cap1 = 8 * (64 / bk) < 16 ? 8 * (64 / bk) : 16;
+        while (stages < cap1 && smem_for(stages + 1) <= 220 * 1024) ++stages;
         if (smem_for(stages) > 227 * 1024) return TK_ERR_CAPACITY;
     }
     const size_t smem = smem_for(stages);
     CUtensorMap mx, mw, md;
-    if (!make_map(&mx, x, (unsigned long long)M, (unsigned long long)K, (unsigned long long)x_pitch, BM)) return TK_ERR_CUDA;
-    if (!make_map(&mw, w, (unsigned long long)N, (unsigned long long)K, (unsigned long long)K, (unsigned)block_n)) return TK_ERR_CUDA;
-    if (!make_map(&md, (const __nv_bfloat16*)dst + dst_off, (unsigned long long)M, (unsigned long long)N, (unsigned long long)dst_pitch, BM)) return TK_ERR_CUDA;
+    if (!make_map(&mx, x, (unsigned long long)M, (unsigned long long)K, (unsigned long long)x_pitch, BM, (unsigned)bk)) return TK_ERR_CUDA;
+    if (!make_map(&mw, w, (unsigned long long)N, (unsigned long long)K, (unsigned long long)K, (unsigned)block_n, (unsigned)bk)) return TK_ERR_CUDA;
+    if (!make_map(&md, (const __nv_bfloat16*)dst + dst_off, (unsigned long long)M, (unsigned long long)N, (unsigned long long)dst_pitch, BM, 64)) return TK_ERR_CUDA;
     if (!g_sms) {
         int dev = 0;
         TK_CUDA_TRY(cudaGetDevice(&dev));
         TK_CUDA_TRY(cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev));
     }
     C1Params p;
-    p.M = M; p.K = K; p.N = N; p.block_n = block_n; p.n_blocks = n_blocks; p.stages = stages; p.tmem_cols = tmem_cols;
+    p.M = M; p.K = K; p.N = N; p.bk = bk; p.block_n = block_n; p.n_blocks = n_blocks; p.stages = stages; p.tmem_cols = tmem_cols;
     p.epi_warps = g_epi_warps; p.stg_bufs = stg_bufs;
     p.bias = bias; p.res = (const __nv_bfloat16*)residual; p.res_pitch = res_pitch; p.res_off = res_off; p.act = act;
     const long long tiles = ((M + BM - 1) / BM) * n_blocks;

@@ -271,8 +271,12 @@ extern "C" int tk_conv3x3_bias_act_bf16(const void* x, int n_images, int H, int 
         g_one3 = o ? atoi(o) : 0;
     }
     const int bk = (Cin % 64 == 0) ? 64 : ((Cin % 32 == 0) ? 32 : 16);
+    // several blocks only in multiples of 64 channels: the store boxes are 64 channels wide and are clipped by the tensor extent, not
+    // by the block, so a narrower last box of block k would spill into block k+1's channels (N = 320 -> 5 x 64, not 2 x 160)
     int n_blocks = 1;
-    while (N / n_blocks > 256 || N % n_blocks || (N / n_blocks) % 16) { if (++n_blocks > N / 16) return TK_ERR_ARG; }
+    while (N / n_blocks > 256 || N % n_blocks || (N / n_blocks) % 16 || (n_blocks > 1 && (N / n_blocks) % 64)) {
+        if (++n_blocks > N / 16) return TK_ERR_ARG;
+    }
     const int block_n = N / n_blocks;
     int tmem_cols = 32;
     while (tmem_cols < 2 * block_n) tmem_cols <<= 1;

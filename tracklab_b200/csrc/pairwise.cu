@@ -115,38 +115,76 @@ row_inv_norm_kernel(const float* __restrict__ x, float* __restrict__ inv_norm, l
     if ((threadIdx.x & 31) == 0) inv_norm[row] = sqrtf(s);   // the norm itself; the division happens per element like NumPy
 }
 
-// out[p, i, j] = 1 - (a_i / |a_i|) . (b_j / |b_j|); 32x32 output tile per CTA, E walked in chunks of 32 through shared memory
+// out[p, i, j] = 1 - (a_i / |a_i|) . (b_j / |b_j|)  (nn_matching.py:30-49: float32 normalise, float32 dot).
+// Register-tiled: a CTA of 256 threads (16 x 16) owns a (16 TM) x (16 TM) output tile, every thread a TM x TM block of accumulators;
+// E is walked in chunks of 32 through shared memory (k-major, so the inner loop reads TM + TM values for TM * TM fused
+// multiply-adds). The rows are normalised while they are staged (one division per staged element, like NumPy's a / |a|), not in the
+// inner loop. TM = 5 (80 x 80 tiles) wastes 12 % on the 150 x 150 problems of the stress configuration, TM = 4 (64 x 64) 39 %.
+template <int TM>
 __global__ void __launch_bounds__(256)
 cosine_dist_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ na,
                    const float* __restrict__ nb, double* __restrict__ out, int N, int M, int E) {
-    __shared__ float ta[32][33], tb[32][33];
-    const int p = blockIdx.z, i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // 8 rows of threads
+    constexpr int T = 16 * TM, LD = T + 4;
+    __shared__ __align__(16) float ta[32][LD], tb[32][LD];
+    const int p = blockIdx.z, i0 = blockIdx.y * T, j0 = blockIdx.x * T;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const float* ap = a + (size_t)p * N * E;
     const float* bp = b + (size_t)p * M * E;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < E; k0 += 32) {
+    const float* nap = na + (size_t)p * N;
+    const float* nbp = nb + (size_t)p * M;
+    float acc[TM][TM];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int row = ty + 8 * r;
-            const int k = k0 + tx;
+    for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int c = 0; c < TM; ++c) acc[r][c] = 0.0f;
+    const bool vec = (E & 3) == 0;
+    for (int k0 = 0; k0 < E; k0 += 32) {
+        // stage T rows x 32 columns of both operands, transposed to k-major, divided by the row norm
+        for (int q = threadIdx.x; q < T * 8; q += 256) {
+            const int row = q >> 3, kq = (q & 7) * 4, k = k0 + kq;
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
             const int ia = i0 + row, jb = j0 + row;
-            ta[row][tx] = (ia < N && k < E) ? __fdiv_rn(ap[(size_t)ia * E + k], na[(size_t)p * N + ia]) : 0.0f;
-            tb[row][tx] = (jb < M && k < E) ? __fdiv_rn(bp[(size_t)jb * E + k], nb[(size_t)p * M + jb]) : 0.0f;
+            if (ia < N) {
+                const float* src = ap + (size_t)ia * E + k;
+                if (vec && k + 3 < E) va = *reinterpret_cast<const float4*>(src);
+                else { if (k < E) va.x = src[0]; if (k + 1 < E) va.y = src[1]; if (k + 2 < E) va.z = src[2]; if (k + 3 < E) va.w = src[3]; }
+                const float n = nap[ia];
+                va.x = __fdiv_rn(va.x, n); va.y = __fdiv_rn(va.y, n); va.z = __fdiv_rn(va.z, n); va.w = __fdiv_rn(va.w, n);
+            }
+            if (jb < M) {
+                const float* src = bp + (size_t)jb * E + k;
+                if (vec && k + 3 < E) vb = *reinterpret_cast<const float4*>(src);
+                else { if (k < E) vb.x = src[0]; if (k + 1 < E) vb.y = src[1]; if (k + 2 < E) vb.z = src[2]; if (k + 3 < E) vb.w = src[3]; }
+                const float n = nbp[jb];
+                vb.x = __fdiv_rn(vb.x, n); vb.y = __fdiv_rn(vb.y, n); vb.z = __fdiv_rn(vb.z, n); vb.w = __fdiv_rn(vb.w, n);
+            }
+            ta[kq][row] = va.x; ta[kq + 1][row] = va.y; ta[kq + 2][row] = va.z; ta[kq + 3][row] = va.w;
+            tb[kq][row] = vb.x; tb[kq + 1][row] = vb.y; tb[kq + 2][row] = vb.z; tb[kq + 3][row] = vb.w;
         }
         __syncthreads();
 #pragma unroll 8
         for (int k = 0; k < 32; ++k) {
-            const float bv = tb[tx][k];
+            float av[TM], bv[TM];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] = fmaf(ta[ty + 8 * r][k], bv, acc[r]);
+            for (int r = 0; r < TM; ++r) av[r] = ta[k][ty * TM + r];
+#pragma unroll
+            for (int c = 0; c < TM; ++c) bv[c] = tb[k][tx * TM + c];
+#pragma unroll
+            for (int r = 0; r < TM; ++r)
+#pragma unroll
+                for (int c = 0; c < TM; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int i = i0 + ty + 8 * r, j = j0 + tx;
-        if (i < N && j < M) out[((size_t)p * N + i) * M + j] = (double)__fsub_rn(1.0f, acc[r]);
+    for (int r = 0; r < TM; ++r) {
+        const int i = i0 + ty * TM + r;
+        if (i >= N) continue;
+#pragma unroll
+        for (int c = 0; c < TM; ++c) {
+            const int j = j0 + tx * TM + c;
+            if (j < M) out[((size_t)p * N + i) * M + j] = (double)__fsub_rn(1.0f, acc[r][c]);
+        }
     }
 }
 
@@ -363,8 +401,15 @@ int tk_cosine_dist(const float* a, const float* b, double* out, float* norm_scra
     const long long ra = (long long)n_problems * N, rb = (long long)n_problems * M;
     row_inv_norm_kernel<<<(unsigned)((ra + 7) / 8), 256, 0, st>>>(a, na, ra, E);
     row_inv_norm_kernel<<<(unsigned)((rb + 7) / 8), 256, 0, st>>>(b, nb, rb, E);
-    dim3 grid((M + 31) / 32, (N + 31) / 32, n_problems);
-    cosine_dist_kernel<<<grid, 256, 0, st>>>(a, b, na, nb, out, N, M, E);
+    // tile size by covered-area waste: 80 x 80 (TM = 5) or 64 x 64 (TM = 4)
+    auto waste = [&](int t) { return (double)(((N + t - 1) / t) * t) * (((M + t - 1) / t) * t) / ((double)N * M); };
+    if (waste(80) <= waste(64)) {
+        dim3 grid((M + 79) / 80, (N + 79) / 80, n_problems);
+        cosine_dist_kernel<5><<<grid, 256, 0, st>>>(a, b, na, nb, out, N, M, E);
+    } else {
+        dim3 grid((M + 63) / 64, (N + 63) / 64, n_problems);
+        cosine_dist_kernel<4><<<grid, 256, 0, st>>>(a, b, na, nb, out, N, M, E);
+    }
     TK_CUDA_TRY(cudaGetLastError());
     return TK_OK;
 }

@@ -46,7 +46,10 @@ class YoloxFused:
         import os
         self.device = torch.device(device)
         self.use_tc = use_tc
-        self.use_tc3 = (use_tc and os.environ.get("TK_NO_TC3", "0") != "1") if use_tc3 is None else use_tc3
+        # 3x3 layers on the implicit-GEMM tcgen05 kernel: opt-in (TK_TC3=1). Measured on B200 (profiles/r02_conv_microbench.md) it is
+        # correct but slower than cuDNN's native sm_100 3x3 kernels + the epilogue pass at the detector's channel counts
+        # (per-tap TMA boxes with 64..256-byte rows are request-bound), so the default keeps cuDNN for 3x3.
+        self.use_tc3 = (use_tc and os.environ.get("TK_TC3", "0") == "1") if use_tc3 is None else use_tc3
         self.tc_layers = 0        # 1x1 layers of the last forward that ran on the tcgen05 path
         self.nc = model.num_classes
         dev = self.device
