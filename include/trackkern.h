@@ -374,6 +374,34 @@ int tk_lap_batched(const double* cost, int n_problems, int N, int M, double cost
  * StrongSORT / BPBReID kernels use the same routine in shared memory (csrc/lsap_scipy.cuh). */
 int tk_lsap_scipy_batched(const double* cost, int n_problems, int N, int M, int* x_out, int* y_out, int* status_dev, void* stream);
 
+/* ---- HOTA of one sequence on the device -----------------------------------------------------------------------
+ * Replaces HOTA.eval_sequence of the TrackEval fork vendored in the reference
+ * (/root/reference/plugins/eval/PoseTrack21/posetrack21/posetrack21/trackeval/metrics/hota.py:28-154, final fields :205-221) with the
+ * box similarity of its MOT dataset (trackeval/datasets/_base_dataset.py:244-282, box_format 'xywh'; posetrack_mot.py:479).
+ * gt / tracker rows are frame-major: boxes [rows,4] float64 xywh, ids [rows] int32 already mapped to 0..n_ids-1 (unique within a
+ * frame, as the reference's _check_unique_ids demands), offsets [n_frames+1] int32 — all device pointers. `alphas_host` (host
+ * pointer, <= 32 values; the reference uses np.arange(0.05, 0.99, 0.05)). `pairs_cap` >= sum over frames of gt rows x tracker rows.
+ * out [TK_HOTA_FIELDS, n_alphas] float64 (device), rows in the order below. The FragA field of the fork is not computed.
+ * Integer fields (TP/FN/FP, the assignments) are exact; the float fields follow the reference's own summation order. */
+#define TK_HOTA_HOTA 0
+#define TK_HOTA_DETA 1
+#define TK_HOTA_ASSA 2
+#define TK_HOTA_DETRE 3
+#define TK_HOTA_DETPR 4
+#define TK_HOTA_ASSRE 5
+#define TK_HOTA_ASSPR 6
+#define TK_HOTA_LOCA 7
+#define TK_HOTA_TP 8
+#define TK_HOTA_FN 9
+#define TK_HOTA_FP 10
+#define TK_HOTA_FIELDS 11
+int tk_hota_workspace_bytes(int n_frames, int n_gt_ids, int n_tr_ids, int n_alphas, long long pairs_cap, long long* bytes_out);
+int tk_hota_sequence(const double* gt_boxes_xywh, const int* gt_ids, const int* gt_offsets, long long n_gt_rows,
+                     const double* tr_boxes_xywh, const int* tr_ids, const int* tr_offsets, long long n_tr_rows, int n_frames,
+                     int n_gt_ids, int n_tr_ids, int max_gt_per_frame, int max_tr_per_frame, const double* alphas_host,
+                     int n_alphas, long long pairs_cap, void* workspace, long long workspace_bytes, double* out, int* status_dev,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

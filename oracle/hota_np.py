@@ -23,6 +23,36 @@ def iou_ltwh(a, b):
     return np.where(union > 0, inter / np.maximum(union, 1e-300), 0.0)
 
 
+def box_ious_xywh(b1, b2):
+    """_BaseDataset._calculate_box_ious(box_format='xywh') of the vendored TrackEval fork
+    (/root/reference/plugins/eval/PoseTrack21/posetrack21/posetrack21/trackeval/datasets/_base_dataset.py:244-282), the similarity
+    its MOT dataset class feeds HOTA with (posetrack_mot.py:479)."""
+    eps = np.finfo("float").eps
+    b1, b2 = np.array(b1, dtype=float).reshape(-1, 4), np.array(b2, dtype=float).reshape(-1, 4)
+    b1[:, 2] = b1[:, 0] + b1[:, 2]; b1[:, 3] = b1[:, 1] + b1[:, 3]
+    b2[:, 2] = b2[:, 0] + b2[:, 2]; b2[:, 3] = b2[:, 1] + b2[:, 3]
+    mn = np.minimum(b1[:, None, :], b2[None, :, :]); mx = np.maximum(b1[:, None, :], b2[None, :, :])
+    inter = np.maximum(mn[..., 2] - mx[..., 0], 0) * np.maximum(mn[..., 3] - mx[..., 1], 0)
+    a1 = (b1[..., 2] - b1[..., 0]) * (b1[..., 3] - b1[..., 1])
+    a2 = (b2[..., 2] - b2[..., 0]) * (b2[..., 3] - b2[..., 1])
+    union = a1[:, None] + a2[None, :] - inter
+    inter[a1 <= 0 + eps, :] = 0
+    inter[:, a2 <= 0 + eps] = 0
+    inter[union <= 0 + eps] = 0
+    union[union <= 0 + eps] = 1
+    return inter / union
+
+
+def hota_from_boxes(gt_boxes, gt_ids, gt_off, tr_boxes, tr_ids, tr_off):
+    """Frame-major xywh boxes + contiguous ids + offsets -> hota_sequence (the inputs of tk_hota_sequence)."""
+    g, t, s = [], [], []
+    for f in range(len(gt_off) - 1):
+        a, b = slice(gt_off[f], gt_off[f + 1]), slice(tr_off[f], tr_off[f + 1])
+        g.append(np.asarray(gt_ids[a], dtype=int)); t.append(np.asarray(tr_ids[b], dtype=int))
+        s.append(box_ious_xywh(gt_boxes[a], tr_boxes[b]))
+    return hota_sequence(g, t, s)
+
+
 def hota_sequence(gt_ids, tr_ids, sims):
     """gt_ids / tr_ids: per frame int arrays of contiguous ids (0..n-1); sims: per frame [n_gt_t, n_tr_t] similarities.
     Returns dict of arrays over ALPHAS (HOTA, DetA, AssA, LocA, HOTA_TP/FN/FP) like the reference's res."""

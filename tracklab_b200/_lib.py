@@ -80,6 +80,9 @@ def _declare(lib):
         "tk_cosine_dist": ([vp, vp, vp, vp, ci, ci, ci, ci, vp], ci),
         "tk_lap_batched": ([vp, ci, ci, ci, cd, ci, vp, vp, vp, vp], ci),
         "tk_lsap_scipy_batched": ([vp, ci, ci, ci, vp, vp, vp, vp], ci),
+        "tk_hota_workspace_bytes": ([ci, ci, ci, ci, ctypes.c_longlong, P(ctypes.c_longlong)], ci),
+        "tk_hota_sequence": ([vp, vp, vp, ctypes.c_longlong, vp, vp, vp, ctypes.c_longlong, ci, ci, ci, ci, ci, P(cd), ci,
+                             ctypes.c_longlong, vp, ctypes.c_longlong, vp, vp, vp], ci),
         "tk_part_dist": ([vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp], ci),
         "tk_kf_gate": ([vp, vp, vp, vp, ci, ci, ci, vp, vp], ci),
         "tk_bytetrack_create": ([P(BytetrackParams), ci, ci, ci, P(vp)], ci),
