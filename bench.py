@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-config2", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA graphs (ncu launch lists only; never a bench value)")
     return ap.parse_args()
 
 
@@ -356,7 +357,8 @@ def run_config(config, args, dev, rank, world, local, frames_cap, batch, steps, 
     frames = torch.empty((F, video.height, video.width, 3), dtype=torch.uint8, device=dev)
     for f0 in range(0, F, 25):
         frames[f0:min(F, f0 + 25)] = make_frames(video, f0, min(F, f0 + 25), device="cpu").to(dev)
-    pipe = build_pipeline(config, device=dev, batch=batch, frames_cap=F, image_size=(video.width, video.height))
+    pipe = build_pipeline(config, device=dev, batch=batch, frames_cap=F, image_size=(video.width, video.height),
+                          use_graphs=not args.no_graphs)
     if not pipe.det.trained:
         pipe.det.calibrate(frames[:batch], target_per_image=60.0)
     cols = 14 if cfg["tracker"] == "bpbreid" else 8
@@ -523,6 +525,8 @@ def run_ours(args):
                               "ids": allm[:, 3].tolist(), "ms_per_step": allm[:, 4].tolist(), "e2e_ms_per_step": allm[:, 5].tolist()},
                 "detector_rows_per_frame": main["host"].det_rows / F, "numa": numa,
                 "tc_layers_per_forward": getattr(main["pipe"].det.fused, "tc_layers", None)}
+        if args.no_graphs:
+            line["invalid"] = "--no-graphs: eager launches for an ncu launch list, not a bench value"
         if second is not None:
             v2, ms2, e2 = headline(second, allm2)
             roof2, tens2, kern2 = roofline_blocks(second, peak_hbm, peak_tf, peak_src)
@@ -558,9 +562,52 @@ def hota_block(r):
     from oracle.hota_np import hota_of_tracker_rows
     if r["cfg"]["tracker"] == "bpbreid":
         return None
+    t0 = time.perf_counter()
     h = hota_of_tracker_rows(r["video"], r["host"].rows, r["host"].frame)
-    return {"HOTA": float(h["HOTA"].mean()), "DetA": float(h["DetA"].mean()), "AssA": float(h["AssA"].mean()),
-            "note": "device chain, all frames; tracker output boxes vs generator boxes/identities"}
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    out = {"HOTA": float(h["HOTA"].mean()), "DetA": float(h["DetA"].mean()), "AssA": float(h["AssA"].mean()),
+           "note": "device chain, all frames; tracker output boxes vs generator boxes/identities", "cpu_oracle_ms": cpu_ms}
+    try:
+        out["device"] = hota_on_device(r, h)
+    except Exception as e:
+        out["device"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
+def hota_on_device(r, cpu):
+    """The same HOTA through tk_hota_sequence: rows already on the device, device-timed, compared with the CPU oracle."""
+    import numpy as np
+    import torch
+
+    from tracklab_b200.hota import HotaDevice, frame_major
+    v, rows, fr = r["video"], r["host"].rows, r["host"].frame
+    dev = r["frames"].device
+    keep = v.gt_identity >= 0
+    d = v.dets[keep]
+    det_frame = np.repeat(np.arange(v.n_frames), np.diff(v.offsets))[keep]
+    cu = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    gb = cu(np.column_stack([d[:, 0], d[:, 1], d[:, 2] - d[:, 0], d[:, 3] - d[:, 1]]), np.float64)
+    tb = cu(np.column_stack([rows[:, 0], rows[:, 1], rows[:, 2] - rows[:, 0], rows[:, 3] - rows[:, 1]]), np.float64)
+    go, goff = frame_major(cu(det_frame, np.int64), v.n_frames)
+    to, toff = frame_major(cu(fr, np.int64), v.n_frames)
+    gu, gi = torch.unique(cu(v.gt_identity[keep], np.int64)[go], return_inverse=True)
+    tu, ti = torch.unique(cu(rows[:, 4], np.int64)[to], return_inverse=True)
+    ng, nt = (goff[1:] - goff[:-1]).to(torch.int64), (toff[1:] - toff[:-1]).to(torch.int64)
+    h = HotaDevice(v.n_frames, int(gu.numel()), int(tu.numel()), int((ng * nt).sum().item()), int(ng.max().item()), int(nt.max().item()), device=dev)
+    args = (gb[go].contiguous(), gi.to(torch.int32).contiguous(), goff, tb[to].contiguous(), ti.to(torch.int32).contiguous(), toff,
+            int(gu.numel()), int(tu.numel()))
+    h.run(*args)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        h.run(*args)
+    e1.record()
+    torch.cuda.synchronize()
+    res = h.result()
+    return {"ms": e0.elapsed_time(e1) / 5, "frames": int(v.n_frames), "gt_rows": int(gb.shape[0]), "tracker_rows": int(tb.shape[0]),
+            "counts_equal_cpu_oracle": bool(all(np.array_equal(res[k], cpu[k]) for k in ("HOTA_TP", "HOTA_FN", "HOTA_FP"))),
+            "max_abs_diff_HOTA": float(np.abs(res["HOTA"] - cpu["HOTA"]).max()), "HOTA": float(res["HOTA"].mean())}
 
 
 def cpu_baseline(args, r):

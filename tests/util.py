@@ -10,7 +10,8 @@ def load_golden(name):
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     return dict(rows=g["rows"], frames=g["frames"], gen=ast.literal_eval(str(g["gen"])),
                 hyper=ast.literal_eval(str(g["hyper"])), min_conf=float(g["min_conf"]),
-                tracker=str(g["tracker"]), dets_sha=bytes(g["dets_sha"].tobytes()))
+                tracker=str(g["tracker"]), dets_sha=bytes(g["dets_sha"].tobytes()) if "dets_sha" in g.files else None,
+                **{k: g[k] for k in ("affines", "raw_emb") if k in g.files})
 
 
 def load_bpbreid_golden(name):
@@ -76,3 +77,23 @@ def assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1e-6, allow_re
     err = np.abs(a[:, :4] - b[:, :4]).max() if len(a) else 0.0
     assert err <= box_tol, f"box error {err}"
     return err
+
+
+def blackout_video(video, period=12, span=3, keep_frac=0.15, seed=0):
+    """Copy of ``video`` in which, for ``span`` frames of every ``period``, only ``keep_frac`` of the detections survive (a detector
+    black-out): tracks die during the gap and the full set of detections returns at once, so detections outnumber the live
+    trackers in the frames after it (exercises the unassigned-row handling of the association rounds)."""
+    import dataclasses
+    rng = np.random.default_rng(seed)
+    keep = np.ones(len(video.dets), dtype=bool)
+    for f in range(video.n_frames):
+        if f % period >= period - span:
+            sl = slice(video.offsets[f], video.offsets[f + 1])
+            keep[sl] = rng.random(sl.stop - sl.start) < keep_frac
+    off = np.concatenate([[0], np.cumsum([keep[video.offsets[f]:video.offsets[f + 1]].sum() for f in range(video.n_frames)])]).astype(video.offsets.dtype)
+    rep = dict(dets=video.dets[keep].copy(), offsets=off, gt_identity=video.gt_identity[keep].copy())
+    if video.embeddings is not None:
+        rep["embeddings"] = video.embeddings[keep].copy()
+    if video.visibility is not None:
+        rep["visibility"] = video.visibility[keep].copy()
+    return dataclasses.replace(video, **rep)

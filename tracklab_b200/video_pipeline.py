@@ -311,11 +311,15 @@ CONFIGS = {
 
 def build_pipeline(config: str = "config3", device="cuda:0", batch: int = 20, frames_cap: int = 512, image_size=(1920, 1080),
                    weights="auto", reid_precision: str = "bf16", min_confidence: float = 0.4, max_per_frame: int = 96,
-                   ctas_per_video: int = 32, detector_kwargs=None, reid_model=None, detector_model=None) -> DetectReidTrackPipeline:
+                   ctas_per_video: int = 32, detector_kwargs=None, reid_model=None, detector_model=None,
+                   use_graphs: bool = True) -> DetectReidTrackPipeline:
     """Assemble the product pipeline of one BASELINE configuration. ``weights``: "auto" = weights/yolox_<variant>_synth.pt
     when present (the detector trained on the synthetic generator), else seeded random weights with calibrated heads;
-    None = seeded; a path = that file (missing -> error)."""
+    None = seeded; a path = that file (missing -> error). ``use_graphs=False``: eager launches of the same kernels (for ncu launch
+    lists; the timed bench always runs the CUDA graphs)."""
     cfg = CONFIGS[config]
+    if not use_graphs:
+        detector_kwargs = dict(detector_kwargs or {}, use_graph=False)
     dev = torch.device(device)
     rows_cap = frames_cap * max_per_frame
     w = synth_weights_path(cfg["variant"]) if weights == "auto" else weights
@@ -325,7 +329,7 @@ def build_pipeline(config: str = "config3", device="cuda:0", batch: int = 20, fr
     reid = None
     if cfg["reid"] is not None:
         from .reid import ReidStageDevice
-        reid = ReidStageDevice(device=dev, arch=cfg["reid"], precision=reid_precision, model=reid_model)
+        reid = ReidStageDevice(device=dev, arch=cfg["reid"], precision=reid_precision, model=reid_model, use_graphs=use_graphs)
     W, H = image_size
     if cfg["tracker"] == "bytetrack":
         trk = ByteTrackDevice(**cfg["hyper"], min_confidence=min_confidence, cap_tracks=256, cap_dets=128, device=dev)
