@@ -374,6 +374,43 @@ int tk_lap_batched(const double* cost, int n_problems, int N, int M, double cost
  * StrongSORT / BPBReID kernels use the same routine in shared memory (csrc/lsap_scipy.cuh). */
 int tk_lsap_scipy_batched(const double* cost, int n_problems, int N, int M, int* x_out, int* y_out, int* status_dev, void* stream);
 
+/* ---- Deep OC-SORT: whole-video association with externally supplied embeddings and camera-motion affines ----
+ * Replaces OCSort.update of the deep_oc_sort plugin called once per frame by the wrapper, minus the in-tracker ReID forward
+ * (`_get_features`, a separate stage here) and the camera-motion estimator (`CMCComputer.compute_affine`: its 2x3 result is an input):
+ *   /root/reference/plugins/track/deep_oc_sort/ocsort.py:374-542        (update), :96-304 (KalmanBoxTracker, 8-d filter)
+ *   /root/reference/plugins/track/deep_oc_sort/association.py:202-212,263-360
+ *   /root/reference/plugins/track/deep_oc_sort/kalmanfilter.py:340-379,383-481,483-569
+ *   /root/reference/tracklab/wrappers/track/deep_oc_sort_api.py:57-91   (per-frame filter + row layout)
+ * Hyper-parameters: /root/reference/tracklab/configs/modules/track/deep_oc_sort.yaml (new_kf_off must be false).
+ * dets [N,7] float64 (x1,y1,x2,y2,score,cls,det_id), embeddings float32 [N, feature_dim] (row i belongs to dets row i, as the
+ * plugin's ReID returns them: not normalised by the tracker), affines float64 [n_seq, n_frames, 2, 3] (NULL when cmc_off),
+ * offsets int32 [n_seq, n_frames+1]. Output rows [x1,y1,x2,y2,track_id,cls,conf,det_id], at most one per detection of a frame.
+ * cap_tracks + cap_dets <= 256 and 2 * cap_dets <= 256. */
+typedef struct {
+    double det_thresh;        /* 0 */
+    double iou_threshold;     /* 0.2213... */
+    double inertia;           /* 0.3941... */
+    double min_confidence;    /* wrapper filter (0.4), deep_oc_sort_api.py:65 */
+    double w_association_emb; /* 0.75 */
+    double alpha_fixed_emb;   /* 0.95 */
+    double aw_param;          /* 0.5 */
+    int max_age;              /* 50 */
+    int min_hits;             /* 1 */
+    int delta_t;              /* 1 (<= 7) */
+    int asso_func;            /* TK_ASSO_* of the second (OCR) round; round 1 is plain IoU */
+    int embedding_off;        /* false */
+    int cmc_off;              /* false */
+    int aw_off;               /* false */
+    int feature_dim;          /* E */
+} tk_deepocsort_params;
+
+int tk_deepocsort_create(const tk_deepocsort_params* p, int n_seq, int cap_tracks, int cap_dets, void** handle);
+int tk_deepocsort_reset(void* handle, void* stream);
+int tk_deepocsort_run(void* handle, const double* dets, const float* embeddings, const double* affines, const int* offsets, int n_frames,
+                      double* out_rows, const int* out_start, int* out_frame_count, int* out_count, int out_capacity_rows, void* stream);
+int tk_deepocsort_status(void* handle, int* status_host, void* stream);
+int tk_deepocsort_destroy(void* handle);
+
 /* ---- HOTA of one sequence on the device -----------------------------------------------------------------------
  * Replaces HOTA.eval_sequence of the TrackEval fork vendored in the reference
  * (/root/reference/plugins/eval/PoseTrack21/posetrack21/posetrack21/trackeval/metrics/hota.py:28-154, final fields :205-221) with the
