@@ -385,7 +385,8 @@ int tk_lsap_scipy_batched(const double* cost, int n_problems, int N, int M, int*
  * dets [N,7] float64 (x1,y1,x2,y2,score,cls,det_id), embeddings float32 [N, feature_dim] (row i belongs to dets row i, as the
  * plugin's ReID returns them: not normalised by the tracker), affines float64 [n_seq, n_frames, 2, 3] (NULL when cmc_off),
  * offsets int32 [n_seq, n_frames+1]. Output rows [x1,y1,x2,y2,track_id,cls,conf,det_id], at most one per detection of a frame.
- * cap_tracks + cap_dets <= 256 and 2 * cap_dets <= 256. */
+ * cap_tracks + cap_dets <= 512. lap 0.5.12 (the solver the plugin imports) is not vendored: its published (n+m)^2 extension is
+ * solved with scipy's algorithm incl. its tie-breaking, like the stand-in the goldens were generated with. */
 typedef struct {
     double det_thresh;        /* 0 */
     double iou_threshold;     /* 0.2213... */

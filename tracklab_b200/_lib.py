@@ -49,6 +49,14 @@ class BpbreidParams(ctypes.Structure):
                 ("gating_thres_factor", ctypes.c_double), ("w_kfgd", ctypes.c_double), ("w_reid", ctypes.c_double), ("w_st", ctypes.c_double)]
 
 
+class DeepocsortParams(ctypes.Structure):
+    _fields_ = [("det_thresh", ctypes.c_double), ("iou_threshold", ctypes.c_double), ("inertia", ctypes.c_double),
+                ("min_confidence", ctypes.c_double), ("w_association_emb", ctypes.c_double), ("alpha_fixed_emb", ctypes.c_double),
+                ("aw_param", ctypes.c_double), ("max_age", ctypes.c_int), ("min_hits", ctypes.c_int), ("delta_t", ctypes.c_int),
+                ("asso_func", ctypes.c_int), ("embedding_off", ctypes.c_int), ("cmc_off", ctypes.c_int), ("aw_off", ctypes.c_int),
+                ("feature_dim", ctypes.c_int)]
+
+
 ASSO_CODES = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3, "ct_dist": 4}
 
 _lib = None
@@ -95,6 +103,11 @@ def _declare(lib):
         "tk_ocsort_run": ([vp, vp, vp, ci, vp, vp, vp, vp, vp], ci),
         "tk_ocsort_status": ([vp, P(ci), vp], ci),
         "tk_ocsort_destroy": ([vp], ci),
+        "tk_deepocsort_create": ([P(DeepocsortParams), ci, ci, ci, P(vp)], ci),
+        "tk_deepocsort_reset": ([vp, vp], ci),
+        "tk_deepocsort_run": ([vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp], ci),
+        "tk_deepocsort_status": ([vp, P(ci), vp], ci),
+        "tk_deepocsort_destroy": ([vp], ci),
         "tk_strongsort_create": ([P(StrongsortParams), ci, ci, ci, P(vp)], ci),
         "tk_strongsort_reset": ([vp, ci, vp], ci),
         "tk_strongsort_run": ([vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp], ci),

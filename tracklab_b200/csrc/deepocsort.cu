@@ -21,6 +21,7 @@
 //   q5  first round: plain IoU, VDC term multiplied by the class column.
 //   q6  embedding EMA, appearance matrix and adaptive weights in float32; everything else float64.
 #include "lap.cuh"
+#include "lsap_scipy.cuh"
 #include "oc_boxes.cuh"
 #include "tk_common.cuh"
 #include "trackkern.h"
@@ -30,6 +31,7 @@ namespace {
 using namespace tk;
 
 constexpr int DOC_THREADS = 256;
+constexpr int DOC_LSAP_MAX = 512;   // rows + columns of the extended assignment problem
 constexpr int DRING = 8;   // observations of ages age-delta_t .. age (delta_t <= 7)
 
 struct DocParams {
@@ -81,17 +83,14 @@ struct DocScratch {
 
 // The unmatched lists of the second round keep raw duplicates (q1): up to 2 capd detections x (cap + capd) trackers.
 __host__ __device__ inline size_t doc_mat(int cap, int capd) { return (size_t)(2 * capd + 2) * (cap + capd + 2); }
-__host__ __device__ inline size_t doc_cost(int cap, int capd) {
-    const size_t m = (size_t)((2 * capd + 2) > (cap + capd + 2) ? (2 * capd + 2) : (cap + capd + 2));
-    return m * (m + 2);
-}
+__host__ __device__ inline size_t doc_cost(int cap, int capd) { return doc_mat(cap, capd); }
 
 __host__ __device__ inline size_t doc_scratch_bytes(int cap, int capd) {
     const size_t mat = doc_mat(cap, capd);
     const size_t lst = (size_t)2 * (cap + capd) + 8;
     size_t s = 0;
     s += doc_al(mat * sizeof(double));                                  // iou / left
-    s += doc_al(doc_cost(cap, capd) * sizeof(double));                  // cost (smaller side as rows, lap_pitch leading dimension)
+    s += doc_al(doc_cost(cap, capd) * sizeof(double));                  // cost, row-major like iou
     s += doc_al((size_t)cap * 4 * sizeof(double)) + 2 * doc_al((size_t)cap * 5 * sizeof(double)) + doc_al((size_t)capd * sizeof(double));
     s += doc_al(mat * sizeof(float)) + doc_al((size_t)capd * sizeof(float)) + doc_al((size_t)cap * sizeof(float));
     s += 11 * doc_al(lst * sizeof(int));
@@ -368,45 +367,71 @@ __device__ void doc_update_emb_warp(float* emb, const float* det, double alpha, 
 
 struct DocShared {
     int nd, nt, n_ud, n_ut, n_pairs, n_match, maxflag, lap_ok, n_gd, out_n;
-    unsigned long long dmax_bits;
-    double lap_u[LAP_MAX_COLS];
-    int col4row[LAP_MAX_COLS], row4col[LAP_MAX_COLS], path[LAP_MAX_COLS];
+    unsigned long long dmax_bits, cmax_key;
+    double u[DOC_LSAP_MAX], v[DOC_LSAP_MAX], spc[DOC_LSAP_MAX];
+    int path[DOC_LSAP_MAX], col4row[DOC_LSAP_MAX], row4col[DOC_LSAP_MAX], remaining[DOC_LSAP_MAX];
+    unsigned char SR[DOC_LSAP_MAX], SC[DOC_LSAP_MAX];
 };
 
-// min-cost assignment of the smaller side (lap.lapjv(extend_cost=True) of association.py:206): match[d] = t or -1
-__device__ void doc_solve(const double* C, int nd, int nt, int* match, DocShared* sh, int* status) {
-    for (int i = threadIdx.x; i < nd; i += blockDim.x) match[i] = -1;
-    __syncthreads();
-    const bool d_rows = nd <= nt;
-    const int nr = d_rows ? nd : nt, nc = d_rows ? nt : nd;
-    const bool ok = lap_solve_cta(C, lap_pitch(nc), nr, nc, false, sh->lap_u, sh->col4row, sh->row4col, sh->path, &sh->lap_ok);
-    if (!ok) { if (threadIdx.x == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); return; }
-    for (int r = threadIdx.x; r < nr; r += blockDim.x) {
-        const int c = sh->col4row[r];
-        if (d_rows) match[r] = c; else match[c] = r;
+// lap.lapjv(cost, extend_cost=True) of association.py:206 on the nd x nt matrix C (row-major): lap 0.5.12 is not vendored, so - like
+// the goldens' stand-in (oracle/ref_shims/lap) - its published extension is solved: the (nd+nt)^2 matrix with C in the top-left block,
+// cost.max() + 1 in the off-diagonal blocks and 0 in the bottom-right block, by scipy's solver INCLUDING its tie-breaking
+// (lsap_scipy.cuh). Ties are real here: all zero-overlap pairs of tracks without a velocity cost exactly 0, which of them receives the
+// discarded dummy pair orders `unmatched_detections`, i.e. the birth order, i.e. which tracker is `trackers[-1]` for q1.
+// match[d] = t or -1; *ylast = detection assigned to the last tracker or -1. `cmax` = C.max().
+__device__ void doc_solve(const double* C, int nd, int nt, double cmax, int* match, int* ylast, DocShared* sh, int* status) {
+    if (nd + nt > DOC_LSAP_MAX) {     // cannot happen for cap_tracks + cap_dets <= DOC_LSAP_MAX unless the second-round lists are full of duplicates
+        if (threadIdx.x == 0) { atomicOr(status, TK_DEV_OVERFLOW_ASSIGN); *ylast = -1; }
+        for (int d = threadIdx.x; d < nd; d += blockDim.x) match[d] = -1;
+        __syncthreads();
+        return;
+    }
+    if (warp_id() == 0) {
+        const int N = nd + nt;
+        const double fill = cmax + 1.0;
+        const bool ok = lsap_scipy_warp(N, N, [&](int i, int j) {
+            return (i < nd && j < nt) ? C[(size_t)i * nt + j] : ((i >= nd && j >= nt) ? 0.0 : fill);
+        }, sh->u, sh->v, sh->spc, sh->path, sh->col4row, sh->row4col, sh->remaining, sh->SR, sh->SC);
+        __syncwarp();
+        if (!ok) { if (lane_id() == 0) atomicOr(status, TK_DEV_LAP_INFEASIBLE); }
+        for (int d = lane_id(); d < nd; d += 32) match[d] = (ok && sh->col4row[d] < nt) ? sh->col4row[d] : -1;
+        if (lane_id() == 0) *ylast = (ok && sh->row4col[nt - 1] < nd) ? sh->row4col[nt - 1] : -1;
     }
     __syncthreads();
+}
+
+__device__ __forceinline__ double key_to_double(unsigned long long k) {   // inverse of tk::ordered_key
+    const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
 }
 
 __device__ __forceinline__ int wrap(int i, int n) { return i < 0 ? i + n : i; }
 
 // Apply (tracker, detection) updates given as raw index pairs, in list order per tracker (the same tracker may appear several times,
-// q1): one warp per tracker walks the list; lane 0 does the Kalman work, the warp the embedding EMA.
+// q1). Pass A: one thread per tracker walks the list and does the Kalman work (all trackers in parallel); pass B: one warp per
+// tracker walks it again for the embedding EMA.
 template <class Pair>
 __device__ void doc_apply_updates(DocDev& S, const DocParams& prm, int n_pairs, Pair pair, int nt, int nd, const double* D,
                                   const int* d_idx, const float* det_embs, float* trk_embs, const double* alpha, int* status) {
-    const int nw = blockDim.x >> 5;
-    for (int k = warp_id(); k < nt; k += nw) {
+    for (int k = threadIdx.x; k < nt; k += blockDim.x) {
         const int s = S.list[k];
         for (int i = 0; i < n_pairs; ++i) {
             int pd, pt;
-            if (!pair(i, pd, pt)) continue;
-            if (wrap(pt, nt) != k) continue;
-            const int d = wrap(pd, nd);
-            const double* db = D + (size_t)d_idx[d] * 7;
-            if (lane_id() == 0) doc_track_update(S, s, db, db[5], db[6], prm.delta_t, status);
-            __syncwarp();
-            if (!prm.embedding_off) doc_update_emb_warp(trk_embs + (size_t)s * prm.emb_dim, det_embs + (size_t)d_idx[d] * prm.emb_dim, alpha[d], prm.emb_dim);
+            if (!pair(i, pd, pt) || wrap(pt, nt) != k) continue;
+            const double* db = D + (size_t)d_idx[wrap(pd, nd)] * 7;
+            doc_track_update(S, s, db, db[5], db[6], prm.delta_t, status);
+        }
+    }
+    if (!prm.embedding_off && det_embs) {
+        const int nw = blockDim.x >> 5;
+        for (int k = warp_id(); k < nt; k += nw) {
+            const int s = S.list[k];
+            for (int i = 0; i < n_pairs; ++i) {
+                int pd, pt;
+                if (!pair(i, pd, pt) || wrap(pt, nt) != k) continue;
+                const int d = wrap(pd, nd);
+                doc_update_emb_warp(trk_embs + (size_t)s * prm.emb_dim, det_embs + (size_t)d_idx[d] * prm.emb_dim, alpha[d], prm.emb_dim);
+            }
         }
     }
     __syncthreads();
@@ -544,13 +569,16 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
             } else {
                 const bool use_emb = !prm.embedding_off && DE != nullptr;
                 if (use_emb) {
-                    for (int e = tid; e < nd * nt; e += DOC_THREADS) {    // dets_embs @ trk_embs.T (float32), zero where IoU <= 0
+                    for (int e = warp_id(); e < nd * nt; e += DOC_THREADS / 32) {    // dets_embs @ trk_embs.T (float32), zero where IoU <= 0
                         const int d = e / nt, t = e - d * nt;
-                        const float* a = DE + (size_t)W.d_idx[d] * E;
-                        const float* b = trk_embs + (size_t)S.list[t] * E;
                         float acc = 0.0f;
-                        for (int k = 0; k < E; ++k) acc = fmaf(a[k], b[k], acc);
-                        W.emb[e] = (W.iou[e] <= 0) ? 0.0f : acc;
+                        if (!(W.iou[e] <= 0)) {          // only the overlapping pairs need the dot product
+                            const float* a = DE + (size_t)W.d_idx[d] * E;
+                            const float* b = trk_embs + (size_t)S.list[t] * E;
+                            for (int k = lane_id(); k < E; k += 32) acc = fmaf(a[k], b[k], acc);
+                            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                        }
+                        if (lane_id() == 0) W.emb[e] = acc;
                     }
                     __syncthreads();
                     if (!prm.aw_off) {          // compute_aw_max_metric (association.py:263-288), float32
@@ -578,10 +606,10 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
                         __syncthreads();
                     }
                 }
-                // final_cost = -(iou + angle_diff_cost + emb_cost), stored with the smaller side as rows
-                const bool dr = nd <= nt;
-                const int ld = lap_pitch(dr ? nt : nd);
+                // final_cost = -(iou + angle_diff_cost + emb_cost)
                 const float w0 = (float)prm.w_emb;
+                if (tid == 0) sh->cmax_key = 0ull;
+                __syncthreads();
                 for (int e = tid; e < nd * nt; e += DOC_THREADS) {
                     const int d = e / nt, t = e - d * nt;
                     const double* db = D + (size_t)W.d_idx[d] * 7;
@@ -606,13 +634,13 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
                         embc = (double)__fmul_rn(w, W.emb[e]);
                     }
                     const double v = -__dadd_rn(__dadd_rn(W.iou[e], vdc), embc);
-                    if (dr) W.cost[(size_t)d * ld + t] = v; else W.cost[(size_t)t * ld + d] = v;
+                    W.cost[e] = v;
+                    atomicMax(&sh->cmax_key, ordered_key(v));
                 }
                 __syncthreads();
-                doc_solve(W.cost, nd, nt, W.match, sh, status);
+                doc_solve(W.cost, nd, nt, key_to_double(sh->cmax_key), W.match, &sh->lap_ok, sh, status);
                 if (tid == 0) {                 // [[y[i], i] for i in x] (q1)
-                    int ylast = -1;
-                    for (int d = 0; d < nd; ++d) if (W.match[d] == nt - 1) ylast = d;
+                    const int ylast = sh->lap_ok;
                     for (int d = 0; d < nd; ++d) {
                         const int i = W.match[d];
                         W.p0[d] = i >= 0 ? d : ylast;
@@ -656,10 +684,8 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
         // ---- second round: OCR on the last observations (ocsort.py:474-508) ---------------------------------------------------
         if (sh->n_ud > 0 && sh->n_ut > 0) {
             const int nud = sh->n_ud, nut = sh->n_ut;
-            if (tid == 0) { sh->maxflag = 0; sh->dmax_bits = 0ull; }
+            if (tid == 0) { sh->maxflag = 0; sh->dmax_bits = 0ull; sh->cmax_key = 0ull; }
             __syncthreads();
-            const bool dr = nud <= nut;
-            const int l2 = lap_pitch(dr ? nut : nud);
             if (prm.asso == TK_ASSO_CT_DIST) {
                 for (int e = tid; e < nud * nut; e += DOC_THREADS) {
                     const double dd = centre_dist(D + (size_t)W.d_idx[wrap(W.un_d[e / nut], nd)] * 7, W.last_snap + 5 * wrap(W.un_t[e % nut], nt));
@@ -674,15 +700,15 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
                 const double v = prm.asso == TK_ASSO_CT_DIST ? 1.0 - W.iou[e] / dmax
                                                              : asso_value(prm.asso, D + (size_t)W.d_idx[wrap(W.un_d[a], nd)] * 7, W.last_snap + 5 * wrap(W.un_t[b], nt));
                 W.iou[e] = v;
-                if (dr) W.cost[(size_t)a * l2 + b] = -v; else W.cost[(size_t)b * l2 + a] = -v;
+                W.cost[e] = -v;
+                atomicMax(&sh->cmax_key, ordered_key(-v));
                 if (v > prm.iou_threshold) sh->maxflag = 1;
             }
             __syncthreads();
             if (sh->maxflag) {
-                doc_solve(W.cost, nud, nut, W.match, sh, status);
+                doc_solve(W.cost, nud, nut, key_to_double(sh->cmax_key), W.match, &sh->lap_ok, sh, status);
                 if (tid == 0) {
-                    int ylast = -1;
-                    for (int a = 0; a < nud; ++a) if (W.match[a] == nut - 1) ylast = a;
+                    const int ylast = sh->lap_ok;
                     int ng = 0;
                     for (int a = 0; a < nud; ++a) {
                         const int i = W.match[a];
@@ -826,7 +852,7 @@ extern "C" {
 
 int tk_deepocsort_create(const tk_deepocsort_params* p, int n_seq, int cap_tracks, int cap_dets, void** handle) {
     if (!p || !handle || n_seq <= 0 || cap_tracks <= 0 || cap_dets <= 0) return TK_ERR_ARG;
-    if (cap_tracks + cap_dets > tk::LAP_MAX_COLS || 2 * cap_dets > tk::LAP_MAX_COLS) return TK_ERR_CAPACITY;   // second-round lists keep duplicates
+    if (cap_dets + cap_tracks > DOC_LSAP_MAX) return TK_ERR_CAPACITY;   // rows + columns of the extended assignment problem
     if (p->delta_t < 1 || p->delta_t >= DRING || p->asso_func < 0 || p->asso_func > TK_ASSO_CT_DIST) return TK_ERR_ARG;
     if (!p->embedding_off && p->feature_dim <= 0) return TK_ERR_ARG;
     DocHandle* h = new DocHandle();

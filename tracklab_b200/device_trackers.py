@@ -122,6 +122,66 @@ class OCSortDevice(_VideoTrackerDevice):
                                        _lib.ASSO_CODES[asso_func], int(bool(use_byte))), n_seq, cap_tracks, cap_dets, device)
 
 
+class DeepOCSortDevice(_VideoTrackerDevice):
+    """Deep OC-SORT for ``n_seq`` independent videos (C ABI: tk_deepocsort_*).
+
+    Mirrors OCSort(model_weights, device, fp16, **hyperparams) of the deep_oc_sort plugin + the wrapper's ``min_confidence`` filter
+    (/root/reference/plugins/track/deep_oc_sort/ocsort.py:324-372, /root/reference/tracklab/wrappers/track/deep_oc_sort_api.py:57-67)
+    with the plugin's constructor defaults; the in-tracker ReID forward and the camera-motion estimator are separate stages whose
+    outputs (embeddings float32 [N,E], affines float64 [n_seq,F,2,3]) are passed to ``run``."""
+
+    _prefix = "deepocsort"
+
+    def __init__(self, feature_dim, det_thresh=0.0, max_age=30, min_hits=3, iou_threshold=0.3, delta_t=3, asso_func="iou", inertia=0.2,
+                 w_association_emb=0.75, alpha_fixed_emb=0.95, aw_param=0.5, embedding_off=False, cmc_off=False, aw_off=False,
+                 new_kf_off=False, min_confidence=0.4, n_seq=1, cap_tracks=128, cap_dets=128, device="cuda:0"):
+        if new_kf_off:
+            raise _lib.TrackKernError("new_kf_off=True (the 7-d SORT filter inside Deep OC-SORT) is not built; the reference default is False")
+        if asso_func not in _lib.ASSO_CODES:
+            raise _lib.TrackKernError(f"asso_func {asso_func!r} not supported on device (iou/giou/diou/ciou/ct_dist)")
+        self.feature_dim = int(feature_dim)
+        self.embedding_off, self.cmc_off = bool(embedding_off), bool(cmc_off)
+        self._create(_lib.DeepocsortParams(det_thresh, iou_threshold, inertia, min_confidence, w_association_emb, alpha_fixed_emb, aw_param,
+                                           max_age, min_hits, delta_t, _lib.ASSO_CODES[asso_func], int(self.embedding_off),
+                                           int(self.cmc_off), int(bool(aw_off)), self.feature_dim), n_seq, cap_tracks, cap_dets, device)
+
+    def reset(self, keep_id_counter: bool = False):
+        with torch.cuda.device(self.device):
+            _lib.check(self._fn["reset"](self.handle, _stream_ptr()), "tk_deepocsort_reset")
+
+    def run(self, dets: torch.Tensor, offsets: torch.Tensor, embeddings: torch.Tensor | None = None, affines: torch.Tensor | None = None,
+            out_rows: torch.Tensor | None = None, out_start: torch.Tensor | None = None, out_count: torch.Tensor | None = None):
+        """dets float64 [N,7], offsets int32 [n_seq,F+1], embeddings float32 [N,E], affines float64 [n_seq,F,2,3] (device).
+        Returns (out_rows, out_frame_count, out_count), nothing synchronised."""
+        _require_cuda(dets, "dets"); _require_cuda(offsets, "offsets")
+        assert dets.dtype == torch.float64 and dets.is_contiguous()
+        assert offsets.dtype == torch.int32 and offsets.is_contiguous() and offsets.shape[0] == self.n_seq
+        n_frames = offsets.shape[1] - 1
+        if not self.embedding_off:
+            if embeddings is None:
+                raise _lib.TrackKernError("DeepOCSortDevice.run: embeddings are required unless embedding_off")
+            _require_cuda(embeddings, "embeddings")
+            assert embeddings.dtype == torch.float32 and embeddings.is_contiguous() and embeddings.shape == (dets.shape[0], self.feature_dim)
+        if not self.cmc_off:
+            if affines is None:
+                raise _lib.TrackKernError("DeepOCSortDevice.run: one 2x3 affine per frame is required unless cmc_off")
+            _require_cuda(affines, "affines")
+            assert affines.dtype == torch.float64 and affines.is_contiguous() and tuple(affines.shape) == (self.n_seq, n_frames, 2, 3)
+        if out_rows is None:
+            out_rows = torch.empty((max(1, dets.shape[0]), 8), dtype=torch.float64, device=dets.device)
+        if out_start is None:
+            out_start = offsets[:, 0].contiguous()
+        if out_count is None:
+            out_count = torch.zeros(self.n_seq, dtype=torch.int32, device=dets.device)
+        out_fc = torch.empty((self.n_seq, n_frames), dtype=torch.int32, device=dets.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._fn["run"](self.handle, dets.data_ptr(), embeddings.data_ptr() if embeddings is not None else None,
+                                       affines.data_ptr() if affines is not None else None, offsets.data_ptr(), n_frames,
+                                       out_rows.data_ptr(), out_start.data_ptr(), out_fc.data_ptr(), out_count.data_ptr(),
+                                       int(out_rows.shape[0]), _stream_ptr()), "tk_deepocsort_run")
+        return out_rows, out_fc, out_count
+
+
 class StrongSortDevice(_VideoTrackerDevice):
     """StrongSORT association for ``n_seq`` videos with externally supplied ReID features (C ABI: tk_strongsort_*).
 
