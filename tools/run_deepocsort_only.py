@@ -23,3 +23,15 @@ for _ in range(3):
     torch.cuda.synchronize()
     print("deepocsort", F, "frames:", e0.elapsed_time(e1) * 1e3 / F, "us/frame", int(cnt.item()), "rows,", len(video.dets) / F, "det/frame, E", E)
 trk.check_status()
+
+import ctypes
+from tracklab_b200 import _lib
+lib = _lib.load()
+if hasattr(lib, "tk_debug_deepocsort_phases"):      # library built with EXTRA=-DTK_PHASE_PROF
+    buf = (ctypes.c_ulonglong * 32)()
+    lib.tk_debug_deepocsort_phases(buf, 1)
+    trk.reset(); trk.run(dets, offs, embs, aff); torch.cuda.synchronize()
+    lib.tk_debug_deepocsort_phases(buf, 0)
+    names = {0: "filter", 1: "cmc+alpha", 2: "predict", 3: "snapshot", 4: "round1 lists", 5: "update1", 6: "ocr", 7: "miss", 8: "birth", 9: "out+death",
+             10: "round1 iou/emb/cost (inside 4)", 11: "round1 solver (inside 4)"}
+    print("phase cycles/frame:", ", ".join(f"{names.get(k, k)} {buf[k] / F:.0f}" for k in range(12)), "| total", int(sum(buf[:10]) / F + (buf[10] + buf[11]) / F))

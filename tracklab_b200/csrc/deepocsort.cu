@@ -30,6 +30,14 @@ namespace {
 
 using namespace tk;
 
+// Optional per-phase cycle accounting (build with -DTK_PHASE_PROF), read with tk_debug_deepocsort_phases().
+#ifdef TK_PHASE_PROF
+__device__ unsigned long long g_doc_prof[32];
+#define PH(k) do { __syncthreads(); if (threadIdx.x == 0) { const long long _t = clock64(); g_doc_prof[k] += (unsigned long long)(_t - ph_t0); ph_t0 = _t; } } while (0)
+#else
+#define PH(k) do { } while (0)
+#endif
+
 constexpr int DOC_THREADS = 256;
 constexpr int DOC_LSAP_MAX = 512;   // rows + columns of the extended assignment problem
 constexpr int DRING = 8;   // observations of ages age-delta_t .. age (delta_t <= 7)
@@ -159,43 +167,6 @@ __device__ bool inv4(const double* A, double* inv) {
     return true;
 }
 
-// KalmanFilterNew.update with measurement z and diagonal R (kalmanfilter.py:531-569), H = [I4 0]
-__device__ bool kf8_correct(double* x, double* P, const double* z, const double* rdiag) {
-    double S[16], SI[16], K[32], y[4];
-    for (int i = 0; i < 4; ++i) y[i] = __dsub_rn(z[i], x[i]);
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) S[i * 4 + j] = P[i * 8 + j] + (i == j ? rdiag[i] : 0.0);
-    if (!inv4(S, SI)) return false;
-    for (int i = 0; i < 8; ++i)
-        for (int j = 0; j < 4; ++j) {
-            double acc = 0.0;
-            for (int k = 0; k < 4; ++k) acc += P[i * 8 + k] * SI[k * 4 + j];      // K = P H^T S^-1
-            K[i * 4 + j] = acc;
-        }
-    for (int i = 0; i < 8; ++i) {
-        double acc = 0.0;
-        for (int k = 0; k < 4; ++k) acc += K[i * 4 + k] * y[k];
-        x[i] += acc;
-    }
-    // P = (I - K H) P (I - K H)^T + K R K^T
-    double T[64];
-    for (int i = 0; i < 8; ++i)
-        for (int j = 0; j < 8; ++j) {
-            double acc = P[i * 8 + j];
-            for (int k = 0; k < 4; ++k) acc -= K[i * 4 + k] * P[k * 8 + j];
-            T[i * 8 + j] = acc;                                                       // (I - K H) P
-        }
-    for (int i = 0; i < 8; ++i)
-        for (int j = 0; j < 8; ++j) {
-            double acc = T[i * 8 + j];
-            for (int k = 0; k < 4; ++k) acc -= T[i * 8 + k] * K[j * 4 + k];           // ... (I - K H)^T
-            double krk = 0.0;
-            for (int k = 0; k < 4; ++k) krk += K[i * 4 + k] * rdiag[k] * K[j * 4 + k];
-            P[i * 8 + j] = acc + krk;
-        }
-    return true;
-}
-
 // big_m = kron(I4, m): x <- big_m x (+ t on the first two), P <- big_m P big_m^T   (kalmanfilter.py:393-397)
 __device__ void kf8_affine(double* x, double* P, const double* A) {
     const double m00 = A[0], m01 = A[1], t0 = A[2], m10 = A[3], m11 = A[4], t1 = A[5];
@@ -266,74 +237,148 @@ __device__ void doc_track_affine(DocDev& S, int s, const double* A, int delta_t)
     }
 }
 
-// KalmanBoxTracker.update(bbox) (ocsort.py:203-238) incl. KalmanFilterNew.update with the ORU replay (kalmanfilter.py:432-481, 483-569)
-__device__ void doc_track_update(DocDev& S, int s, const double* bbox5, double cls, double det_id, int delta_t, int* status) {
+// ---- warp-cooperative filter arithmetic: x[8], P[64] and the temporaries live in a per-warp shared buffer, every lane owns two
+// entries of the 8x8 products. A single thread doing these products keeps ~200 doubles live in local memory (335 us per frame for
+// ~36 tracks, measured with -DTK_PHASE_PROF); the cooperative form takes a few microseconds.
+struct KfBuf { double x[8], P[64], T[64], K[32], S[16], SI[16], y[4]; int ok; };
+
+__device__ void kf8_predict_warp(KfBuf& B, const double* q) {
+    const int l = lane_id();
+    __syncwarp();
+    for (int e = l; e < 64; e += 32) {
+        const int i = e >> 3, c = e & 7;
+        double a = B.P[e];
+        if (i < 4) a = __dadd_rn(a, B.P[(i + 4) * 8 + c]);                       // (F P)[i][c]
+        if (c < 4) {
+            double b2 = B.P[i * 8 + c + 4];
+            if (i < 4) b2 = __dadd_rn(b2, B.P[(i + 4) * 8 + c + 4]);             // (F P)[i][c+4]
+            a = __dadd_rn(a, b2);
+        }
+        if (i == c) a = __dadd_rn(a, q[i]);
+        B.T[e] = a;
+    }
+    double xn = 0.0;
+    if (l < 8) xn = l < 4 ? __dadd_rn(B.x[l], B.x[l + 4]) : B.x[l];
+    __syncwarp();
+    for (int e = l; e < 64; e += 32) B.P[e] = B.T[e];
+    if (l < 8) B.x[l] = xn;
+    __syncwarp();
+}
+
+__device__ bool kf8_correct_warp(KfBuf& B, const double* z, const double* rdiag) {
+    const int l = lane_id();
+    __syncwarp();
+    if (l < 16) { const int a = l >> 2, b = l & 3; B.S[l] = B.P[a * 8 + b] + (a == b ? rdiag[a] : 0.0); }
+    if (l < 4) B.y[l] = __dsub_rn(z[l], B.x[l]);
+    __syncwarp();
+    if (l == 0) B.ok = inv4(B.S, B.SI) ? 1 : 0;
+    __syncwarp();
+    if (!B.ok) return false;
+    {   // K = P H^T S^-1: lane -> (i, j)
+        const int i = l >> 2, j = l & 3;
+        double acc = 0.0;
+        for (int k = 0; k < 4; ++k) acc += B.P[i * 8 + k] * B.SI[k * 4 + j];
+        B.K[l] = acc;
+    }
+    __syncwarp();
+    double xn = 0.0;
+    if (l < 8) { double acc = 0.0; for (int k = 0; k < 4; ++k) acc += B.K[l * 4 + k] * B.y[k]; xn = B.x[l] + acc; }
+    for (int e = l; e < 64; e += 32) {          // T = (I - K H) P
+        const int i = e >> 3, c = e & 7;
+        double acc = B.P[e];
+        for (int k = 0; k < 4; ++k) acc -= B.K[i * 4 + k] * B.P[k * 8 + c];
+        B.T[e] = acc;
+    }
+    __syncwarp();
+    if (l < 8) B.x[l] = xn;
+    for (int e = l; e < 64; e += 32) {          // P = T (I - K H)^T + K R K^T
+        const int i = e >> 3, c = e & 7;
+        double acc = B.T[e], krk = 0.0;
+        for (int k = 0; k < 4; ++k) acc -= B.T[i * 8 + k] * B.K[c * 4 + k];
+        for (int k = 0; k < 4; ++k) krk += B.K[i * 4 + k] * rdiag[k] * B.K[c * 4 + k];
+        B.P[e] = acc + krk;
+    }
+    __syncwarp();
+    return true;
+}
+
+// KalmanBoxTracker.update(bbox) (ocsort.py:203-238) incl. KalmanFilterNew.update with the ORU replay (kalmanfilter.py:432-481, 483-569).
+// One warp: lane 0 does the book-keeping, all lanes the filter arithmetic.
+__device__ void doc_track_update(DocDev& S, int s, const double* bbox5, double cls, double det_id, int delta_t, int* status, KfBuf& B) {
+    const int l = lane_id();
     double* lo = S.last_obs + (size_t)s * 5;
-    const int age = S.age[s];
-    S.frozen_flag[s] = 0;
-    S.cls[s] = cls;
-    if (sum5(lo) >= 0) {
-        const double* prev = nullptr;
-        for (int dt = delta_t; dt >= 1; --dt) { prev = obs_at(S, s, age - dt); if (prev) break; }
-        if (!prev) prev = lo;
-        const double cx1 = (prev[0] + prev[2]) / 2.0, cy1 = (prev[1] + prev[3]) / 2.0;
-        const double cx2 = (bbox5[0] + bbox5[2]) / 2.0, cy2 = (bbox5[1] + bbox5[3]) / 2.0;
-        const double dy = cy2 - cy1, dx = cx2 - cx1;
-        const double norm = sqrt(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx))) + 1e-6;
-        S.vel[(size_t)s * 2] = dy / norm; S.vel[(size_t)s * 2 + 1] = dx / norm; S.has_vel[s] = 1;
+    if (l == 0) {
+        const int age = S.age[s];
+        S.frozen_flag[s] = 0;
+        S.cls[s] = cls;
+        if (sum5(lo) >= 0) {
+            const double* prev = nullptr;
+            for (int dt = delta_t; dt >= 1; --dt) { prev = obs_at(S, s, age - dt); if (prev) break; }
+            if (!prev) prev = lo;
+            const double cx1 = (prev[0] + prev[2]) / 2.0, cy1 = (prev[1] + prev[3]) / 2.0;
+            const double cx2 = (bbox5[0] + bbox5[2]) / 2.0, cy2 = (bbox5[1] + bbox5[3]) / 2.0;
+            const double dy = cy2 - cy1, dx = cx2 - cx1;
+            const double norm = sqrt(__dadd_rn(__dmul_rn(dy, dy), __dmul_rn(dx, dx))) + 1e-6;
+            S.vel[(size_t)s * 2] = dy / norm; S.vel[(size_t)s * 2 + 1] = dx / norm; S.has_vel[s] = 1;
+        }
+        // last_observation = bbox; observations[age] = bbox (one object). The previous newest observation keeps living in the dict.
+        const int la = S.last_age[s];
+        if (la >= 0 && la != age) {
+            const int r = la % DRING;
+            S.ring_age[(size_t)s * DRING + r] = la;
+            for (int i = 0; i < 5; ++i) S.ring_obs[((size_t)s * DRING + r) * 5 + i] = lo[i];
+        }
+        for (int i = 0; i < 5; ++i) lo[i] = bbox5[i];
+        S.last_age[s] = age;
+        S.tsu[s] = 0;
+        S.streak[s] += 1;
+        S.hist_len[s] += 1;                                     // history_obs.append(z)
+        S.det_id[s] = det_id;
     }
-    // last_observation = bbox; observations[age] = bbox (one object). The previous newest observation keeps living in the dict.
-    const int la = S.last_age[s];
-    if (la >= 0 && la != age) {
-        const int r = la % DRING;
-        S.ring_age[(size_t)s * DRING + r] = la;
-        for (int i = 0; i < 5; ++i) S.ring_obs[((size_t)s * DRING + r) * 5 + i] = lo[i];
-    }
-    for (int i = 0; i < 5; ++i) lo[i] = bbox5[i];
-    S.last_age[s] = age;
-    S.tsu[s] = 0;
-    S.streak[s] += 1;
-    double x[8], P[64], z[4], rdiag[4];
-    for (int i = 0; i < 8; ++i) x[i] = S.x[(size_t)s * 8 + i];
+    __syncwarp();
+    double z[4], rdiag[4];
+    box_to_z8(bbox5, z);
     {   // R from the state BEFORE the replay (q4)  ocsort.py:234
-        const double m = 1.0 / 20, mw = __dmul_rn(m, x[2]), mh = __dmul_rn(m, x[3]);
+        const double m = 1.0 / 20, mw = __dmul_rn(m, S.x[(size_t)s * 8 + 2]), mh = __dmul_rn(m, S.x[(size_t)s * 8 + 3]);
         rdiag[0] = __dmul_rn(mw, mw); rdiag[1] = __dmul_rn(mh, mh); rdiag[2] = rdiag[0]; rdiag[3] = rdiag[1];
     }
-    box_to_z8(bbox5, z);
-    S.hist_len[s] += 1;                                     // history_obs.append(z)
     bool ok = true;
-    if (!S.observed[s] && S.has_saved[s]) {               // unfreeze (kalmanfilter.py:432-481)
+    const bool replay = !S.observed[s] && S.has_saved[s];
+    if (replay) {               // unfreeze (kalmanfilter.py:432-481)
         const int full_len = S.hist_len[s], n = S.saved_n[s];
-        for (int i = 0; i < 8; ++i) x[i] = S.sx[(size_t)s * 8 + i];
-        for (int i = 0; i < 64; ++i) P[i] = S.sP[(size_t)s * 64 + i];
+        if (l < 8) B.x[l] = S.sx[(size_t)s * 8 + l];
+        for (int e = l; e < 64; e += 32) B.P[e] = S.sP[(size_t)s * 64 + e];
         const double* lm = S.s_last + (size_t)s * 4;
         const double x1 = lm[0], y1 = lm[1], w1 = sqrt(lm[2] * lm[3]), h1 = sqrt(lm[2] / lm[3]);
         const double x2 = z[0], y2 = z[1], w2 = sqrt(z[2] * z[3]), h2 = sqrt(z[2] / z[3]);
         const int gap = (full_len - 1) - (n - 2);
         const double g = (double)gap;
         const double dx = (x2 - x1) / g, dy = (y2 - y1) / g, dw = (w2 - w1) / g, dh = (h2 - h1) / g;
-        const double one4[4] = {1.0, 1.0, 1.0, 1.0}, one8[8] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+        const double one8[8] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
         double vz[4] = {z[0], z[1], z[2], z[3]};
         for (int i = 0; i < gap; ++i) {
             const double k = (double)(i + 1);
             const double ww = w1 + k * dw, hh = h1 + k * dh;
             vz[0] = x1 + k * dx; vz[1] = y1 + k * dy; vz[2] = ww * hh; vz[3] = ww / hh;
-            ok = kf8_correct(x, P, vz, one4) && ok;
-            if (i != gap - 1) kf8_predict(x, P, one8);
+            ok = kf8_correct_warp(B, vz, one8) && ok;
+            if (i != gap - 1) kf8_predict_warp(B, one8);
         }
-        S.hist_len[s] = (n - 1) + gap;
-        for (int i = 0; i < 4; ++i) S.last_entry[(size_t)s * 4 + i] = vz[i];      // history_obs[-1] is the last virtual box
-        S.has_saved[s] = 0;
+        if (l == 0) {
+            S.hist_len[s] = (n - 1) + gap;
+            for (int i = 0; i < 4; ++i) S.last_entry[(size_t)s * 4 + i] = vz[i];      // history_obs[-1] is the last virtual box
+            S.has_saved[s] = 0;
+        }
     } else {
-        for (int i = 0; i < 64; ++i) P[i] = S.P[(size_t)s * 64 + i];
-        for (int i = 0; i < 4; ++i) S.last_entry[(size_t)s * 4 + i] = z[i];
+        if (l < 8) B.x[l] = S.x[(size_t)s * 8 + l];
+        for (int e = l; e < 64; e += 32) B.P[e] = S.P[(size_t)s * 64 + e];
+        if (l < 4) S.last_entry[(size_t)s * 4 + l] = z[l];
     }
-    S.observed[s] = 1;
-    ok = kf8_correct(x, P, z, rdiag) && ok;
-    if (!ok) atomicOr(status, TK_DEV_BAD_CHOLESKY);
-    for (int i = 0; i < 8; ++i) S.x[(size_t)s * 8 + i] = x[i];
-    for (int i = 0; i < 64; ++i) S.P[(size_t)s * 64 + i] = P[i];
-    S.det_id[s] = det_id;
+    ok = kf8_correct_warp(B, z, rdiag) && ok;
+    if (!ok && l == 0) atomicOr(status, TK_DEV_BAD_CHOLESKY);
+    if (l < 8) S.x[(size_t)s * 8 + l] = B.x[l];
+    for (int e = l; e < 64; e += 32) S.P[(size_t)s * 64 + e] = B.P[e];
+    if (l == 0) S.observed[s] = 1;
+    __syncwarp();
 }
 
 // KalmanBoxTracker.update(None) (ocsort.py:239-241): freeze on the observed -> unobserved transition (kalmanfilter.py:506-518)
@@ -408,30 +453,22 @@ __device__ __forceinline__ double key_to_double(unsigned long long k) {   // inv
 __device__ __forceinline__ int wrap(int i, int n) { return i < 0 ? i + n : i; }
 
 // Apply (tracker, detection) updates given as raw index pairs, in list order per tracker (the same tracker may appear several times,
-// q1). Pass A: one thread per tracker walks the list and does the Kalman work (all trackers in parallel); pass B: one warp per
-// tracker walks it again for the embedding EMA.
+// q1): one warp per tracker walks the list; Kalman update and embedding EMA are warp-cooperative.
 template <class Pair>
 __device__ void doc_apply_updates(DocDev& S, const DocParams& prm, int n_pairs, Pair pair, int nt, int nd, const double* D,
-                                  const int* d_idx, const float* det_embs, float* trk_embs, const double* alpha, int* status) {
-    for (int k = threadIdx.x; k < nt; k += blockDim.x) {
+                                  const int* d_idx, const float* det_embs, float* trk_embs, const double* alpha, int* status, KfBuf* bufs) {
+    const int nw = blockDim.x >> 5;
+    KfBuf& B = bufs[warp_id()];
+    for (int k = warp_id(); k < nt; k += nw) {
         const int s = S.list[k];
         for (int i = 0; i < n_pairs; ++i) {
             int pd, pt;
             if (!pair(i, pd, pt) || wrap(pt, nt) != k) continue;
-            const double* db = D + (size_t)d_idx[wrap(pd, nd)] * 7;
-            doc_track_update(S, s, db, db[5], db[6], prm.delta_t, status);
-        }
-    }
-    if (!prm.embedding_off && det_embs) {
-        const int nw = blockDim.x >> 5;
-        for (int k = warp_id(); k < nt; k += nw) {
-            const int s = S.list[k];
-            for (int i = 0; i < n_pairs; ++i) {
-                int pd, pt;
-                if (!pair(i, pd, pt) || wrap(pt, nt) != k) continue;
-                const int d = wrap(pd, nd);
+            const int d = wrap(pd, nd);
+            const double* db = D + (size_t)d_idx[d] * 7;
+            doc_track_update(S, s, db, db[5], db[6], prm.delta_t, status, B);
+            if (!prm.embedding_off && det_embs)
                 doc_update_emb_warp(trk_embs + (size_t)s * prm.emb_dim, det_embs + (size_t)d_idx[d] * prm.emb_dim, alpha[d], prm.emb_dim);
-            }
         }
     }
     __syncthreads();
@@ -444,6 +481,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
                         double* __restrict__ out_rows, const int* __restrict__ out_start, int* __restrict__ out_frame_count,
                         int* __restrict__ out_count, int out_capacity_rows) {
     __shared__ DocShared shs;
+    __shared__ KfBuf kfbufs[DOC_THREADS / 32];
     DocShared* sh = &shs;
     const int seq = blockIdx.x, tid = threadIdx.x;
     DocDev S = doc_carve(state_base + (size_t)seq * state_stride, cap);
@@ -455,6 +493,9 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
     if (tid == 0) sh->out_n = out_count[seq];
     __syncthreads();
 
+#ifdef TK_PHASE_PROF
+    long long ph_t0 = clock64();
+#endif
     for (int f = 0; f < n_frames; ++f) {
         const int r0 = offsets[seq * F1 + f], r1 = offsets[seq * F1 + f + 1];
         const int nraw = r1 - r0;
@@ -471,6 +512,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
         const int nd = sh->nd;
         int nt = sh->nt;
 
+        PH(0);
         // ---- CMC (ocsort.py:405-408) -----------------------------------------------------------------------------------------
         if (!prm.cmc_off && affines) {
             const double* A = affines + ((size_t)seq * n_frames + f) * 6;
@@ -482,6 +524,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
             const double trust = (D[(size_t)W.d_idx[d] * 7 + 4] - prm.det_thresh) / (1 - prm.det_thresh);
             W.alpha[d] = prm.alpha_fixed + (1 - prm.alpha_fixed) * (1 - trust);
         }
+        PH(1);
         // ---- predict (ocsort.py:273-299, 420-427) -----------------------------------------------------------------------------
         for (int k = tid; k < nt; k += DOC_THREADS) {
             const int s = S.list[k];
@@ -518,6 +561,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
         }
         __syncthreads();
         nt = sh->nt;
+        PH(2);
         // velocities / last_boxes snapshot / k_previous_obs (ocsort.py:438-440, 22-30)
         for (int k = tid; k < nt; k += DOC_THREADS) {
             const int s = S.list[k];
@@ -531,6 +575,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
         }
         __syncthreads();
 
+        PH(3);
         // ---- first round (association.py:291-360) ---------------------------------------------------------------------------
         if (tid == 0) { sh->n_pairs = 0; sh->n_match = 0; sh->n_ud = 0; sh->n_ut = 0; }
         __syncthreads();
@@ -638,7 +683,9 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
                     atomicMax(&sh->cmax_key, ordered_key(v));
                 }
                 __syncthreads();
+                PH(10);
                 doc_solve(W.cost, nd, nt, key_to_double(sh->cmax_key), W.match, &sh->lap_ok, sh, status);
+                PH(11);
                 if (tid == 0) {                 // [[y[i], i] for i in x] (q1)
                     const int ylast = sh->lap_ok;
                     for (int d = 0; d < nd; ++d) {
@@ -674,13 +721,15 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
             if (tid == 0) sh->n_ut = nt;
             __syncthreads();
         }
+        PH(4);
         // matched updates (ocsort.py:467-469)
         {
             const int nm = sh->n_match;
             doc_apply_updates(S, prm, nm, [&](int i, int& pd, int& pt) { pd = W.m0[i]; pt = W.m1[i]; return true; }, nt, nd, D, W.d_idx,
-                              DE, trk_embs, W.alpha, status);
+                              DE, trk_embs, W.alpha, status, kfbufs);
         }
 
+        PH(5);
         // ---- second round: OCR on the last observations (ocsort.py:474-508) ---------------------------------------------------
         if (sh->n_ud > 0 && sh->n_ut > 0) {
             const int nud = sh->n_ud, nut = sh->n_ut;
@@ -722,7 +771,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
                 }
                 __syncthreads();
                 doc_apply_updates(S, prm, nud, [&](int i, int& pd, int& pt) { pd = W.p0[i]; pt = W.p1[i]; return W.tmp[i] != 0; }, nt, nd, D,
-                                  W.d_idx, DE, trk_embs, W.alpha, status);
+                                  W.d_idx, DE, trk_embs, W.alpha, status, kfbufs);
                 if (tid == 0) {   // np.setdiff1d: sorted unique values of the list that are not in the removed set
                     const int ng = sh->n_gd;
                     for (int pass = 0; pass < 2; ++pass) {
@@ -746,6 +795,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
             }
         }
 
+        PH(6);
         // ---- unmatched trackers: update(None) once per list entry (ocsort.py:510-511) -----------------------------------------
         {
             const int nut = sh->n_ut;
@@ -756,6 +806,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
             }
             __syncthreads();
         }
+        PH(7);
         // ---- births (ocsort.py:513-519) ---------------------------------------------------------------------------------------
         {
             const int nud = sh->n_ud;
@@ -793,6 +844,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
             }
             __syncthreads();
         }
+        PH(8);
         // ---- output + removal (ocsort.py:520-540), reversed list order --------------------------------------------------------
         if (warp_id() == 0) {
             const int ntrk = S.hdr[2];
@@ -826,9 +878,11 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
             if (lane_id() == 0) { S.hdr[2] = keep; S.hdr[5] = nfree2; }
         }
         __syncthreads();
+        PH(9);
     }
     if (tid == 0) out_count[seq] = sh->out_n;
 }
+
 
 struct DocHandle {
     DocParams prm;
@@ -912,6 +966,15 @@ int tk_deepocsort_status(void* handle, int* status_host, void* stream) {
     TK_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return TK_OK;
 }
+
+#ifdef TK_PHASE_PROF
+int tk_debug_deepocsort_phases(unsigned long long* host_out32, int reset) {
+    cudaDeviceSynchronize();
+    if (host_out32) cudaMemcpyFromSymbol(host_out32, g_doc_prof, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_doc_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 int tk_deepocsort_destroy(void* handle) {
     if (!handle) return TK_ERR_ARG;
