@@ -91,39 +91,51 @@ struct DocScratch {
 
 // The unmatched lists of the second round keep raw duplicates (q1): up to 2 capd detections x (cap + capd) trackers.
 __host__ __device__ inline size_t doc_mat(int cap, int capd) { return (size_t)(2 * capd + 2) * (cap + capd + 2); }
-__host__ __device__ inline size_t doc_cost(int cap, int capd) { return doc_mat(cap, capd); }
 
-__host__ __device__ inline size_t doc_scratch_bytes(int cap, int capd) {
-    const size_t mat = doc_mat(cap, capd);
+// Small per-frame arrays always live in shared memory; the three matrices (iou / cost float64, emb float32) do when the frame's
+// problem fits the rest of the CTA's shared memory (B200: ~800-cycle L2 round trips dominated the per-frame latency when every
+// phase went through global scratch), else in the global scratch of the video.
+__host__ __device__ inline size_t doc_small_bytes(int cap, int capd) {
     const size_t lst = (size_t)2 * (cap + capd) + 8;
     size_t s = 0;
-    s += doc_al(mat * sizeof(double));                                  // iou / left
-    s += doc_al(doc_cost(cap, capd) * sizeof(double));                  // cost, row-major like iou
     s += doc_al((size_t)cap * 4 * sizeof(double)) + 2 * doc_al((size_t)cap * 5 * sizeof(double)) + doc_al((size_t)capd * sizeof(double));
-    s += doc_al(mat * sizeof(float)) + doc_al((size_t)capd * sizeof(float)) + doc_al((size_t)cap * sizeof(float));
+    s += doc_al((size_t)capd * sizeof(float)) + doc_al((size_t)cap * sizeof(float));
     s += 11 * doc_al(lst * sizeof(int));
     s += doc_al((size_t)cap);
     return s;
 }
 
-__host__ __device__ inline DocScratch doc_scratch_carve(char* base, int cap, int capd) {
+__host__ __device__ inline size_t doc_scratch_bytes(int cap, int capd) {      // global fallback for the matrices
+    const size_t mat = doc_mat(cap, capd);
+    return 2 * doc_al(mat * sizeof(double)) + doc_al(mat * sizeof(float));
+}
+
+__device__ inline DocScratch doc_scratch_carve(char* small, char* big, int cap, int capd) {
     DocScratch d;
     const size_t mat = doc_mat(cap, capd);
     const size_t lst = (size_t)2 * (cap + capd) + 8;
-    char* p = base;
+    char* p = big;
     d.iou = (double*)p; p += doc_al(mat * sizeof(double));
-    d.cost = (double*)p; p += doc_al(doc_cost(cap, capd) * sizeof(double));
+    d.cost = (double*)p; p += doc_al(mat * sizeof(double));
+    d.emb = (float*)p;
+    p = small;
     d.trk_box = (double*)p; p += doc_al((size_t)cap * 4 * sizeof(double));
     d.kobs = (double*)p; p += doc_al((size_t)cap * 5 * sizeof(double));
     d.last_snap = (double*)p; p += doc_al((size_t)cap * 5 * sizeof(double));
     d.alpha = (double*)p; p += doc_al((size_t)capd * sizeof(double));
-    d.emb = (float*)p; p += doc_al(mat * sizeof(float));
     d.rw = (float*)p; p += doc_al((size_t)capd * sizeof(float));
     d.cw = (float*)p; p += doc_al((size_t)cap * sizeof(float));
     int** lists[11] = {&d.d_idx, &d.un_d, &d.un_t, &d.p0, &d.p1, &d.m0, &d.m1, &d.match, &d.gd, &d.gt, &d.tmp};
     for (int i = 0; i < 11; ++i) { *lists[i] = (int*)p; p += doc_al(lst * sizeof(int)); }
     d.flag_t = (unsigned char*)p;
     return d;
+}
+
+// matrices of an (rows x cols) problem: shared memory when they fit `sm_entries` (20 bytes per entry), else the global scratch
+__device__ __forceinline__ void doc_place_matrices(DocScratch& W, const DocScratch& G, char* sm_mat, size_t sm_entries, size_t entries) {
+    if (entries <= sm_entries) {
+        W.iou = (double*)sm_mat; W.cost = W.iou + sm_entries; W.emb = (float*)(W.cost + sm_entries);
+    } else { W.iou = G.iou; W.cost = G.cost; W.emb = G.emb; }
 }
 
 // ---- 8-d filter (ocsort.py:82-93, kalmanfilter.py:340-379, 531-569) --------------------------------------------------------------
@@ -479,13 +491,18 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
                         float* trk_emb_base, int cap, int capd, const double* __restrict__ dets, const float* __restrict__ embs,
                         const double* __restrict__ affines, const int* __restrict__ offsets, int n_frames,
                         double* __restrict__ out_rows, const int* __restrict__ out_start, int* __restrict__ out_frame_count,
-                        int* __restrict__ out_count, int out_capacity_rows) {
+                        int* __restrict__ out_count, int out_capacity_rows, int sm_mat_entries) {
     __shared__ DocShared shs;
     __shared__ KfBuf kfbufs[DOC_THREADS / 32];
     DocShared* sh = &shs;
     const int seq = blockIdx.x, tid = threadIdx.x;
     DocDev S = doc_carve(state_base + (size_t)seq * state_stride, cap);
-    DocScratch W = doc_scratch_carve(scratch_base + (size_t)seq * scratch_stride, cap, capd);
+    extern __shared__ __align__(16) char doc_dsm[];
+    const size_t small_bytes = doc_small_bytes(cap, capd);
+    const DocScratch G = doc_scratch_carve(doc_dsm, scratch_base + (size_t)seq * scratch_stride, cap, capd);
+    DocScratch W = G;
+    char* sm_mat = doc_dsm + small_bytes;
+    const size_t sm_entries = sm_mat_entries;
     float* trk_embs = trk_emb_base + (size_t)seq * cap * (prm.embedding_off ? 1 : prm.emb_dim);
     int* status = &S.hdr[4];
     const int F1 = n_frames + 1, E = prm.emb_dim;
@@ -584,6 +601,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
             if (tid == 0) sh->n_ud = nd;
             __syncthreads();
         } else if (nd > 0) {
+            doc_place_matrices(W, G, sm_mat, sm_entries, (size_t)nd * nt);
             // IoU, thresholded row / column counts
             for (int k = tid; k < nd + nt; k += DOC_THREADS) W.tmp[k] = 0;
             __syncthreads();
@@ -733,6 +751,7 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
         // ---- second round: OCR on the last observations (ocsort.py:474-508) ---------------------------------------------------
         if (sh->n_ud > 0 && sh->n_ut > 0) {
             const int nud = sh->n_ud, nut = sh->n_ut;
+            doc_place_matrices(W, G, sm_mat, sm_entries, (size_t)nud * nut);
             if (tid == 0) { sh->maxflag = 0; sh->dmax_bits = 0ull; sh->cmax_key = 0ull; }
             __syncthreads();
             if (prm.asso == TK_ASSO_CT_DIST) {
@@ -887,7 +906,8 @@ deepocsort_video_kernel(DocParams prm, char* state_base, size_t state_stride, ch
 struct DocHandle {
     DocParams prm;
     int n_seq, cap, capd;
-    size_t state_stride, scratch_stride;
+    size_t state_stride, scratch_stride, smem_bytes;
+    int sm_mat_entries;
     char *state, *scratch;
     float* trk_emb;
 };
@@ -919,6 +939,17 @@ int tk_deepocsort_create(const tk_deepocsort_params* p, int n_seq, int cap_track
     h->state_stride = (doc_state_bytes(cap_tracks) + 255) & ~(size_t)255;
     h->scratch_stride = (doc_scratch_bytes(cap_tracks, cap_dets) + 255) & ~(size_t)255;
     h->state = nullptr; h->scratch = nullptr; h->trk_emb = nullptr;
+    {   // shared memory: the small arrays + as many matrix entries (20 bytes each) as fit ~190 KB together with the static part
+        const size_t small = doc_small_bytes(cap_tracks, cap_dets);
+        const size_t budget = 190 * 1024 - sizeof(DocShared) - sizeof(KfBuf) * (DOC_THREADS / 32);
+        if (small + 20 * 64 > budget) { delete h; return TK_ERR_CAPACITY; }
+        size_t ent = (budget - small) / 20;
+        const size_t mat = doc_mat(cap_tracks, cap_dets);
+        if (ent > mat) ent = mat;
+        ent &= ~(size_t)1;
+        h->sm_mat_entries = (int)ent;
+        h->smem_bytes = small + ent * 20;
+    }
     cudaError_t e = cudaMalloc((void**)&h->state, h->state_stride * n_seq);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->scratch, h->scratch_stride * n_seq);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->trk_emb, sizeof(float) * (size_t)n_seq * cap_tracks * h->prm.emb_dim);
@@ -950,9 +981,11 @@ int tk_deepocsort_run(void* handle, const double* dets, const float* embeddings,
     if (!h->prm.embedding_off && !embeddings) return TK_ERR_ARG;
     if (!h->prm.cmc_off && !affines) return TK_ERR_ARG;
     if (n_frames == 0) return TK_OK;
-    deepocsort_video_kernel<<<h->n_seq, DOC_THREADS, 0, (cudaStream_t)stream>>>(
+    // the attribute is per kernel function, not per handle: set it before every launch
+    TK_CUDA_TRY(cudaFuncSetAttribute(deepocsort_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    deepocsort_video_kernel<<<h->n_seq, DOC_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(
         h->prm, h->state, h->state_stride, h->scratch, h->scratch_stride, h->trk_emb, h->cap, h->capd, dets, embeddings, affines, offsets,
-        n_frames, out_rows, out_start, out_frame_count, out_count, out_capacity_rows);
+        n_frames, out_rows, out_start, out_frame_count, out_count, out_capacity_rows, h->sm_mat_entries);
     TK_CUDA_TRY(cudaGetLastError());
     return TK_OK;
 }
