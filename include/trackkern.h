@@ -81,6 +81,7 @@ int tk_crop_resize_norm(const unsigned char* frames, int H, int W, long long fra
  */
 #define TK_CROP_RULE_STRONGSORT 0
 #define TK_CROP_RULE_LTWH_ROUNDED 1
+#define TK_CROP_RULE_XYXY_INT 2   /* rows [l,t,r,b,..]: box.astype(int) + NumPy slice (deep_oc_sort/ocsort.py:560-565, bot_sort `_get_features`) */
 int tk_crop_resize_norm_ex(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,
                            const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,
                            const float* mean3, const float* std3, int crop_rule, void* stream);

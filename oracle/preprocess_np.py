@@ -142,12 +142,20 @@ REID_MEAN = (0.485, 0.456, 0.406)
 REID_STD = (0.229, 0.224, 0.225)
 
 
-def reid_crops(frame_rgb, dets_xyxy, out_hw=(256, 128), use_pil=True):
+def xyxy_int_crop_box(bb, W, H):
+    """Deep OC-SORT / BoT-SORT crop (deep_oc_sort/ocsort.py:560-565, bot_sort/bot_sort.py `_get_features`): `box.astype(int)` on
+    x1,y1,x2,y2 and the NumPy slice `img[y1:y2, x1:x2]` (stops clamp at the image size). Negative starts would wrap around in
+    NumPy; boxes are clipped to the image by the detector wrappers, so they are clamped to 0 here (documented deviation)."""
+    x1, y1, x2, y2 = (int(v) for v in np.asarray(bb, dtype=np.float64)[:4].astype(int))
+    return max(x1, 0), max(y1, 0), min(max(x2, 0), W), min(max(y2, 0), H)
+
+
+def reid_crops(frame_rgb, dets_xyxy, out_hw=(256, 128), use_pil=True, rule="strongsort"):
     """float32 [D,3,256,128] network input of the in-tracker ReID (reid_multibackend.py:184-195) for one frame."""
     H, W = frame_rgb.shape[:2]
     out = np.zeros((len(dets_xyxy), 3, out_hw[0], out_hw[1]), dtype=np.float32)
     for i, bb in enumerate(dets_xyxy):
-        x1, y1, x2, y2 = strongsort_crop_box(bb, W, H)
+        x1, y1, x2, y2 = strongsort_crop_box(bb, W, H) if rule == "strongsort" else xyxy_int_crop_box(bb, W, H)
         crop = frame_rgb[y1:y2, x1:x2]
         if use_pil:
             from PIL import Image

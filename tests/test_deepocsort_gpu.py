@@ -91,3 +91,83 @@ def test_deepocsort_empty_and_all_filtered_frames():
     (rows, frames), = _run_device(v2, np.ascontiguousarray(e[keep]), aff, hyper, 0.4)
     _assert_same(rows, frames, ref_rows, ref_frames, box_tol=1e-6)
     assert not np.isin(frames, [5, 6, 7, 12, 13]).any()
+
+
+def test_xyxy_int_crop_rule_matches_pil():
+    """TK_CROP_RULE_XYXY_INT (deep_oc_sort/ocsort.py:560-565: box.astype(int) + NumPy slice) vs PIL on the same crops: identical pixels."""
+    from oracle.preprocess_np import reid_crops
+    from tracklab_b200 import kernels
+    rng = np.random.default_rng(4)
+    frame = rng.integers(0, 256, size=(1, 1080, 1920, 3), dtype=np.uint8)
+    boxes = np.array([[0, 0, 1919.9, 1079.9], [5.7, 9.2, 40.9, 80.1], [1800.3, 900.2, 1950.0, 1100.0], [100, 100, 228, 356],
+                      [100.2, 50.7, 164.9, 178.9], [700.99, 300.01, 760.5, 480.99]], dtype=np.float64)
+    dets = np.concatenate([boxes, np.ones((len(boxes), 3))], axis=1)
+    out = kernels.crop_resize_norm(torch.from_numpy(frame).cuda(), torch.from_numpy(dets).cuda(),
+                                   torch.zeros(len(boxes), dtype=torch.int32, device="cuda"), ltwh_rows=kernels.CROP_RULE_XYXY_INT)
+    ref = reid_crops(frame[0], boxes, rule="xyxy_int")
+    mean = np.asarray(kernels.REID_MEAN, np.float32)[None, :, None, None]
+    std = np.asarray(kernels.REID_STD, np.float32)[None, :, None, None]
+    assert np.array_equal(np.rint((out.cpu().numpy() * std + mean) * 255), np.rint((ref * std + mean) * 255))
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-6
+
+
+def test_deepocsort_module_through_engine_equals_oracle_chain(tmp_path):
+    """modules.DeepOCSORT (drop-in for deep_oc_sort_api.DeepOCSORT) on PNG frames through the engine protocol: its ids must equal
+    the oracle tracker fed with the module's own stage outputs (device ReID features of the xyxy-int crops, device ECC affines
+    composed over skipped frames)."""
+    import types
+
+    import cv2
+
+    from oracle.deepocsort_np import DeepOCSortOracle
+    from tests.golden.make_deepocsort_golden import YAML
+    from tests.test_engine_modules_gpu import _tracking_frames
+    from tracklab_b200 import kernels, modules
+    from tracklab_b200.engine_mirror import OfflineEngineMirror
+    from tracklab_b200.synth import make_frames, make_video
+    F = 14
+    video = make_video(seed=3100, n_frames=F, n_ids=16)
+    frames = make_frames(video, 0, F, device="cpu").numpy()
+    for f in range(F):
+        cv2.imwrite(str(tmp_path / f"{f:06d}.png"), frames[f][..., ::-1])
+    vmd, imd, det = _tracking_frames([video])
+    imd["file_path"] = [str(tmp_path / f"{f:06d}.png") for f in range(F)]
+    det = det[~det["image_id"].isin([5])]                   # one frame without detections: skipped by the wrapper, affine composed
+    cfg = types.SimpleNamespace(min_confidence=0.4, hyperparams=dict(YAML), reid_arch="resnet50", reid_precision="fp32",
+                                synthetic_weights=True, model_weights=None, cap_tracks=128, cap_dets=128)
+    mod = modules.DeepOCSORT(cfg, "cuda:0")
+    assert mod.level == "image" and mod.name == "DeepOCSORT"
+    out = OfflineEngineMirror([mod], vmd, imd, det).track_dataset().sort_index()
+    has = out["track_id"].notna().to_numpy()
+    assert has.sum() > 0.8 * (det["bbox_conf"] > 0.4).sum()
+    # the same chain with the oracle tracker on the module's own stage outputs
+    dsort = det.sort_index()
+    ltwh = np.stack(dsort["bbox_ltwh"].to_numpy()).astype(np.float64)
+    rows = np.zeros((len(dsort), 7))
+    rows[:, :4] = ltwh; rows[:, 2] += rows[:, 0]; rows[:, 3] += rows[:, 1]
+    rows[:, 4] = dsort["bbox_conf"].to_numpy(dtype=float); rows[:, 5] = dsort["category_id"].to_numpy(dtype=float); rows[:, 6] = dsort.index.to_numpy()
+    img = dsort["image_id"].to_numpy().astype(int)
+    offs = np.concatenate([[0], np.cumsum(np.bincount(img, minlength=F))])
+    fr = torch.from_numpy(frames).cuda()
+    feats = mod.reid.features(fr, torch.from_numpy(rows).cuda(), torch.from_numpy(img.astype(np.int32)).cuda(), ltwh_rows=kernels.CROP_RULE_XYXY_INT).cpu().numpy()
+    warps, _, _ = kernels.ecc_euclidean(kernels.ecc_gray_small(fr, 0.1), 100, 1e-5, 0.1)
+    aff = modules.compose_skipped_affines(warps.double().cpu().numpy().reshape(-1, 2, 3), np.diff(offs) > 0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want, wf = DeepOCSortOracle(**YAML, min_confidence=0.4).run_video(rows, offs, feats, aff)
+    want = want[~pd_duplicated_first(want[:, 7], wf)]
+    got_ids = out["track_id"].to_numpy(dtype=float, na_value=np.nan)
+    ref_ids = np.full(len(out), np.nan)
+    pos = {int(i): k for k, i in enumerate(out.index.to_numpy())}
+    for r in want:
+        ref_ids[pos[int(r[7])]] = r[4]
+    assert np.array_equal(np.isnan(got_ids), np.isnan(ref_ids)) and np.array_equal(got_ids[has], ref_ids[has])
+
+
+def pd_duplicated_first(det_ids, frames):
+    """results[~results.index.duplicated(keep='first')] per frame (deep_oc_sort_api.py:88)."""
+    seen, dup = set(), np.zeros(len(det_ids), dtype=bool)
+    for k, (d, f) in enumerate(zip(det_ids, frames)):
+        dup[k] = (f, d) in seen
+        seen.add((f, d))
+    return dup

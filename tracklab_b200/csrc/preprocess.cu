@@ -383,6 +383,10 @@ crop_resize_norm_kernel(const unsigned char* __restrict__ frames, size_t frame_s
         const float h = fmaxf(1.0f, fminf((float)d[3], __fsub_rn((float)(H - 1), t)));
         x1 = __float2int_rn(l); y1 = __float2int_rn(t);
         x2 = __float2int_rn(__fadd_rn(l, w)); y2 = __float2int_rn(__fadd_rn(t, h));
+    } else if (crop_rule == TK_CROP_RULE_XYXY_INT) {
+        // Deep OC-SORT / BoT-SORT rule (deep_oc_sort/ocsort.py:560-565): box.astype(int), then the NumPy slice img[y1:y2, x1:x2]
+        x1 = max((int)d[0], 0); y1 = max((int)d[1], 0);
+        x2 = min(max((int)d[2], 0), W); y2 = min(max((int)d[3], 0), H);
     } else {
         // StrongSORT crop rule (strong_sort.py:102-108): centre box -> int() truncation -> clip
         const double cx = (d[0] + d[2]) / 2, cy = (d[1] + d[3]) / 2, bw = d[2] - d[0], bh = d[3] - d[1];
@@ -504,7 +508,7 @@ extern "C" int tk_crop_resize_norm(const unsigned char* frames, int H, int W, lo
 extern "C" int tk_crop_resize_norm_ex(const unsigned char* frames, int H, int W, long long frame_stride_bytes, const double* dets,
                                       const int* det_frame, int n_dets, void* out, int out_dtype, int out_nhwc, int out_h, int out_w,
                                       const float* mean3, const float* std3, int crop_rule, void* stream) {
-    if (crop_rule != TK_CROP_RULE_STRONGSORT && crop_rule != TK_CROP_RULE_LTWH_ROUNDED) return TK_ERR_ARG;
+    if (crop_rule != TK_CROP_RULE_STRONGSORT && crop_rule != TK_CROP_RULE_LTWH_ROUNDED && crop_rule != TK_CROP_RULE_XYXY_INT) return TK_ERR_ARG;
     if (!frames || !dets || !det_frame || !out || !mean3 || !std3 || n_dets < 0 || H <= 0 || W <= 0 || out_h <= 0 || out_w <= 0) return TK_ERR_ARG;
     if (out_dtype != TK_DTYPE_F32 && out_dtype != TK_DTYPE_BF16) return TK_ERR_ARG;
     if (out_nhwc == TK_CROP_LAYOUT_S2D16 && ((out_h | out_w) & 1)) return TK_ERR_ARG;

@@ -8,6 +8,7 @@ import torch
 from . import _lib
 
 F32, BF16 = 0, 1
+CROP_RULE_STRONGSORT, CROP_RULE_LTWH_ROUNDED, CROP_RULE_XYXY_INT = 0, 1, 2   # TK_CROP_RULE_* (``ltwh_rows`` of crop_resize_norm accepts them)
 
 LAUNCHES = 0   # number of libtrackkern kernel launches issued through this module (bench.py reports it)
 

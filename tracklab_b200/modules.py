@@ -303,6 +303,123 @@ class _StrongSortImpl:
         return sel[["track_bbox_ltwh", "track_bbox_conf", "track_id"]]
 
 
+class _DeepOCSortImpl(_StrongSortImpl):
+    """Shared implementation bound into ``DeepOCSORT``. Replaces /root/reference/tracklab/wrappers/track/deep_oc_sort_api.py:16-91:
+    the reference decodes the frame in ``process``, crops (``box.astype(int)`` + NumPy slice, deep_oc_sort/ocsort.py:560-565), runs
+    the ReID network and the camera-motion estimator inside the tracker for every frame; here all crops of a batch of frames go through
+    the crop-gather kernel (TK_CROP_RULE_XYXY_INT) + backbone together and the whole video is associated by one tk_deepocsort_run
+    launch. Camera motion: the plugin's estimator is sparse optical flow + RANSAC (cmc.py:138-166, OpenCV); here the 2x3 transform of
+    every consecutive frame pair comes from the device ECC (tk_ecc_gray_small + tk_ecc_euclidean, the estimator StrongSORT's wrapper
+    uses) and the transforms of frames the wrapper skips (no detections) are composed into the next processed frame - a different
+    estimator of the same camera motion; the association itself is the plugin's, operation by operation, given the matrices."""
+
+    def __init__(self, cfg, device, **kwargs):
+        ImageLevelModule.__init__(self, batch_size=1)
+        if not torch.cuda.is_available():
+            raise _lib.TrackKernError(f"{type(self).__name__} needs a CUDA device: tracklab_b200 has no CPU path")
+        from .device_trackers import DeepOCSortDevice
+        from .reid import ReidStageDevice
+        self.cfg = cfg
+        self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
+        self.cap_tracks = int(_cfg_get(cfg, "cap_tracks", 128))
+        self.cap_dets = int(_cfg_get(cfg, "cap_dets", 128))
+        self.frames_per_batch = _cfg_get(cfg, "frames_per_batch", None)
+        self.decode_batch = int(_cfg_get(cfg, "decode_batch", 16))
+        self.hyper = dict(_cfg_get(cfg, "hyperparams", {}) or {})
+        self.min_confidence = float(_cfg_get(cfg, "min_confidence", 0.4))
+        self.ecc = not bool(self.hyper.get("cmc_off", False))
+        weights = _cfg_get(cfg, "model_weights", None)
+        name = os.path.basename(str(weights)) if weights is not None else ""
+        arch = _cfg_get(cfg, "reid_arch", None) or next((a for a in ("osnet_ibn_x1_0", "osnet_x1_0", "resnet50") if a in name), "osnet_x1_0")
+        model = None
+        if weights is not None and not os.path.isfile(str(weights)) and not bool(_cfg_get(cfg, "synthetic_weights", False)):
+            raise _lib.TrackKernError(f"ReID weights {weights!r} not found (pass synthetic_weights=True to run on seeded random weights)")
+        if weights is not None and os.path.isfile(str(weights)):
+            from .reid import build_reid_model
+            sd = torch.load(str(weights), map_location="cpu")
+            model = build_reid_model(arch).from_reference_state_dict(sd.get("state_dict", sd))
+        self.reid = None
+        if not bool(self.hyper.get("embedding_off", False)):
+            self.reid = ReidStageDevice(device=self.device, model=model, precision=_cfg_get(cfg, "reid_precision", "bf16"), arch=arch)
+        self._trk_cls = DeepOCSortDevice
+        self.tracker = None
+        self._pipe = _TrackerDatapipe(self, self.frames_per_batch)
+        self._result = None
+
+    def _track_video(self, img_metadatas, detections):
+        import cv2
+
+        from . import kernels
+        image_ids = np.asarray(img_metadatas.index)
+        if detections is None or len(detections) == 0:
+            self._result = pd.DataFrame(columns=["image_id"] + self.output_columns)
+            return
+        rows, offsets, _ = _rows_from_detections(image_ids, detections, self.cap_dets)
+        paths = list(img_metadatas["file_path"])
+        E = self.reid.feature_dim if self.reid is not None else 1
+        if self.tracker is None:
+            self.tracker = self._trk_cls(E, **self.hyper, min_confidence=self.min_confidence, cap_tracks=self.cap_tracks,
+                                         cap_dets=self.cap_dets, device=self.device)
+        d_dev = torch.from_numpy(rows).to(self.device)
+        feats = torch.empty((len(rows), E), dtype=torch.float32, device=self.device) if self.reid is not None else None
+        small = []
+        for f0 in range(0, len(paths), self.decode_batch):
+            f1 = min(len(paths), f0 + self.decode_batch)
+            batch = np.stack([cv2.cvtColor(cv2.imread(p), cv2.COLOR_BGR2RGB) for p in paths[f0:f1]])
+            fr = torch.from_numpy(batch).to(self.device)
+            if self.ecc:
+                small.append(kernels.ecc_gray_small(fr, 0.1))
+            r0, r1 = int(offsets[f0]), int(offsets[f1])
+            if r1 > r0 and self.reid is not None:
+                det_frame = torch.from_numpy(np.repeat(np.arange(f1 - f0), np.diff(offsets[f0:f1 + 1])).astype(np.int32)).to(self.device)
+                feats[r0:r1] = self.reid.features(fr, d_dev[r0:r1], det_frame, ltwh_rows=kernels.CROP_RULE_XYXY_INT)
+        o_dev = torch.from_numpy(offsets)[None].to(self.device)
+        affines = None
+        if self.ecc:
+            warps, _, _ = kernels.ecc_euclidean(torch.cat(small), 100, 1e-5, 0.1)   # row f: frame f-1 -> f (NaN: first frame / failed)
+            affines = torch.from_numpy(compose_skipped_affines(warps.double().cpu().numpy().reshape(-1, 2, 3), np.diff(offsets) > 0))
+            affines = affines[None].contiguous().to(self.device)
+        out_rows, out_fc, out_cnt = self.tracker.run(d_dev, o_dev, feats, affines)
+        self.tracker.check_status()
+        n = int(out_cnt[0].item())
+        res = out_rows[:n].cpu().numpy()
+        fc = out_fc[0].cpu().numpy()
+        frame_of_row = np.repeat(np.arange(len(fc)), fc)
+        ltrb = res[:, :4]
+        self._result = pd.DataFrame({
+            "track_bbox_ltwh": list(np.column_stack([ltrb[:, 0], ltrb[:, 1], ltrb[:, 2] - ltrb[:, 0], ltrb[:, 3] - ltrb[:, 1]])),
+            "track_bbox_conf": res[:, 6], "track_id": res[:, 4], "image_id": image_ids[frame_of_row],
+        }, index=pd.Index(res[:, 7].astype(int), name="idxs"))
+
+    def process(self, batch, detections, metadatas):
+        if len(detections) == 0 or self._result is None or len(self._result) == 0:
+            return []
+        sel = self._result[self._result["image_id"].isin(list(metadatas.index))]
+        if len(sel) == 0:
+            return []
+        return sel[~sel.index.duplicated(keep="first")][["track_bbox_ltwh", "track_bbox_conf", "track_id"]]   # deep_oc_sort_api.py:88
+
+
+def compose_skipped_affines(pair_warps, processed):
+    """pair_warps float64 [F,2,3]: frame f-1 -> f (row 0 / failed pairs NaN -> identity). The plugin's estimator is only called on
+    frames the wrapper processes (deep_oc_sort_api.py:61-62) and relates each call to the previous CALL, so the transforms of skipped
+    frames are folded into the next processed one; the first processed frame gets the identity (cmc.py:144-148)."""
+    F = len(pair_warps)
+    out = np.tile(np.eye(2, 3), (F, 1, 1))
+    acc, seen = np.eye(3), False
+    for f in range(F):
+        A = np.eye(3)
+        if f > 0 and np.isfinite(pair_warps[f]).all():
+            A[:2] = pair_warps[f]
+        acc = A @ acc
+        if processed[f]:
+            if seen:
+                out[f] = acc[:2]
+            seen = True
+            acc = np.eye(3)
+    return out
+
+
 def _rows_from_detections(image_ids, detections, cap_dets):
     """DataFrame rows of one video -> float64 [N,7] = [l,t,r,b,conf,cls,det_id] grouped by frame + int32 offsets."""
     pos = {int(i): k for k, i in enumerate(image_ids)}
@@ -342,6 +459,18 @@ class StrongSORT(ImageLevelModule):
 
 
 _bind_from(StrongSORT, _StrongSortImpl)
+
+
+class DeepOCSORT(ImageLevelModule):
+    """Drop-in for tracklab.wrappers.track.deep_oc_sort_api.DeepOCSORT (ReID + camera-motion affines + association on device)."""
+    input_columns = list(_IN_COLS)
+    output_columns = list(_OUT_COLS)
+    collate_fn = None
+
+
+_bind_from(DeepOCSORT, _StrongSortImpl)
+for _name in ("__init__", "_track_video", "process"):
+    setattr(DeepOCSORT, _name, _DeepOCSortImpl.__dict__[_name])
 
 
 # ---- BPBReID-StrongSORT: part-based embeddings + visibility scores come from the upstream ReID module ---------------
