@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-config2", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[3] (RT-DETR + part-based StrongSORT) and configs[4] (stress) objects")
     ap.add_argument("--no-graphs", action="store_true", help="eager launches instead of CUDA graphs (ncu launch lists only; never a bench value)")
     return ap.parse_args()
 
@@ -495,6 +496,10 @@ def run_ours(args):
         second = run_config("config2", args, dev, rank, world, local, args.frames, 50, max(3, args.steps), args.warmup, want_e2e=not args.no_e2e)
         allm2 = gather_and_reduce(second, dev, world)
 
+    extra4 = extra5 = None
+    if not args.no_extra:
+        extra4, extra5 = extra_blocks(dev, rank, world)
+
     if rank == 0:
         peak_hbm, peak_tf, peak_src = measured_peaks()
         F = args.frames
@@ -539,6 +544,7 @@ def run_ours(args):
                                           for n, v in second["stage_ms"].items()},
                                "per_video": {"ms_per_step": allm2[:, 4].tolist(), "e2e_ms_per_step": allm2[:, 5].tolist(),
                                              "detector_rows": allm2[:, 1].tolist(), "track_rows": allm2[:, 2].tolist()}}
+        line["config4"], line["config5_stress"] = extra4, extra5
         if world == 1:
             try:
                 line["hota_vs_generator"] = hota_block(main)
@@ -552,6 +558,29 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_blocks(dev, rank, world):
+    """BASELINE configs[3] (RT-DETR + part embeddings + part-based StrongSORT, one video per GPU) and configs[4] (4K-scale stress:
+    150 x 150 x 256-d cost-matrix + assignment kernels, one problem set per GPU) as secondary objects of the same line; every rank
+    runs them, times are the max over ranks (tools/bench_config4.py, tools/stress_sweep.py hold the measurement code)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    out4, out5 = None, None
+    try:
+        import bench_config4
+        out4 = bench_config4.run(dev, rank, world, frames=96, batch=16, steps=3, warmup=2)
+    except Exception as e:      # e.g. transformers missing: the same on every rank
+        out4 = {"error": f"{type(e).__name__}: {e}"}
+    try:
+        import stress_sweep
+        recs = stress_sweep.sweep(dev, rank, world, reps=10, batches=(1, 64, 512))
+        out5 = {"workload": "configs[4] stress: D = T = 150 detections / tracks, 256-d embeddings (4K-frame scale), one problem set per GPU; "
+                            "CUDA events, 256 MB L2 flush before every timed launch, max over ranks", "n_gpus": world,
+                "kernels": [{k: r[k] for k in ("kernel", "B", "ms", "us_per_problem", "GBps", "frac_of_hbm_peak", "problems_per_s_all_gpus")}
+                            | ({"GFLOPs_per_gpu": r["GFLOPs_per_gpu"]} if "GFLOPs_per_gpu" in r else {}) for r in recs]}
+    except Exception as e:
+        out5 = {"error": f"{type(e).__name__}: {e}"}
+    return out4, out5
 
 
 def hota_block(r):
