@@ -46,8 +46,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=500)
-    ap.add_argument("--batch", type=int, default=20, help="detector batch of the headline configuration")
+    ap.add_argument("--batch", type=int, default=50, help="detector batch of the headline configuration (sweep on B200, profiles/r02_batch_ctas_sweep.md: 20 -> 1554, 50 -> 1706 frames/s)")
     ap.add_argument("--config", default="config3")
+    ap.add_argument("--ctas", type=int, default=16, help="CTAs of the cooperative StrongSORT / BPBReID kernel per video")
     ap.add_argument("--ref-frames", type=int, default=6, help="frames per step of the CPU arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -358,7 +359,7 @@ def run_config(config, args, dev, rank, world, local, frames_cap, batch, steps, 
     frames = torch.empty((F, video.height, video.width, 3), dtype=torch.uint8, device=dev)
     for f0 in range(0, F, 25):
         frames[f0:min(F, f0 + 25)] = make_frames(video, f0, min(F, f0 + 25), device="cpu").to(dev)
-    pipe = build_pipeline(config, device=dev, batch=batch, frames_cap=F, image_size=(video.width, video.height),
+    pipe = build_pipeline(config, device=dev, batch=batch, frames_cap=F, image_size=(video.width, video.height), ctas_per_video=args.ctas,
                           use_graphs=not args.no_graphs)
     if not pipe.det.trained:
         pipe.det.calibrate(frames[:batch], target_per_image=60.0)
