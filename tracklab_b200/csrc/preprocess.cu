@@ -331,6 +331,8 @@ extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, in
 namespace {
 
 constexpr int CR_ROWS = 8;    // output rows per CTA of the crop / frame resize kernels
+constexpr int CR_HROWS = 40;  // source rows resampled horizontally into shared memory per CTA (separable crop path)
+constexpr int CR_HCOLS = 128; // output columns of the separable crop path
 constexpr int CR_KMAX = 64;   // taps per axis: 2*ceil(scale)+1 -> crops up to ~31x the output size (a full 4K row into 128 px)
 
 // Pillow precompute_coeffs + normalize_coeffs_8bpc for one output index (bilinear filter, support 1)
@@ -405,38 +407,106 @@ crop_resize_norm_kernel(const unsigned char* __restrict__ frames, size_t frame_s
         s_ymin[threadIdx.x] = ym;
     }
     __syncthreads();
-    for (int xx = threadIdx.x; xx < out_w; xx += blockDim.x) {
+    // Separable form (Pillow itself runs the horizontal pass first and rounds it to 8 bits): the CTA's output rows need the source
+    // rows [ylo, yhi); each of them is resampled horizontally ONCE into shared memory (uint8, like Pillow's intermediate image)
+    // instead of once per output row whose vertical support contains it (x2-3 fewer source loads at the usual scales), then the
+    // vertical pass runs out of shared memory. Falls back to the direct form when the rows do not fit (strong down-scaling).
+    __shared__ unsigned char hbuf[CR_HROWS][CR_HCOLS][3];
+    __shared__ int s_lo, s_hi;
+    const int n_rows = min(CR_ROWS, out_h - y0);
+    if (threadIdx.x == 0) {
+        int lo = 0x7fffffff, hi = 0;
+        if (cw > 0 && ch > 0)
+            for (int r = 0; r < n_rows; ++r) { lo = min(lo, s_ymin[r]); hi = max(hi, s_ymin[r] + s_ny[r]); }
+        s_lo = lo; s_hi = hi;
+    }
+    __syncthreads();
+    const int ylo = s_lo, n_src = s_hi - s_lo;
+    const bool separable = cw > 0 && ch > 0 && n_src <= CR_HROWS && out_w <= CR_HCOLS;
+    for (int xx0 = 0; xx0 < out_w; xx0 += blockDim.x) {
+        const int xx = xx0 + threadIdx.x;
         int kh[CR_KMAX], xmin = 0, nx = 0;
-        if (cw > 0 && ch > 0) nx = pil_taps(cw, out_w, xx, kh, xmin);
-        for (int r = 0; r < CR_ROWS && y0 + r < out_h; ++r) {
+        if (xx < out_w && cw > 0 && ch > 0) nx = pil_taps(cw, out_w, xx, kh, xmin);
+        if (separable && xx < out_w) {
+            for (int rr = 0; rr < n_src; ++rr) {
+                const unsigned char* row = img + ((size_t)(y1 + ylo + rr) * W + (x1 + xmin)) * 3;
+                int h[3] = {1 << 21, 1 << 21, 1 << 21};
+                for (int kx = 0; kx < nx; ++kx) {
+                    h[0] += row[kx * 3 + 0] * kh[kx]; h[1] += row[kx * 3 + 1] * kh[kx]; h[2] += row[kx * 3 + 2] * kh[kx];
+                }
+                hbuf[rr][xx][0] = (unsigned char)clip8(h[0]); hbuf[rr][xx][1] = (unsigned char)clip8(h[1]); hbuf[rr][xx][2] = (unsigned char)clip8(h[2]);
+            }
+        }
+        // (no barrier needed: a thread only reads the hbuf column it wrote)
+        float o2[2][3];
+        for (int r = 0; r < n_rows; ++r) {
             const int yy = y0 + r;
             int v[3] = {0, 0, 0};
-            if (cw > 0 && ch > 0) {
+            if (xx < out_w && cw > 0 && ch > 0) {
                 int acc[3] = {1 << 21, 1 << 21, 1 << 21};
-                for (int ky = 0; ky < s_ny[r]; ++ky) {
-                    const unsigned char* row = img + ((size_t)(y1 + s_ymin[r] + ky) * W + (x1 + xmin)) * 3;
-                    int h[3] = {1 << 21, 1 << 21, 1 << 21};
-                    // (when a size already matches, Pillow skips that pass; the taps then are {1<<22, 0}, i.e. the identity)
-                    for (int kx = 0; kx < nx; ++kx) {
-                        h[0] += row[kx * 3 + 0] * kh[kx]; h[1] += row[kx * 3 + 1] * kh[kx]; h[2] += row[kx * 3 + 2] * kh[kx];
+                if (separable) {
+                    const int rb = s_ymin[r] - ylo;
+                    for (int ky = 0; ky < s_ny[r]; ++ky) {
+                        const int w = kv[r][ky];
+                        acc[0] += hbuf[rb + ky][xx][0] * w; acc[1] += hbuf[rb + ky][xx][1] * w; acc[2] += hbuf[rb + ky][xx][2] * w;
                     }
+                } else {
+                    for (int ky = 0; ky < s_ny[r]; ++ky) {
+                        const unsigned char* row = img + ((size_t)(y1 + s_ymin[r] + ky) * W + (x1 + xmin)) * 3;
+                        int h[3] = {1 << 21, 1 << 21, 1 << 21};
+                        // (when a size already matches, Pillow skips that pass; the taps then are {1<<22, 0}, i.e. the identity)
+                        for (int kx = 0; kx < nx; ++kx) {
+                            h[0] += row[kx * 3 + 0] * kh[kx]; h[1] += row[kx * 3 + 1] * kh[kx]; h[2] += row[kx * 3 + 2] * kh[kx];
+                        }
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) acc[c] += clip8(h[c]) * kv[r][ky];
+                        for (int c = 0; c < 3; ++c) acc[c] += clip8(h[c]) * kv[r][ky];
+                    }
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) v[c] = clip8(acc[c]);
             }
+            float o[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const float t = __fdiv_rn((float)v[c], 255.0f);                 // ToTensor
-                const float o = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);      // Normalize
+                o[c] = __fdiv_rn(__fsub_rn(t, mean[c]), stdv[c]);               // Normalize
+            }
+            if (nhwc == TK_CROP_LAYOUT_S2D16 && sizeof(OutT) == 2 && (n_rows & 1) == 0) {
+                // 2x2 space-to-depth, 16-channel pitch: the quad (rows yy, yy+1; columns xx, xx+1) is 12 contiguous bf16 of one
+                // 32-byte group -> the even lane collects its neighbour's values and writes 16 + 8 bytes instead of 12 2-byte stores
+#pragma unroll
+                for (int c = 0; c < 3; ++c) o2[r & 1][c] = o[c];
+                if (r & 1) {
+                    float nb[2][3];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) nb[q][c] = __shfl_down_sync(0xffffffffu, o2[q][c], 1);
+                    if (!(xx & 1) && xx < out_w) {
+                        const size_t g = (((size_t)n * (out_h / 2 + 3) + ((yy - 1) >> 1) + 2) * (out_w / 2 + 3) + (xx >> 1) + 2) << 4;
+                        __nv_bfloat162 w01 = __floats2bfloat162_rn(o2[0][0], o2[0][1]), w23 = __floats2bfloat162_rn(o2[0][2], nb[0][0]);
+                        __nv_bfloat162 w45 = __floats2bfloat162_rn(nb[0][1], nb[0][2]), w67 = __floats2bfloat162_rn(o2[1][0], o2[1][1]);
+                        __nv_bfloat162 w89 = __floats2bfloat162_rn(o2[1][2], nb[1][0]), wab = __floats2bfloat162_rn(nb[1][1], nb[1][2]);
+                        uint4 a4; uint2 b2;
+                        a4.x = *reinterpret_cast<unsigned*>(&w01); a4.y = *reinterpret_cast<unsigned*>(&w23);
+                        a4.z = *reinterpret_cast<unsigned*>(&w45); a4.w = *reinterpret_cast<unsigned*>(&w67);
+                        b2.x = *reinterpret_cast<unsigned*>(&w89); b2.y = *reinterpret_cast<unsigned*>(&wab);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + g) = a4;
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + g + 8) = b2;
+                    }
+                }
+                continue;
+            }
+            if (xx >= out_w) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
                 size_t idx;
                 if (nhwc == TK_CROP_LAYOUT_S2D16)   // 2x2 space-to-depth, 16-channel pitch, zero border of 2 before / 1 after (see trackkern.h)
                     idx = ((((size_t)n * (out_h / 2 + 3) + (yy >> 1) + 2) * (out_w / 2 + 3) + (xx >> 1) + 2) << 4) + (((yy & 1) * 2 + (xx & 1)) * 3 + c);
                 else
                     idx = nhwc ? (((size_t)n * out_h + yy) * out_w + xx) * nhwc + c   // nhwc = channel pitch (3, or 8 with zero padding)
                                : (((size_t)n * 3 + c) * out_h + yy) * out_w + xx;
-                out[idx] = cvt_out<OutT>(o);
+                out[idx] = cvt_out<OutT>(o[c]);
             }
         }
     }
