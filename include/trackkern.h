@@ -413,6 +413,37 @@ int tk_deepocsort_run(void* handle, const double* dets, const float* embeddings,
 int tk_deepocsort_status(void* handle, int* status_host, void* stream);
 int tk_deepocsort_destroy(void* handle);
 
+/* ---- BoT-SORT: whole-video association with externally supplied embeddings and camera-motion warps ---------
+ * Replaces BoTSORT.update of the bot_sort plugin called once per frame by the wrapper, minus the in-tracker ReID forward
+ * (`_get_features`) and the camera-motion estimator (`GMC.apply`: its 2x3 result is an input):
+ *   /root/reference/plugins/track/bot_sort/bot_sort.py:275-485 (update), :15-240 (STrack), :507-545 (list helpers)
+ *   /root/reference/plugins/track/bot_sort/matching.py:37-48,72-89,127-195,198-233
+ *   /root/reference/plugins/track/bot_sort/kalman_filter.py:55-268
+ *   /root/reference/tracklab/wrappers/track/bot_sort_api.py:57-87 (per-frame filter + row layout)
+ * Hyper-parameters: /root/reference/tracklab/configs/modules/track/bot_sort.yaml. dets [N,7] float64, embeddings float32
+ * [N, feature_dim] (raw backbone outputs; the tracker normalises them), warps float64 [n_seq, n_frames, 2, 3], offsets int32
+ * [n_seq, n_frames+1]. Output rows [x1,y1,x2,y2,track_id,cls,score,det_id]. The class histogram of the plugin (update_cls) is
+ * reduced to the class of the last matched detection. */
+typedef struct {
+    double track_high_thresh; /* 0.45 */
+    double new_track_thresh;  /* 0.6 */
+    double match_thresh;      /* 0.8 */
+    double proximity_thresh;  /* 0.5 */
+    double appearance_thresh; /* 0.25 */
+    double lambda_;           /* 0.985 */
+    double min_confidence;    /* wrapper filter (0.4), bot_sort_api.py:65 */
+    int track_buffer;         /* 30 */
+    int frame_rate;           /* 30 */
+    int feature_dim;          /* E */
+} tk_botsort_params;
+
+int tk_botsort_create(const tk_botsort_params* p, int n_seq, int cap_tracks, int cap_dets, void** handle);
+int tk_botsort_reset(void* handle, int keep_id_counter, void* stream);
+int tk_botsort_run(void* handle, const double* dets, const float* embeddings, const double* warps, const int* offsets, int n_frames,
+                   double* out_rows, const int* out_start, int* out_frame_count, int* out_count, void* stream);
+int tk_botsort_status(void* handle, int* status_host, void* stream);
+int tk_botsort_destroy(void* handle);
+
 /* ---- HOTA of one sequence on the device -----------------------------------------------------------------------
  * Replaces HOTA.eval_sequence of the TrackEval fork vendored in the reference
  * (/root/reference/plugins/eval/PoseTrack21/posetrack21/posetrack21/trackeval/metrics/hota.py:28-154, final fields :205-221) with the

@@ -57,6 +57,13 @@ class DeepocsortParams(ctypes.Structure):
                 ("feature_dim", ctypes.c_int)]
 
 
+class BotsortParams(ctypes.Structure):
+    _fields_ = [("track_high_thresh", ctypes.c_double), ("new_track_thresh", ctypes.c_double), ("match_thresh", ctypes.c_double),
+                ("proximity_thresh", ctypes.c_double), ("appearance_thresh", ctypes.c_double), ("lambda_", ctypes.c_double),
+                ("min_confidence", ctypes.c_double), ("track_buffer", ctypes.c_int), ("frame_rate", ctypes.c_int),
+                ("feature_dim", ctypes.c_int)]
+
+
 ASSO_CODES = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3, "ct_dist": 4}
 
 _lib = None
@@ -103,6 +110,11 @@ def _declare(lib):
         "tk_ocsort_run": ([vp, vp, vp, ci, vp, vp, vp, vp, vp], ci),
         "tk_ocsort_status": ([vp, P(ci), vp], ci),
         "tk_ocsort_destroy": ([vp], ci),
+        "tk_botsort_create": ([P(BotsortParams), ci, ci, ci, P(vp)], ci),
+        "tk_botsort_reset": ([vp, ci, vp], ci),
+        "tk_botsort_run": ([vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp], ci),
+        "tk_botsort_status": ([vp, P(ci), vp], ci),
+        "tk_botsort_destroy": ([vp], ci),
         "tk_deepocsort_create": ([P(DeepocsortParams), ci, ci, ci, P(vp)], ci),
         "tk_deepocsort_reset": ([vp, vp], ci),
         "tk_deepocsort_run": ([vp, vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp], ci),

@@ -182,6 +182,50 @@ class DeepOCSortDevice(_VideoTrackerDevice):
         return out_rows, out_fc, out_count
 
 
+class BotSortDevice(_VideoTrackerDevice):
+    """BoT-SORT for ``n_seq`` independent videos (C ABI: tk_botsort_*).
+
+    Mirrors BoTSORT(model_weights, device, fp16, **hyperparams) of the bot_sort plugin with its constructor defaults + the wrapper's
+    ``min_confidence`` filter (/root/reference/plugins/track/bot_sort/bot_sort.py:243-273, /root/reference/tracklab/wrappers/track/
+    bot_sort_api.py:57-66); the in-tracker ReID forward and the camera-motion estimator (``cmc_method``) are separate stages whose
+    outputs (embeddings float32 [N,E], warps float64 [n_seq,F,2,3]; identity rows for cmc_method 'none') are passed to ``run``."""
+
+    _prefix = "botsort"
+
+    def __init__(self, feature_dim, track_high_thresh=0.45, new_track_thresh=0.6, track_buffer=30, match_thresh=0.8, proximity_thresh=0.5,
+                 appearance_thresh=0.25, cmc_method="sparseOptFlow", frame_rate=30, lambda_=0.985, min_confidence=0.4, n_seq=1,
+                 cap_tracks=128, cap_dets=128, device="cuda:0"):
+        self.feature_dim = int(feature_dim)
+        self.cmc_method = cmc_method
+        self._create(_lib.BotsortParams(track_high_thresh, new_track_thresh, match_thresh, proximity_thresh, appearance_thresh, lambda_,
+                                        min_confidence, int(track_buffer), int(frame_rate), self.feature_dim), n_seq, cap_tracks, cap_dets, device)
+
+    def run(self, dets: torch.Tensor, offsets: torch.Tensor, embeddings: torch.Tensor, warps: torch.Tensor | None = None,
+            out_rows: torch.Tensor | None = None, out_start: torch.Tensor | None = None, out_count: torch.Tensor | None = None):
+        """dets float64 [N,7], offsets int32 [n_seq,F+1], embeddings float32 [N,E], warps float64 [n_seq,F,2,3] (None = identity)."""
+        _require_cuda(dets, "dets"); _require_cuda(offsets, "offsets"); _require_cuda(embeddings, "embeddings")
+        assert dets.dtype == torch.float64 and dets.is_contiguous()
+        assert offsets.dtype == torch.int32 and offsets.is_contiguous() and offsets.shape[0] == self.n_seq
+        assert embeddings.dtype == torch.float32 and embeddings.is_contiguous() and tuple(embeddings.shape) == (dets.shape[0], self.feature_dim)
+        n_frames = offsets.shape[1] - 1
+        if warps is None:
+            warps = torch.eye(2, 3, dtype=torch.float64, device=dets.device).repeat(self.n_seq, n_frames, 1, 1).contiguous()
+        _require_cuda(warps, "warps")
+        assert warps.dtype == torch.float64 and warps.is_contiguous() and tuple(warps.shape) == (self.n_seq, n_frames, 2, 3)
+        if out_rows is None:
+            out_rows = torch.empty((max(1, dets.shape[0]), 8), dtype=torch.float64, device=dets.device)
+        if out_start is None:
+            out_start = offsets[:, 0].contiguous()
+        if out_count is None:
+            out_count = torch.zeros(self.n_seq, dtype=torch.int32, device=dets.device)
+        out_fc = torch.empty((self.n_seq, n_frames), dtype=torch.int32, device=dets.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._fn["run"](self.handle, dets.data_ptr(), embeddings.data_ptr(), warps.data_ptr(), offsets.data_ptr(), n_frames,
+                                       out_rows.data_ptr(), out_start.data_ptr(), out_fc.data_ptr(), out_count.data_ptr(), _stream_ptr()),
+                       "tk_botsort_run")
+        return out_rows, out_fc, out_count
+
+
 class StrongSortDevice(_VideoTrackerDevice):
     """StrongSORT association for ``n_seq`` videos with externally supplied ReID features (C ABI: tk_strongsort_*).
 
