@@ -80,11 +80,12 @@ def test_every_device_stage_and_module_refuses_to_run_without_cuda():
     if torch.cuda.is_available():
         pytest.skip("CUDA present")
     from tracklab_b200 import _lib, modules
-    from tracklab_b200.device_trackers import BpbreidStrongSortDevice, DeepOCSortDevice, OCSortDevice, StrongSortDevice
+    from tracklab_b200.device_trackers import BotSortDevice, BpbreidStrongSortDevice, DeepOCSortDevice, OCSortDevice, StrongSortDevice
     from tracklab_b200.detector import YoloxDetectorDevice
     from tracklab_b200.reid import ReidStageDevice
     from tracklab_b200.rtdetr_detector import RTDetrDetectorDevice
-    for ctor in (lambda: OCSortDevice(), lambda: StrongSortDevice(64), lambda: DeepOCSortDevice(64),
+    for ctor in (lambda: OCSortDevice(), lambda: StrongSortDevice(64), lambda: DeepOCSortDevice(64), lambda: BotSortDevice(64),
+                 lambda: modules.BotSORT(types.SimpleNamespace(hyperparams={}), "cuda"),
                  lambda: modules.DeepOCSORT(types.SimpleNamespace(hyperparams={}), "cuda"), lambda: BpbreidStrongSortDevice(4, 32), lambda: YoloxDetectorDevice("s"),
                  lambda: ReidStageDevice(), lambda: ReidStageDevice(arch="osnet_x1_0"), lambda: RTDetrDetectorDevice(model=object()),
                  lambda: modules.StrongSORT(types.SimpleNamespace(hyperparams={}, ecc=False), "cuda"),
@@ -98,7 +99,9 @@ def test_new_modules_follow_the_reference_column_contracts():
     from tracklab_b200 import modules
     assert modules.DeepOCSORT.input_columns == ["bbox_ltwh", "bbox_conf", "category_id"]                        # deep_oc_sort_api.py:17-22
     assert modules.DeepOCSORT.output_columns == ["track_id", "track_bbox_ltwh", "track_bbox_conf"]
-    for cls in (modules.StrongSORT, modules.BPBReIDStrongSORT, modules.RTDetr, modules.DeepOCSORT):
+    assert modules.BotSORT.input_columns == ["bbox_ltwh", "bbox_conf", "category_id"]                           # bot_sort_api.py:19-24
+    assert modules.BotSORT.output_columns == ["track_id", "track_bbox_ltwh", "track_bbox_conf"]
+    for cls in (modules.StrongSORT, modules.BPBReIDStrongSORT, modules.RTDetr, modules.DeepOCSORT, modules.BotSORT):
         assert cls.__bases__[0].__name__ == "ImageLevelModule"
     assert modules.BPBReIDStrongSORT.input_columns == ["bbox_ltwh", "embeddings", "visibility_scores"]          # bpbreid_strong_sort_api.py:15-19
     assert modules.BPBReIDStrongSORT.output_columns == ["track_id", "track_bbox_kf_ltwh", "track_bbox_pred_kf_ltwh", "matched_with", "costs",

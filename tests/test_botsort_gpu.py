@@ -56,3 +56,53 @@ def test_botsort_matches_oracle_fresh_seed(seed, hyper):
         ref_rows, ref_frames = BotSortOracle(**hyper, min_confidence=0.4).run_video(v.dets, v.offsets, e.copy(), warps)
     (rows, frames), = _run_device(v, e, warps, hyper, 0.4)
     assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1e-6)
+
+
+def test_botsort_module_through_engine_equals_oracle_chain(tmp_path):
+    """modules.BotSORT (drop-in for bot_sort_api.BotSORT) on PNG frames through the engine protocol: its ids must equal the oracle
+    tracker fed with the module's own stage outputs (device ReID features of the StrongSORT-rule crops, device ECC warps)."""
+    import types
+
+    import cv2
+
+    from oracle.botsort_np import BotSortOracle
+    from tests.golden.make_botsort_golden import YAML
+    from tests.test_engine_modules_gpu import _tracking_frames
+    from tracklab_b200 import kernels, modules
+    from tracklab_b200.engine_mirror import OfflineEngineMirror
+    from tracklab_b200.synth import make_frames, make_video
+    F = 14
+    video = make_video(seed=3200, n_frames=F, n_ids=16)
+    frames = make_frames(video, 0, F, device="cpu").numpy()
+    for f in range(F):
+        cv2.imwrite(str(tmp_path / f"{f:06d}.png"), frames[f][..., ::-1])
+    vmd, imd, det = _tracking_frames([video])
+    imd["file_path"] = [str(tmp_path / f"{f:06d}.png") for f in range(F)]
+    det = det[~det["image_id"].isin([6])]
+    cfg = types.SimpleNamespace(min_confidence=0.4, hyperparams=dict(YAML), reid_arch="resnet50", reid_precision="fp32",
+                                synthetic_weights=True, model_weights=None, cap_tracks=128, cap_dets=128)
+    mod = modules.BotSORT(cfg, "cuda:0")
+    assert mod.level == "image" and mod.name == "BotSORT"
+    out = OfflineEngineMirror([mod], vmd, imd, det).track_dataset().sort_index()
+    has = out["track_id"].notna().to_numpy()
+    assert has.sum() > 0.5 * (det["bbox_conf"] > 0.4).sum()
+    dsort = det.sort_index()
+    ltwh = np.stack(dsort["bbox_ltwh"].to_numpy()).astype(np.float64)
+    rows = np.zeros((len(dsort), 7))
+    rows[:, :4] = ltwh; rows[:, 2] += rows[:, 0]; rows[:, 3] += rows[:, 1]
+    rows[:, 4] = dsort["bbox_conf"].to_numpy(dtype=float); rows[:, 5] = dsort["category_id"].to_numpy(dtype=float); rows[:, 6] = dsort.index.to_numpy()
+    img = dsort["image_id"].to_numpy().astype(int)
+    offs = np.concatenate([[0], np.cumsum(np.bincount(img, minlength=F))])
+    fr = torch.from_numpy(frames).cuda()
+    feats = mod.reid.features(fr, torch.from_numpy(rows).cuda(), torch.from_numpy(img.astype(np.int32)).cuda(), ltwh_rows=kernels.CROP_RULE_STRONGSORT).cpu().numpy()
+    w, _, _ = kernels.ecc_euclidean(kernels.ecc_gray_small(fr, 0.1), 100, 1e-5, 0.1)
+    warps = modules.compose_skipped_affines(w.double().cpu().numpy().reshape(-1, 2, 3), np.diff(offs) > 0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want, wf = BotSortOracle(**YAML, min_confidence=0.4).run_video(rows, offs, feats.copy(), warps)
+    got_ids = out["track_id"].to_numpy(dtype=float, na_value=np.nan)
+    ref_ids = np.full(len(out), np.nan)
+    pos = {int(i): k for k, i in enumerate(out.index.to_numpy())}
+    for r in want:
+        ref_ids[pos[int(r[7])]] = r[4]
+    assert np.array_equal(np.isnan(got_ids), np.isnan(ref_ids)) and np.array_equal(got_ids[has], ref_ids[has])

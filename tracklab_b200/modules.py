@@ -372,7 +372,7 @@ class _DeepOCSortImpl(_StrongSortImpl):
             r0, r1 = int(offsets[f0]), int(offsets[f1])
             if r1 > r0 and self.reid is not None:
                 det_frame = torch.from_numpy(np.repeat(np.arange(f1 - f0), np.diff(offsets[f0:f1 + 1])).astype(np.int32)).to(self.device)
-                feats[r0:r1] = self.reid.features(fr, d_dev[r0:r1], det_frame, ltwh_rows=kernels.CROP_RULE_XYXY_INT)
+                feats[r0:r1] = self.reid.features(fr, d_dev[r0:r1], det_frame, ltwh_rows=getattr(self, "_crop_rule", kernels.CROP_RULE_XYXY_INT))
         o_dev = torch.from_numpy(offsets)[None].to(self.device)
         affines = None
         if self.ecc:
@@ -398,6 +398,54 @@ class _DeepOCSortImpl(_StrongSortImpl):
         if len(sel) == 0:
             return []
         return sel[~sel.index.duplicated(keep="first")][["track_bbox_ltwh", "track_bbox_conf", "track_id"]]   # deep_oc_sort_api.py:88
+
+
+class _BotSortImpl(_DeepOCSortImpl):
+    """Shared implementation bound into ``BotSORT``. Replaces /root/reference/tracklab/wrappers/track/bot_sort_api.py:16-87 like
+    ``_DeepOCSortImpl`` replaces the Deep OC-SORT wrapper: ReID forward of all crops of a batch of frames (the plugin's crop is the
+    StrongSORT rule: centre box, int(), clip - bot_sort.py:487-495 = TK_CROP_RULE_STRONGSORT), camera motion from the device ECC for every
+    ``cmc_method`` except 'none' (the plugin's default estimator is OpenCV sparse optical flow, gmc.py:239-303: a different estimator of the
+    same motion), one tk_botsort_run launch per video."""
+
+    def __init__(self, cfg, device, **kwargs):
+        ImageLevelModule.__init__(self, batch_size=1)
+        if not torch.cuda.is_available():
+            raise _lib.TrackKernError(f"{type(self).__name__} needs a CUDA device: tracklab_b200 has no CPU path")
+        from .device_trackers import BotSortDevice
+        from .reid import ReidStageDevice
+        self.cfg = cfg
+        self.device = torch.device(device if str(device) != "cuda" else "cuda:0")
+        self.cap_tracks = int(_cfg_get(cfg, "cap_tracks", 128))
+        self.cap_dets = int(_cfg_get(cfg, "cap_dets", 128))
+        self.frames_per_batch = _cfg_get(cfg, "frames_per_batch", None)
+        self.decode_batch = int(_cfg_get(cfg, "decode_batch", 16))
+        self.hyper = dict(_cfg_get(cfg, "hyperparams", {}) or {})
+        self.min_confidence = float(_cfg_get(cfg, "min_confidence", 0.4))
+        self.ecc = str(self.hyper.get("cmc_method", "sparseOptFlow")).lower() != "none"
+        weights = _cfg_get(cfg, "model_weights", None)
+        name = os.path.basename(str(weights)) if weights is not None else ""
+        arch = _cfg_get(cfg, "reid_arch", None) or next((a for a in ("osnet_ibn_x1_0", "osnet_x1_0", "resnet50") if a in name), "osnet_ibn_x1_0")
+        model = None
+        if weights is not None and not os.path.isfile(str(weights)) and not bool(_cfg_get(cfg, "synthetic_weights", False)):
+            raise _lib.TrackKernError(f"ReID weights {weights!r} not found (pass synthetic_weights=True to run on seeded random weights)")
+        if weights is not None and os.path.isfile(str(weights)):
+            from .reid import build_reid_model
+            sd = torch.load(str(weights), map_location="cpu")
+            model = build_reid_model(arch).from_reference_state_dict(sd.get("state_dict", sd))
+        self.reid = ReidStageDevice(device=self.device, model=model, precision=_cfg_get(cfg, "reid_precision", "bf16"), arch=arch)
+        self._trk_cls = BotSortDevice
+        self._crop_rule = 0          # kernels.CROP_RULE_STRONGSORT
+        self.tracker = None
+        self._pipe = _TrackerDatapipe(self, self.frames_per_batch)
+        self._result = None
+
+    def process(self, batch, detections, metadatas):
+        if len(detections) == 0 or self._result is None or len(self._result) == 0:
+            return []
+        sel = self._result[self._result["image_id"].isin(list(metadatas.index))]
+        if len(sel) == 0:
+            return []
+        return sel[["track_bbox_ltwh", "track_bbox_conf", "track_id"]]
 
 
 def compose_skipped_affines(pair_warps, processed):
@@ -471,6 +519,19 @@ class DeepOCSORT(ImageLevelModule):
 _bind_from(DeepOCSORT, _StrongSortImpl)
 for _name in ("__init__", "_track_video", "process"):
     setattr(DeepOCSORT, _name, _DeepOCSortImpl.__dict__[_name])
+
+
+class BotSORT(ImageLevelModule):
+    """Drop-in for tracklab.wrappers.track.bot_sort_api.BotSORT (ReID + camera-motion warps + association on device)."""
+    input_columns = list(_IN_COLS)
+    output_columns = list(_OUT_COLS)
+    collate_fn = None
+
+
+_bind_from(BotSORT, _StrongSortImpl)
+BotSORT._track_video = _DeepOCSortImpl.__dict__["_track_video"]
+for _name in ("__init__", "process"):
+    setattr(BotSORT, _name, _BotSortImpl.__dict__[_name])
 
 
 # ---- BPBReID-StrongSORT: part-based embeddings + visibility scores come from the upstream ReID module ---------------
