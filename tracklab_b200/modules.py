@@ -74,6 +74,24 @@ _IN_COLS = ["bbox_ltwh", "bbox_conf", "category_id"]
 _OUT_COLS = ["track_id", "track_bbox_ltwh", "track_bbox_conf"]
 
 
+# Constructor defaults of the REFERENCE plugin classes: a partial `hyperparams` dict must run the tracker the reference would run
+# (the device classes default to the tuned values of tracklab/configs/modules/track/*.yaml instead).
+REF_DEFAULTS = {
+    "ByteTrack": dict(track_thresh=0.45, track_buffer=25, match_thresh=0.8, frame_rate=30),                 # byte_tracker.py:152
+    "OCSORT": dict(max_age=30, min_hits=3, iou_threshold=0.3, delta_t=3, asso_func="iou", inertia=0.2, use_byte=False),   # ocsort.py:183-184 (det_thresh is required)
+    "StrongSORT": dict(max_dist=0.2, max_iou_dist=0.7, max_age=70, max_unmatched_preds=7, n_init=3, nn_budget=100, mc_lambda=0.995,
+                       ema_alpha=0.9),                                                                      # strong_sort.py:20-31
+}
+
+
+def _with_reference_defaults(name, hyper):
+    out = dict(REF_DEFAULTS.get(name, {}))
+    out.update(hyper)
+    if name == "OCSORT" and "det_thresh" not in out:
+        raise _lib.TrackKernError("OCSORT: hyperparams.det_thresh is required (OCSort.__init__ has no default for it, oc_sort/ocsort.py:183)")
+    return out
+
+
 class _Impl:
     def __init__(self, cfg, device, **kwargs):
         ImageLevelModule.__init__(self, batch_size=1)
@@ -84,7 +102,7 @@ class _Impl:
         self.cap_tracks = int(_cfg_get(cfg, "cap_tracks", 256))
         self.cap_dets = int(_cfg_get(cfg, "cap_dets", 256))
         self.frames_per_batch = _cfg_get(cfg, "frames_per_batch", None)
-        hyper = dict(_cfg_get(cfg, "hyperparams", {}) or {})
+        hyper = _with_reference_defaults(type(self).__name__, dict(_cfg_get(cfg, "hyperparams", {}) or {}))
         self.tracker = self._device_cls(**hyper, min_confidence=float(_cfg_get(cfg, "min_confidence", 0.4)),
                                         cap_tracks=self.cap_tracks, cap_dets=self.cap_dets, device=self.device)
         self._pipe = _TrackerDatapipe(self, self.frames_per_batch)
@@ -212,7 +230,10 @@ class _StrongSortImpl:
         self.cap_dets = int(_cfg_get(cfg, "cap_dets", 128))
         self.frames_per_batch = _cfg_get(cfg, "frames_per_batch", None)
         self.decode_batch = int(_cfg_get(cfg, "decode_batch", 16))
-        self.hyper = dict(_cfg_get(cfg, "hyperparams", {}) or {})
+        self.hyper = _with_reference_defaults("StrongSORT", dict(_cfg_get(cfg, "hyperparams", {}) or {}))
+        if int(self.hyper.get("max_unmatched_preds", 0)) != 0:
+            raise _lib.TrackKernError("StrongSORT: only max_unmatched_preds = 0 (tracklab/configs/modules/track/strong_sort.yaml) is built on the "
+                                      "device; the plugin's constructor default 7 applies when hyperparams omits it - set it explicitly")
         self.min_confidence = float(_cfg_get(cfg, "min_confidence", 0.4))
         # the plugin's factory reads the architecture from the weights file name (deep/reid_model_factory.py:122-127)
         weights = _cfg_get(cfg, "model_weights", None)
