@@ -546,6 +546,11 @@ def run_ours(args):
                                "per_video": {"ms_per_step": allm2[:, 4].tolist(), "e2e_ms_per_step": allm2[:, 5].tolist(),
                                              "detector_rows": allm2[:, 1].tolist(), "track_rows": allm2[:, 2].tolist()}}
         line["config4"], line["config5_stress"] = extra4, extra5
+        if not args.no_extra:
+            try:
+                line["trackers_alone"] = trackers_alone_block(dev)
+            except Exception as e:
+                line["trackers_alone"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1:
             try:
                 line["hota_vs_generator"] = hota_block(main)
@@ -582,6 +587,51 @@ def extra_blocks(dev, rank, world):
     except Exception as e:
         out5 = {"error": f"{type(e).__name__}: {e}"}
     return out4, out5
+
+
+def trackers_alone_block(dev, frames=300):
+    """us/frame of every whole-video association kernel alone (generator detections / embeddings of one 1080p video, one launch,
+    CUDA events, third run) - the latency-bound part of the path, reported next to the connected chain."""
+    import numpy as np
+    import torch
+
+    from tracklab_b200.device_trackers import (BotSortDevice, BpbreidStrongSortDevice, ByteTrackDevice, DeepOCSortDevice, OCSortDevice,
+                                               StrongSortDevice)
+    from tracklab_b200.synth import make_video
+    out = {}
+    v = make_video(seed=2000, n_frames=frames, n_ids=44, emb_dim=512)
+    dets = torch.from_numpy(v.dets).to(dev)
+    offs = torch.from_numpy(v.offsets.astype(np.int32))[None].to(dev)
+    embs = torch.from_numpy(np.ascontiguousarray(v.embeddings.astype(np.float32))).to(dev)
+    eye = torch.eye(2, 3, dtype=torch.float64, device=dev).repeat(1, frames, 1, 1).contiguous()
+    vp = make_video(seed=2000, n_frames=frames, n_ids=44, emb_dim=512, n_parts=6)
+    d2 = vp.dets.copy(); d2[:, 2] -= d2[:, 0]; d2[:, 3] -= d2[:, 1]
+    cases = {
+        "bytetrack": (lambda: ByteTrackDevice(device=dev), lambda t: t.run(dets, offs)),
+        "ocsort": (lambda: OCSortDevice(device=dev), lambda t: t.run(dets, offs)),
+        "deepocsort": (lambda: DeepOCSortDevice(512, det_thresh=0.0, max_age=50, min_hits=1, iou_threshold=0.22136877277096445, delta_t=1,
+                                                asso_func="giou", inertia=0.3941737016672115, device=dev), lambda t: t.run(dets, offs, embs, eye)),
+        "botsort": (lambda: BotSortDevice(512, device=dev), lambda t: t.run(dets, offs, embs, eye)),
+        "strongsort": (lambda: StrongSortDevice(512, ctas_per_video=16, device=dev), lambda t: t.run(dets, offs, embs)),
+        "bpbreid_strongsort": (lambda: BpbreidStrongSortDevice(6, 512, ctas_per_video=16, device=dev),
+                               lambda t: t.run(torch.from_numpy(d2).to(dev), torch.from_numpy(vp.offsets.astype(np.int32))[None].to(dev),
+                                               torch.from_numpy(vp.embeddings).to(dev), torch.from_numpy(vp.visibility.astype(np.float32)).to(dev))),
+    }
+    for name, (make, run) in cases.items():
+        try:
+            t = make()
+            ms = None
+            for _ in range(3):
+                t.reset()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); run(t); e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+            t.check_status()
+            out[name] = {"us_per_frame": 1e3 * ms / frames, "frames": frames, "detections_per_frame": len(v.dets) / frames}
+            del t
+        except Exception as e:
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+    return out
 
 
 def hota_block(r):
