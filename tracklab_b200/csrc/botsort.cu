@@ -281,8 +281,13 @@ __device__ __forceinline__ double bo_dot64(const float* a, const float* b, int E
     for (int e = 0; e < E; ++e) s = __dadd_rn(s, __dmul_rn((double)a[e], (double)b[e]));
     return s;
 }
-__device__ __forceinline__ double bo_cos_dist(const float* tf, double tn, const float* df, double dn, int E) {
-    double c = bo_dot64(tf, df, E) / (tn * dn);
+// one warp per pair: coalesced loads, 32 float64 partial sums combined by a butterfly (scipy's sequential sum and this
+// one differ by ~1 ulp of the dot product; the assignment costs are continuous, no decision hangs on that)
+__device__ __forceinline__ double bo_cos_dist_warp(const float* tf, double tn, const float* df, double dn, int E) {
+    double s = 0.0;
+    for (int e = lane_id(); e < E; e += 32) s += (double)tf[e] * (double)df[e];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    double c = s / (tn * dn);
     if (fabs(c) > 1.0) c = copysign(1.0, c);
     return fmax(0.0, 1.0 - c);
 }
@@ -422,8 +427,9 @@ botsort_video_kernel(BoParams prm, char* state_base, size_t state_stride, int ca
     const int E = prm.emb_dim;
     float* tfeat = tfeat_base + (size_t)seq * cap * E;          // smooth feature of every track slot
     float* dfeat = dfeat_base + (size_t)seq * capd * E;         // normalised features of this frame's detections
-    double* gate = gate_base + (size_t)seq * (cap * 25 + capd);  // per pool position: projected mean, Cholesky factor, feature norm
+    double* gate = gate_base + (size_t)seq * ((size_t)cap * 25 + capd + (size_t)cap * capd);  // per pool position: projected mean, Cholesky factor, feature norm
     double* dnorm = gate + (size_t)cap * 25;                    // |feature| of every detection (float64, for cdist)
+    double* gdm = dnorm + capd;                                 // [npool x nh] squared Mahalanobis distances of the first association
 
     int* status = &S.hdr[4];
     const int F1 = n_frames + 1;
@@ -553,15 +559,23 @@ botsort_video_kernel(BoParams prm, char* state_base, size_t state_stride, int ca
             for (int e = tid; e < npool * nh; e += BO_THREADS) {
                 const int it = e / nh, jd = e % nh;
                 const int di = d_high[jd];
-                // fuse_motion (matching.py:165-176): lambda * cosine distance + (1 - lambda) * squared Mahalanobis distance
-                const double* g = gate + (size_t)it * 25;
+                // fuse_motion (matching.py:165-176), part 1: squared Mahalanobis distance; pairs above chi2inv95[4] are infeasible
                 double z[4];
                 det_xyah(d_box + 4 * di, z);
-                const double gd = bo_gate_dist(g, z);
-                const double emb = bo_cos_dist(tfeat + (size_t)pool[it] * E, g[24], dfeat + (size_t)di * E, dnorm[di], E);
-                const double fused = __dadd_rn(__dmul_rn(prm.lambda_, emb), __dmul_rn(1 - prm.lambda_, gd));
-                const double red = (gd > CHI2INV95_4) ? 0.0 : fmin(fused - prm.match_thresh, 0.0);     // inf entries can never match
-                if (a_rows) cost[(size_t)it * ld + jd] = red; else cost[(size_t)jd * ld + it] = red;
+                gdm[e] = bo_gate_dist(gate + (size_t)it * 25, z);
+            }
+            __syncthreads();
+            for (int e = warp_id(); e < npool * nh; e += BO_THREADS / 32) {      // part 2, one warp per pair: the cosine distance of the feasible pairs only
+                const int it = e / nh, jd = e % nh;
+                const int di = d_high[jd];
+                const double gd = gdm[e];
+                double red = 0.0;                                                 // inf entries can never match
+                if (!(gd > CHI2INV95_4)) {
+                    const double emb = bo_cos_dist_warp(tfeat + (size_t)pool[it] * E, gate[(size_t)it * 25 + 24], dfeat + (size_t)di * E, dnorm[di], E);
+                    const double fused = __dadd_rn(__dmul_rn(prm.lambda_, emb), __dmul_rn(1 - prm.lambda_, gd));
+                    red = fmin(fused - prm.match_thresh, 0.0);
+                }
+                if (lane_id() == 0) { if (a_rows) cost[(size_t)it * ld + jd] = red; else cost[(size_t)jd * ld + it] = red; }
             }
             __syncthreads();
             PH(5);
@@ -646,7 +660,12 @@ botsort_video_kernel(BoParams prm, char* state_base, size_t state_stride, int ca
         {
             const bool a_rows = nunc <= nleft;
             const int ld = lap_pitch(a_rows ? nleft : nunc);
-            for (int e = tid; e < nunc * nleft; e += BO_THREADS) {
+            for (int k = tid; k < nunc; k += BO_THREADS) {
+                const int su = unconf[k];
+                gate[(size_t)k * 25 + 24] = sqrt(bo_dot64(tfeat + (size_t)su * E, tfeat + (size_t)su * E, E));
+            }
+            __syncthreads();
+            for (int e = warp_id(); e < nunc * nleft; e += BO_THREADS / 32) {     // one warp per pair
                 const int it = e / nleft, jd = e % nleft;
                 const int di = d_left[jd];
                 // bot_sort.py:412-422: min(fuse_score(IoU distance), cosine distance / 2 gated by appearance and proximity)
@@ -654,12 +673,14 @@ botsort_video_kernel(BoParams prm, char* state_base, size_t state_stride, int ca
                 const float sim = __fsub_rn(1.0f, dist);
                 const double iou_c = __dsub_rn(1.0, __dmul_rn((double)sim, d_score[di]));
                 const int su = unconf[it];
-                const double tn = sqrt(bo_dot64(tfeat + (size_t)su * E, tfeat + (size_t)su * E, E));
-                double emb = bo_cos_dist(tfeat + (size_t)su * E, tn, dfeat + (size_t)di * E, dnorm[di], E) / 2.0;
-                if (emb > prm.appearance_thresh) emb = 1.0;
-                if (dist > (float)prm.proximity_thresh) emb = 1.0;
+                double emb = 1.0;
+                if (!(dist > (float)prm.proximity_thresh)) {
+                    emb = bo_cos_dist_warp(tfeat + (size_t)su * E, gate[(size_t)it * 25 + 24], dfeat + (size_t)di * E, dnorm[di], E) / 2.0;
+                    if (emb > prm.appearance_thresh) emb = 1.0;
+                }
                 const double fused = fmin(iou_c, emb);
                 const double red = fmin(fused - 0.7, 0.0);
+                if (lane_id() != 0) continue;
                 if (a_rows) cost[(size_t)it * ld + jd] = red; else cost[(size_t)jd * ld + it] = red;
             }
             __syncthreads();
@@ -910,7 +931,7 @@ int tk_botsort_create(const tk_botsort_params* p, int n_seq, int cap_tracks, int
     if (e == cudaSuccess && !h->cost_in_smem) e = cudaMalloc((void**)&h->cost, h->cost_stride * sizeof(double) * n_seq);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->tfeat, sizeof(float) * (size_t)n_seq * cap_tracks * p->feature_dim);
     if (e == cudaSuccess) e = cudaMalloc((void**)&h->dfeat, sizeof(float) * (size_t)n_seq * cap_dets * p->feature_dim);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->gate, sizeof(double) * (size_t)n_seq * ((size_t)cap_tracks * 25 + cap_dets));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->gate, sizeof(double) * (size_t)n_seq * ((size_t)cap_tracks * 25 + cap_dets + (size_t)cap_tracks * cap_dets));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(botsort_video_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes);
     if (e != cudaSuccess) {
