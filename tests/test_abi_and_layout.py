@@ -107,3 +107,17 @@ def test_new_modules_follow_the_reference_column_contracts():
     assert modules.BPBReIDStrongSORT.output_columns == ["track_id", "track_bbox_kf_ltwh", "track_bbox_pred_kf_ltwh", "matched_with", "costs",
                                                         "hits", "age", "time_since_update", "state"]                 # :20-30
     assert modules.RTDetr.input_columns == [] and modules.RTDetr.output_columns == ["image_id", "video_id", "category_id", "bbox_ltwh", "bbox_conf"]
+
+
+def test_jpeg_ingest_library_loads_and_exports_the_declared_symbols():
+    """libtkjpeg.so (include/tkjpeg.h, nvJPEG frame ingest): loads in the build container and exports every declared entry point."""
+    import ctypes
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = sorted(set(re.findall(r"^\s*int\s+(tk_jpeg_[a-z0-9_]+)\s*\(", open(os.path.join(root, "include", "tkjpeg.h")).read(), flags=re.M)))
+    assert len(names) == 6
+    from tracklab_b200 import ingest
+    lib = ingest._load()
+    for n in names:
+        assert hasattr(lib, n), n

@@ -285,8 +285,8 @@ class _StrongSortImpl:
         small = []
         for f0 in range(0, len(paths), self.decode_batch):   # decode once per image (cv2_load_image: BGR -> RGB, utils/cv2.py:54-66)
             f1 = min(len(paths), f0 + self.decode_batch)
-            batch = np.stack([cv2.cvtColor(cv2.imread(p), cv2.COLOR_BGR2RGB) for p in paths[f0:f1]])
-            fr = torch.from_numpy(batch).to(self.device)
+            from .ingest import load_frames
+            fr = load_frames(paths[f0:f1], self.device, str(_cfg_get(self.cfg, "decode", "cv2")))     # JPEG: nvJPEG on the device; else cv2_load_image
             if self.ecc:
                 from . import kernels
                 small.append(kernels.ecc_gray_small(fr, 0.1))
@@ -386,8 +386,8 @@ class _DeepOCSortImpl(_StrongSortImpl):
         small = []
         for f0 in range(0, len(paths), self.decode_batch):
             f1 = min(len(paths), f0 + self.decode_batch)
-            batch = np.stack([cv2.cvtColor(cv2.imread(p), cv2.COLOR_BGR2RGB) for p in paths[f0:f1]])
-            fr = torch.from_numpy(batch).to(self.device)
+            from .ingest import load_frames
+            fr = load_frames(paths[f0:f1], self.device, str(_cfg_get(self.cfg, "decode", "cv2")))     # JPEG: nvJPEG on the device; else cv2_load_image
             if self.ecc:
                 small.append(kernels.ecc_gray_small(fr, 0.1))
             r0, r1 = int(offsets[f0]), int(offsets[f1])
@@ -809,7 +809,8 @@ class RTMLibDetector(ImageLevelModule):
     def process(self, batch, detections: pd.DataFrame, metadatas: pd.DataFrame):
         ids = list(metadatas.index)
         paths = [self._pipe.paths[i] if i in self._pipe.paths else metadatas.loc[i, "file_path"] for i in ids]
-        frames = torch.from_numpy(_decode_rgb(paths)).to(self.device)
+        from .ingest import load_frames
+        frames = load_frames(paths, self.device, getattr(self, "decode", "cv2"))      # JPEG: nvJPEG on the device; else cv2_load_image
         det = self.detector
         if self._needs_calibration:
             det.calibrate(frames, target_per_image=60.0)
@@ -921,7 +922,8 @@ class KPReId(DetectionLevelModule):
             r0, r1 = int(offsets[f0]), int(offsets[f1])
             if r1 == r0:
                 continue
-            fr = torch.from_numpy(_decode_rgb(paths[f0:f1])).to(self.device)
+            from .ingest import load_frames
+            fr = load_frames(paths[f0:f1], self.device, getattr(self, "decode", "cv2"))
             det_frame = torch.from_numpy(np.repeat(np.arange(f1 - f0), counts[f0:f1]).astype(np.int32)).to(self.device)
             feats[r0:r1] = self.reid.features(fr, d_dev[r0:r1], det_frame, ltwh_rows=True)
         emb = feats.cpu().numpy()
