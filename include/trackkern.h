@@ -362,6 +362,16 @@ int tk_part_dist(const float* a, const float* va, const float* b, const float* v
                  int M, int K, int E, void* stream);
 int tk_kf_gate(const double* mean, const double* cov, const double* z, double* out, int n_tracks, int n_dets, int aspect_const,
                int* status_dev, void* stream);
+/* Stateless Kalman steps of SURVEY.md 8b's proposed ABI, one thread per track, in place on mean [n,8] / cov [n,8,8] (float64):
+ * model 0 = ByteTrack xyah (/root/reference/plugins/track/byte_track/kalman_filter.py:88-124 predict, :194-226 update),
+ * model 1 = BoT-SORT xywh (/root/reference/plugins/track/bot_sort/kalman_filter.py:88-124, :194-226); z [n,4] = one measurement per track. */
+int tk_kf_predict(double* mean, double* cov, int n_tracks, int model, void* stream);
+int tk_kf_update(double* mean, double* cov, const double* z, int n_tracks, int model, int* status_dev, void* stream);
+/* OC-SORT velocity-direction-consistency cost (/root/reference/plugins/track/oc_sort/association.py:175-184,246-266): dets [D,6]
+ * (x1,y1,x2,y2,score,cls), prev_obs [T,5] (k_previous_obs, score < 0 = placeholder), velocities [T,2] (dy, dx) -> out [D,T] =
+ * valid * (pi/2 - |acos(clip(v . dir))|) / pi * inertia * dets[:, weight_col] (the reference multiplies with column 5, the class). */
+int tk_vdc_cost(const double* dets6, const double* prev_obs5, const double* velocities2, double* out, int n_dets, int n_tracks, double inertia,
+                int weight_col, void* stream);
 int tk_iou_matrix(const double* a, const double* b, double* out, int n_problems, int N, int M, int variant, void* stream);
 int tk_iou_p1_f32(const float* a_tlbr, const float* b_tlbr, float* dist_out, int n_problems, int N, int M, void* stream);
 int tk_cosine_dist(const float* a, const float* b, double* out, float* norm_scratch, int n_problems, int N, int M, int E,

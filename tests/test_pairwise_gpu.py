@@ -143,3 +143,66 @@ def test_lsap_scipy_batched_reproduces_scipy_including_ties():
             want_x = -np.ones(N, dtype=np.int64); want_x[rows] = cols
             want_y = -np.ones(M, dtype=np.int64); want_y[cols] = rows
             assert np.array_equal(x[b], want_x) and np.array_equal(y[b], want_y), (N, M, b)
+
+
+@pytest.mark.parametrize("model", ["bytetrack", "botsort"])
+def test_stateless_kf_predict_update_match_oracle(model):
+    """tk_kf_predict / tk_kf_update vs the NumPy restatements of the two filters (oracle/kalman_xyah_np.py, oracle/botsort_np.py):
+    predict is sums of two entries with one rounding each (bit-equal); update goes through a 4x4 Cholesky (<= 1e-9 relative)."""
+    import oracle.botsort_np as bo
+    import oracle.kalman_xyah_np as kx
+    from tracklab_b200 import kernels
+    rng = np.random.default_rng(5)
+    n = 37
+    if model == "bytetrack":
+        z0 = np.column_stack([rng.uniform(100, 1800, n), rng.uniform(100, 1000, n), rng.uniform(0.3, 0.6, n), rng.uniform(80, 400, n)])
+        init, predict, update = kx.bt_initiate, kx.bt_multi_predict, kx.bt_update
+    else:
+        z0 = np.column_stack([rng.uniform(100, 1800, n), rng.uniform(100, 1000, n), rng.uniform(40, 200, n), rng.uniform(80, 400, n)])
+        init, predict, update = bo.kf_initiate, bo.kf_multi_predict, bo.kf_update
+    mc = [init(z) for z in z0]
+    mean = np.stack([m for m, _ in mc]).astype(np.float64)
+    cov = np.stack([c for _, c in mc]).astype(np.float64)
+    mean[:, 4:] = rng.normal(0, 2, (n, 4))
+    dm, dc = torch.from_numpy(mean.copy()).cuda(), torch.from_numpy(cov.copy()).cuda()
+    for step in range(3):
+        mean, cov = predict(mean, cov)
+        kernels.kf_predict(dm, dc, model)
+        assert np.array_equal(dm.cpu().numpy(), mean) and np.array_equal(dc.cpu().numpy(), cov)
+        z = mean[:, :4] + rng.normal(0, 1.0, (n, 4)) * np.array([3.0, 3.0, 0.01 if model == "bytetrack" else 2.0, 3.0])
+        upd = [update(mean[i], cov[i], z[i]) for i in range(n)]
+        mean, cov = np.stack([u[0] for u in upd]), np.stack([u[1] for u in upd])
+        _, _, st = kernels.kf_update(dm, dc, torch.from_numpy(z).cuda(), model)
+        assert int(st.item()) == 0
+        assert np.allclose(dm.cpu().numpy(), mean, rtol=1e-9, atol=1e-9) and np.allclose(dc.cpu().numpy(), cov, rtol=1e-9, atol=1e-9)
+        dm.copy_(torch.from_numpy(mean)); dc.copy_(torch.from_numpy(cov))       # keep both sides on the same trajectory
+
+
+def test_vdc_cost_matches_reference_formula():
+    """tk_vdc_cost vs the angle term of oc_sort/association.py:246-266 as restated inside oracle/ocsort_np.associate."""
+    from tracklab_b200 import kernels
+    rng = np.random.default_rng(9)
+    D, T = 23, 31
+    dets = np.column_stack([rng.uniform(0, 1800, (D, 2)), rng.uniform(0, 1, D), rng.uniform(0, 3, D)])
+    dets = np.column_stack([dets[:, 0], dets[:, 1], dets[:, 0] + rng.uniform(30, 200, D), dets[:, 1] + rng.uniform(60, 400, D), dets[:, 2], dets[:, 3]])
+    prev = np.column_stack([rng.uniform(0, 1800, (T, 2)), np.zeros((T, 2)), rng.uniform(0.2, 1, T)])
+    prev[:, 2] = prev[:, 0] + 80; prev[:, 3] = prev[:, 1] + 200
+    prev[::5] = -1.0                                                   # placeholder observations
+    vel = rng.normal(0, 1, (T, 2)); vel /= np.linalg.norm(vel, axis=1, keepdims=True)
+    inertia = 0.3941737016672115
+    pt = prev[..., np.newaxis]
+    cx1, cy1 = (dets[:, 0] + dets[:, 2]) / 2.0, (dets[:, 1] + dets[:, 3]) / 2.0
+    cx2, cy2 = (pt[:, 0] + pt[:, 2]) / 2.0, (pt[:, 1] + pt[:, 3]) / 2.0
+    dx, dy = cx1 - cx2, cy1 - cy2
+    norm = np.sqrt(dx ** 2 + dy ** 2) + 1e-6
+    X, Y = dx / norm, dy / norm
+    iy = np.repeat(vel[:, 0][:, np.newaxis], Y.shape[1], axis=1)
+    ix = np.repeat(vel[:, 1][:, np.newaxis], X.shape[1], axis=1)
+    ang = np.arccos(np.clip(ix * X + iy * Y, a_min=-1, a_max=1))
+    ang = (np.pi / 2.0 - np.abs(ang)) / np.pi
+    valid = np.ones(T); valid[np.where(prev[:, 4] < 0)] = 0
+    valid = np.repeat(valid[:, np.newaxis], X.shape[1], axis=1)
+    scores = np.repeat(dets[:, -1][:, np.newaxis], T, axis=1)
+    ref = ((valid * ang) * inertia).T * scores
+    out = kernels.vdc_cost(torch.from_numpy(dets).cuda(), torch.from_numpy(prev).cuda(), torch.from_numpy(vel).cuda(), inertia, 5).cpu().numpy()
+    assert np.abs(out - ref).max() < 1e-12

@@ -90,6 +90,9 @@ def _declare(lib):
         "tk_rtdetr_decode": ([vp, vp, ci, ci, ci, ci, ci, ctypes.c_float, ci, vp, vp, vp], ci),
         "tk_maxpool3x3s2_nhwc": ([vp, ci, ci, ci, ci, vp, vp], ci),
         "tk_avgpool_nhwc": ([vp, ci, ci, ci, vp, vp], ci),
+        "tk_kf_predict": ([vp, vp, ci, ci, vp], ci),
+        "tk_kf_update": ([vp, vp, vp, ci, ci, vp, vp], ci),
+        "tk_vdc_cost": ([vp, vp, vp, vp, ci, ci, cd, ci, vp], ci),
         "tk_iou_matrix": ([vp, vp, vp, ci, ci, ci, ci, vp], ci),
         "tk_iou_p1_f32": ([vp, vp, vp, ci, ci, ci, vp], ci),
         "tk_cosine_dist": ([vp, vp, vp, vp, ci, ci, ci, ci, vp], ci),

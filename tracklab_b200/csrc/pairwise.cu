@@ -313,6 +313,74 @@ kf_gate_kernel(const double* __restrict__ mean, const double* __restrict__ cov, 
     for (int d = threadIdx.x; d < D; d += blockDim.x) out[(size_t)t * D + d] = tk::kf8_maha(c, c + 4, c + 20, z + (size_t)d * 4);
 }
 
+// Stateless Kalman steps (tk_kf_predict / tk_kf_update): one thread per track, float64, the arithmetic of kf_xyah.cuh.
+// model 0 = ByteTrack xyah (byte_track/kalman_filter.py:88-124,194-226: std from h, aspect std 1e-2 / 1e-5, R aspect 1e-1),
+// model 1 = BoT-SORT xywh (bot_sort/kalman_filter.py:88-124,194-226: std from (w, h)).
+__device__ __forceinline__ void kf_noise(int model, const double* m, double* q, double* r) {
+    const double wp = 1.0 / 20, wv = 1.0 / 160;
+    if (model == 0) {
+        const double h = m[3];
+        const double sp = wp * h, sv = wv * h;
+        const double qq[8] = {sp * sp, sp * sp, 1e-2 * 1e-2, sp * sp, sv * sv, sv * sv, 1e-5 * 1e-5, sv * sv};
+        for (int i = 0; i < 8; ++i) q[i] = qq[i];
+        r[0] = sp * sp; r[1] = sp * sp; r[2] = 1e-1 * 1e-1; r[3] = sp * sp;
+    } else {
+        const double sw = wp * m[2], sh = wp * m[3], vw = wv * m[2], vh = wv * m[3];
+        const double qq[8] = {sw * sw, sh * sh, sw * sw, sh * sh, vw * vw, vh * vh, vw * vw, vh * vh};
+        for (int i = 0; i < 8; ++i) q[i] = qq[i];
+        r[0] = sw * sw; r[1] = sh * sh; r[2] = sw * sw; r[3] = sh * sh;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+kf_predict_kernel(double* __restrict__ mean, double* __restrict__ cov, int n, int model) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double m[8], P[64], q[8], r[4];
+    for (int i = 0; i < 8; ++i) m[i] = mean[(size_t)t * 8 + i];
+    for (int i = 0; i < 64; ++i) P[i] = cov[(size_t)t * 64 + i];
+    kf_noise(model, m, q, r);
+    tk::kf8_predict(m, P, q);
+    for (int i = 0; i < 8; ++i) mean[(size_t)t * 8 + i] = m[i];
+    for (int i = 0; i < 64; ++i) cov[(size_t)t * 64 + i] = P[i];
+}
+
+__global__ void __launch_bounds__(128)
+kf_update_kernel(double* __restrict__ mean, double* __restrict__ cov, const double* __restrict__ z, int n, int model, int* __restrict__ status) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double m[8], P[64], q[8], r[4];
+    for (int i = 0; i < 8; ++i) m[i] = mean[(size_t)t * 8 + i];
+    for (int i = 0; i < 64; ++i) P[i] = cov[(size_t)t * 64 + i];
+    kf_noise(model, m, q, r);
+    if (!tk::kf8_update(m, P, z + (size_t)t * 4, r)) atomicOr(status, TK_DEV_BAD_CHOLESKY);
+    for (int i = 0; i < 8; ++i) mean[(size_t)t * 8 + i] = m[i];
+    for (int i = 0; i < 64; ++i) cov[(size_t)t * 64 + i] = P[i];
+}
+
+// OC-SORT velocity-direction-consistency cost (oc_sort/association.py:175-184,246-266): out[d, t] = valid_t * (pi/2 - |acos(clip(
+// v_t . dir(prev_t -> det_d)))|) / pi * inertia * weight_d, weight = the column the reference multiplies with (the class column, q1).
+__global__ void __launch_bounds__(256)
+vdc_cost_kernel(const double* __restrict__ dets, const double* __restrict__ prev, const double* __restrict__ vel, double* __restrict__ out,
+                int D, int T, double inertia, int weight_col) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= D * T) return;
+    const int d = e / T, t = e - d * T;
+    const double* db = dets + (size_t)d * 6;
+    const double* pv = prev + (size_t)t * 5;
+    const double cx1 = (db[0] + db[2]) / 2.0, cy1 = (db[1] + db[3]) / 2.0;
+    const double cx2 = (pv[0] + pv[2]) / 2.0, cy2 = (pv[1] + pv[3]) / 2.0;
+    const double dx = cx1 - cx2, dy = cy1 - cy2;
+    const double norm = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) + 1e-6;
+    const double X = dx / norm, Y = dy / norm;
+    double c = __dadd_rn(__dmul_rn(vel[(size_t)t * 2 + 1], X), __dmul_rn(vel[(size_t)t * 2], Y));
+    c = fmin(fmax(c, -1.0), 1.0);
+    const double pi = 3.141592653589793;
+    const double ang = (pi / 2.0 - fabs(acos(c))) / pi;
+    const double valid = pv[4] < 0 ? 0.0 : 1.0;
+    out[e] = __dmul_rn(__dmul_rn(__dmul_rn(valid, ang), inertia), db[weight_col]);
+}
+
 // scipy.optimize.linear_sum_assignment, one warp per problem, cost read from global memory (stateless form of lsap_scipy.cuh)
 __global__ void __launch_bounds__(32)
 lsap_scipy_batched_kernel(const double* __restrict__ cost, int N, int M, int* __restrict__ x_out, int* __restrict__ y_out,
@@ -448,6 +516,32 @@ int tk_kf_gate(const double* mean, const double* cov, const double* z, double* o
     if (!mean || !cov || !z || !out || !status_dev || n_tracks < 0 || n_dets < 0) return TK_ERR_ARG;
     if (n_tracks == 0 || n_dets == 0) return TK_OK;
     kf_gate_kernel<<<n_tracks, 128, 0, (cudaStream_t)stream>>>(mean, cov, z, out, n_tracks, n_dets, aspect_const, status_dev);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_kf_predict(double* mean, double* cov, int n_tracks, int model, void* stream) {
+    if (!mean || !cov || n_tracks < 0 || model < 0 || model > 1) return TK_ERR_ARG;
+    if (n_tracks == 0) return TK_OK;
+    kf_predict_kernel<<<(n_tracks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, cov, n_tracks, model);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_kf_update(double* mean, double* cov, const double* z, int n_tracks, int model, int* status_dev, void* stream) {
+    if (!mean || !cov || !z || !status_dev || n_tracks < 0 || model < 0 || model > 1) return TK_ERR_ARG;
+    if (n_tracks == 0) return TK_OK;
+    kf_update_kernel<<<(n_tracks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, cov, z, n_tracks, model, status_dev);
+    TK_CUDA_TRY(cudaGetLastError());
+    return TK_OK;
+}
+
+int tk_vdc_cost(const double* dets6, const double* prev_obs5, const double* velocities2, double* out, int n_dets, int n_tracks, double inertia,
+                int weight_col, void* stream) {
+    if (!dets6 || !prev_obs5 || !velocities2 || !out || n_dets < 0 || n_tracks < 0 || weight_col < 0 || weight_col > 5) return TK_ERR_ARG;
+    if (n_dets == 0 || n_tracks == 0) return TK_OK;
+    const int n = n_dets * n_tracks;
+    vdc_cost_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dets6, prev_obs5, velocities2, out, n_dets, n_tracks, inertia, weight_col);
     TK_CUDA_TRY(cudaGetLastError());
     return TK_OK;
 }

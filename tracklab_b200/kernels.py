@@ -365,6 +365,39 @@ def part_dist(a: torch.Tensor, va: torch.Tensor, b: torch.Tensor, vb: torch.Tens
     return out
 
 
+def kf_predict(mean: torch.Tensor, cov: torch.Tensor, model: str = "bytetrack"):
+    """In-place Kalman predict of n tracks (mean float64 [n,8], cov [n,8,8]); model "bytetrack" (xyah) or "botsort" (xywh). C ABI: tk_kf_predict."""
+    lib = _lib.load()
+    _cuda(mean, "mean"); _cuda(cov, "cov")
+    with torch.cuda.device(mean.device):
+        _lib.check(lib.tk_kf_predict(mean.data_ptr(), cov.data_ptr(), mean.shape[0], {"bytetrack": 0, "botsort": 1}[model], _stream()), "tk_kf_predict"); _count()
+    return mean, cov
+
+
+def kf_update(mean: torch.Tensor, cov: torch.Tensor, z: torch.Tensor, model: str = "bytetrack", status: torch.Tensor | None = None):
+    """In-place Kalman measurement update with one measurement z [n,4] per track. C ABI: tk_kf_update."""
+    lib = _lib.load()
+    _cuda(mean, "mean"); _cuda(cov, "cov"); _cuda(z, "z")
+    if status is None:
+        status = torch.zeros((1,), dtype=torch.int32, device=mean.device)
+    with torch.cuda.device(mean.device):
+        _lib.check(lib.tk_kf_update(mean.data_ptr(), cov.data_ptr(), z.data_ptr(), mean.shape[0], {"bytetrack": 0, "botsort": 1}[model],
+                                    status.data_ptr(), _stream()), "tk_kf_update"); _count()
+    return mean, cov, status
+
+
+def vdc_cost(dets6: torch.Tensor, prev_obs5: torch.Tensor, velocities2: torch.Tensor, inertia: float, weight_col: int = 5) -> torch.Tensor:
+    """OC-SORT velocity-direction-consistency cost [D,T] (C ABI: tk_vdc_cost)."""
+    lib = _lib.load()
+    _cuda(dets6, "dets"); _cuda(prev_obs5, "prev_obs"); _cuda(velocities2, "velocities")
+    D, T = dets6.shape[0], prev_obs5.shape[0]
+    out = torch.empty((D, T), dtype=torch.float64, device=dets6.device)
+    with torch.cuda.device(dets6.device):
+        _lib.check(lib.tk_vdc_cost(dets6.data_ptr(), prev_obs5.data_ptr(), velocities2.data_ptr(), out.data_ptr(), D, T, float(inertia),
+                                   int(weight_col), _stream()), "tk_vdc_cost"); _count()
+    return out
+
+
 def kf_gate(mean: torch.Tensor, cov: torch.Tensor, z: torch.Tensor, aspect_const: bool = True, status: torch.Tensor | None = None):
     """Squared Mahalanobis gating distances: mean [T,8], cov [T,8,8], z [D,4] float64 -> [T,D] (C ABI: tk_kf_gate)."""
     lib = _lib.load()
