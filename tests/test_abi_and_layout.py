@@ -121,3 +121,38 @@ def test_jpeg_ingest_library_loads_and_exports_the_declared_symbols():
     lib = ingest._load()
     for n in names:
         assert hasattr(lib, n), n
+
+
+def test_skipped_frame_affines_are_folded_into_the_next_processed_frame():
+    """modules.compose_skipped_affines: the plugins' camera-motion estimators are only called on frames the wrapper processes and relate
+    each call to the previous call (deep_oc_sort/cmc.py:138-166, bot_sort/gmc.py:239-303), so pair-wise device transforms of skipped
+    frames are composed; the first processed frame gets the identity; failed pairs (NaN) count as identity."""
+    import numpy as np
+    from tracklab_b200.modules import compose_skipped_affines
+    def T(tx, ty, th=0.0):
+        return np.array([[np.cos(th), -np.sin(th), tx], [np.sin(th), np.cos(th), ty]])
+    w = np.full((6, 2, 3), np.nan)
+    w[1], w[2], w[3], w[5] = T(2, 0), T(3, 1, 0.01), T(1, 0), T(5, 5)            # w[4] failed
+    out = compose_skipped_affines(w, np.array([True, True, False, True, True, True]))
+    assert np.array_equal(out[0], np.eye(2, 3)) and np.array_equal(out[1], T(2, 0)) and np.array_equal(out[2], np.eye(2, 3))
+    H = lambda a: np.vstack([a, [0, 0, 1]])
+    assert np.allclose(out[3], (H(T(1, 0)) @ H(T(3, 1, 0.01)))[:2])             # frame 2 was skipped: 1->2 then 2->3
+    assert np.array_equal(out[4], np.eye(2, 3)) and np.array_equal(out[5], T(5, 5))
+    out = compose_skipped_affines(w, np.array([False, False, True, True, True, True]))   # the first PROCESSED frame gets the identity
+    assert np.array_equal(out[2], np.eye(2, 3)) and np.array_equal(out[3], T(1, 0))
+
+
+def test_partial_hyperparams_are_completed_with_the_reference_constructor_defaults():
+    """A hyperparams dict that omits keys must run what the reference would run (plugin constructor defaults), not the tuned YAML values
+    the device classes default to; OC-SORT's det_thresh has no default in the reference."""
+    import pytest
+    from tracklab_b200 import _lib
+    from tracklab_b200.modules import _with_reference_defaults
+    h = _with_reference_defaults("ByteTrack", {"track_buffer": 60})
+    assert h == dict(track_thresh=0.45, track_buffer=60, match_thresh=0.8, frame_rate=30)          # byte_tracker.py:152
+    h = _with_reference_defaults("OCSORT", {"det_thresh": 0.1, "asso_func": "giou"})
+    assert h["max_age"] == 30 and h["min_hits"] == 3 and h["delta_t"] == 3 and h["asso_func"] == "giou"   # ocsort.py:183-184
+    with pytest.raises(_lib.TrackKernError):
+        _with_reference_defaults("OCSORT", {"max_age": 5})
+    assert _with_reference_defaults("StrongSORT", {})["max_unmatched_preds"] == 7                   # strong_sort.py:20-31 (rejected loudly by the module)
+    assert _with_reference_defaults("DeepOCSORT", {"a": 1}) == {"a": 1}

@@ -106,3 +106,26 @@ def test_botsort_module_through_engine_equals_oracle_chain(tmp_path):
     for r in want:
         ref_ids[pos[int(r[7])]] = r[4]
     assert np.array_equal(np.isnan(got_ids), np.isnan(ref_ids)) and np.array_equal(got_ids[has], ref_ids[has])
+
+
+def test_botsort_empty_and_all_filtered_frames():
+    """Frames without detections are skipped by the wrapper; frames whose detections are all below min_confidence still run update()
+    (predict + GMC + lost marking) - vs the oracle, with identity warps (cmc_method 'none')."""
+    import dataclasses
+    from oracle.botsort_np import BotSortOracle
+    from tracklab_b200.synth import make_video
+    v = make_video(seed=61, n_frames=40, n_ids=10, emb_dim=16)
+    offs, dets, e = v.offsets.copy(), v.dets.copy(), np.ascontiguousarray(v.embeddings.astype(np.float32))
+    keep = np.ones(len(dets), dtype=bool)
+    keep[offs[5]:offs[8]] = False
+    dets[offs[12]:offs[14], 4] = 0.05
+    new_off = np.concatenate([[0], np.cumsum([keep[offs[f]:offs[f + 1]].sum() for f in range(v.n_frames)])]).astype(np.int32)
+    v2 = dataclasses.replace(v, dets=dets[keep].copy(), offsets=new_off, embeddings=e[keep].copy(), gt_identity=v.gt_identity[keep].copy())
+    hyper = dict(track_high_thresh=0.45, new_track_thresh=0.5, track_buffer=6, match_thresh=0.8, lambda_=0.97)
+    warps = np.tile(np.eye(2, 3), (v.n_frames, 1, 1))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_rows, ref_frames = BotSortOracle(**hyper, min_confidence=0.4).run_video(v2.dets, v2.offsets, e[keep].copy(), warps)
+    (rows, frames), = _run_device(v2, np.ascontiguousarray(e[keep]), warps, hyper, 0.4)
+    assert_rows_match(rows, frames, ref_rows, ref_frames, box_tol=1e-6)
+    assert not np.isin(frames, [5, 6, 7]).any()
