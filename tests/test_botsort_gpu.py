@@ -69,7 +69,7 @@ def test_botsort_module_through_engine_equals_oracle_chain(tmp_path):
     from tests.golden.make_botsort_golden import YAML
     from tests.test_engine_modules_gpu import _tracking_frames
     from tracklab_b200 import kernels, modules
-    from tracklab_b200.engine_mirror import OfflineEngineMirror
+    from tests.engine_mirror import OfflineEngineMirror
     from tracklab_b200.synth import make_frames, make_video
     F = 14
     video = make_video(seed=3200, n_frames=F, n_ids=16)

@@ -34,7 +34,7 @@ def _tracking_frames(videos):
 @pytest.mark.parametrize("name,frames_per_batch", [("bytetrack_2videos", None), ("bytetrack_2videos", 7), ("ocsort_c1", None)])
 def test_modules_through_engine_match_reference_engine(name, frames_per_batch):
     from tracklab_b200 import modules
-    from tracklab_b200.engine_mirror import OfflineEngineMirror
+    from tests.engine_mirror import OfflineEngineMirror
     g = np.load(os.path.join(HERE, "golden", f"engine_{name}.npz"))
     gens, hyper, kind = ast.literal_eval(str(g["gens"])), ast.literal_eval(str(g["hyper"])), str(g["kind"])
     videos = [make_video(**k) for k in gens]
@@ -59,7 +59,7 @@ def test_bpbreid_module_through_engine_matches_reference_plugin():
     unmodified reference plugin: same detection -> track partition, stages, hits and ages; float64 boxes within 1e-6."""
     from tests.util import load_bpbreid_golden
     from tracklab_b200 import modules
-    from tracklab_b200.engine_mirror import OfflineEngineMirror
+    from tests.engine_mirror import OfflineEngineMirror
     g = load_bpbreid_golden("bpbreid_yaml_s6000")
     video = make_video(**g["gen"])
     vmd, imd, det = _tracking_frames([video])
@@ -90,7 +90,7 @@ def test_bpbreid_module_matches_the_real_engine_golden():
     """tests/golden/engine_bpbreid.npz was produced by the REAL OfflineTrackingEngine + the reference BPBReIDStrongSORT wrapper
     (make_engine_bpbreid_golden.py); the drop-in through the mirrored engine protocol must give the same per-detection columns."""
     from tracklab_b200 import modules
-    from tracklab_b200.engine_mirror import OfflineEngineMirror
+    from tests.engine_mirror import OfflineEngineMirror
     g = np.load(os.path.join(HERE, "golden", "engine_bpbreid.npz"))
     video = make_video(**ast.literal_eval(str(g["gen"])))
     cfgd = ast.literal_eval(str(g["cfg"]))
