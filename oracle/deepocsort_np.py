@@ -12,8 +12,9 @@ Behaviour of the reference that decides ids and is therefore kept operation by o
   q1  `linear_assignment` lists `[y[i], i] for i in x` WITHOUT dropping unassigned rows (association.py:207): every detection the
       solver left unassigned contributes the pair `[y[-1], -1]`, i.e. (detection of the LAST tracker, tracker -1). NumPy's negative
       indexing then re-validates that pair against the IoU threshold, so the last tracker is updated once more per unassigned
-      detection (KF update, hit counters, embedding EMA), or - when the last tracker has no detection - the pair (-1, -1) = (last
-      detection, last tracker) is tested and, below the threshold, `-1` enters the unmatched lists.
+      detection (KF update, hit counters, embedding EMA); when that re-validation fails, `-1` enters the unmatched lists. (Rows stay
+      unassigned only when detections outnumber trackers, and then every tracker - the last one included - holds a detection in the
+      optimum of the extension, so `y[-1]` itself is never -1; the code below would handle it like NumPy does anyway.)
   q2  `last_observation` and `observations[age]` are the same array object, and both are row views of that frame's detection array:
       `apply_affine_correction` (ocsort.py:252-268) therefore warps the most recent observation TWICE whenever it is at most
       `delta_t` frames old.
