@@ -8,7 +8,8 @@
 // (new_kf_off = false). The in-tracker ReID forward and the camera-motion estimator are separate stages here: the kernel takes the
 // per-detection embeddings (float32) and one 2x3 affine per frame, what `_get_features` / `CMCComputer.compute_affine` return.
 //
-// Same execution shape as ocsort.cu: one launch walks the frames of a video, state resident in L2, the assignment on lap.cuh.
+// Same execution shape as ocsort.cu: one launch walks the frames of a video, state resident in L2, per-frame scratch in shared memory;
+// the assignment is scipy's solver on lap's published extension (lsap_scipy.cuh, see doc_solve).
 // The behaviour of the reference that decides ids is kept operation by operation (oracle/deepocsort_np.py q1..q6):
 //   q1  linear_assignment keeps `[y[i], i] for i in x` for unassigned rows too -> pairs (detection of the last tracker, -1); NumPy's
 //       negative indices re-validate them, so the last tracker is updated once more per unassigned detection. Indices are kept RAW
@@ -20,7 +21,7 @@
 //       comes from the state before the replay.
 //   q5  first round: plain IoU, VDC term multiplied by the class column.
 //   q6  embedding EMA, appearance matrix and adaptive weights in float32; everything else float64.
-#include "lap.cuh"
+#include "lap.cuh"          // LAP_MAX_COLS
 #include "lsap_scipy.cuh"
 #include "oc_boxes.cuh"
 #include "tk_common.cuh"
