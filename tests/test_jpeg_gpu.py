@@ -25,7 +25,7 @@ def _write_jpegs(tmp_path, n, sampling):
 def test_nvjpeg_batch_decode_vs_libjpeg_turbo(tmp_path):
     import cv2
     from tracklab_b200.ingest import load_frames
-    for sampling, mean_tol, p999_tol in ((cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, 0.6, 4), (cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, 2.5, 80)):
+    for sampling, mean_tol, p999_tol in ((cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, 0.8, 6), (cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, 2.5, 80)):
         video, paths = _write_jpegs(tmp_path, 8, sampling)
         load_frames(paths, "cuda:0", "nvjpeg")
         t0 = time.perf_counter(); dev_frames = load_frames(paths, "cuda:0", "nvjpeg"); torch.cuda.synchronize(); t_nv = time.perf_counter() - t0
