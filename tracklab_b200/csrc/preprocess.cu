@@ -330,8 +330,8 @@ extern "C" int tk_letterbox_u8(const unsigned char* src, int n_frames, int H, in
 // One CTA per (output row, crop): the vertical taps are shared by the row, each thread owns one output column.
 namespace {
 
-constexpr int CR_ROWS = 8;    // output rows per CTA of the crop / frame resize kernels
-constexpr int CR_HROWS = 40;  // source rows resampled horizontally into shared memory per CTA (separable crop path)
+constexpr int CR_ROWS = 16;   // output rows per CTA of the crop / frame resize kernels
+constexpr int CR_HROWS = 48; // source rows resampled horizontally into shared memory per CTA (separable crop path)
 constexpr int CR_HCOLS = 128; // output columns of the separable crop path
 constexpr int CR_KMAX = 64;   // taps per axis: 2*ceil(scale)+1 -> crops up to ~31x the output size (a full 4K row into 128 px)
 
